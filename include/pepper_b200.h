@@ -1,0 +1,243 @@
+/*
+ * pepper_b200.h — C-ABI of libpepper_b200.so (sm_100a).
+ *
+ * Drop-in boundary for PEPPER's pileup-summary encoders and recurrent-network
+ * inference.  Every entry point replaces one Python-visible
+ * pybind class/method or predict function of the reference; the reference
+ * interface it replaces is cited as file:line (relative to the reference repo).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch / STL types;
+ *   - "d_" pointers are DEVICE pointers, "h_" pointers are HOST pointers;
+ *   - every function returns 0 on success, <0 on error (pb_last_error() gives
+ *     the message); nothing ever calls exit() (the reference does:
+ *     region_summary.cpp:151, bam_handler.cpp:9-26);
+ *   - caller owns every buffer; opaque handles own only library scratch;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with PB_ERR_CUDA.
+ *
+ * Read records ("post-get_reads" reads, i.e. what BAM_handler::get_reads
+ * returns: pepper_variant/modules/cpp/bam_handler.cpp:115-451, struct
+ * type_read pepper_variant/modules/cpp/read.h:60) are passed as a
+ * structure-of-arrays in BAM-native packing:
+ *   seq   4-bit codes "=ACMGRSVTWYHKDBN", two bases per byte, high nibble
+ *         first; base i of read r is nibble (seq_off[r] + i)
+ *   qual  one byte per base at qual[seq_off[r] + i]
+ *   cigar uint32 (len << 4 | op), op in {0 M,1 I,2 D,3 N,4 S,5 H,6 P,7 =,8 X}
+ */
+#ifndef PEPPER_B200_H
+#define PEPPER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK             0
+#define PB_ERR_ARG       -1
+#define PB_ERR_CUDA      -2
+#define PB_ERR_CAPACITY  -3   /* output capacity too small; *n_out holds the need */
+#define PB_ERR_STATE     -4
+
+#define PB_VARIANT_WINDOW   33   /* CANDIDATE_WINDOW_SIZE + 1, Options.py:9   */
+#define PB_VARIANT_FEATURES 26   /* IMAGE_HEIGHT, Options.py:7                */
+#define PB_ALLELE_STRIDE    64   /* key "1T" / "2ACG.." / "3ACG.." <=61 + NUL */
+#define PB_POLISH_FEATURES  10   /* summary_generator.cpp:16-32               */
+#define PB_POLISH_SEQ_LEN   1000 /* pepper Options.py SEQ_LENGTH              */
+#define PB_POLISH_CLASSES   5
+
+/* SoA read batch (host or device pointers depending on the entry point). */
+typedef struct {
+    int64_t         n_reads;
+    const int64_t  *pos;        /* [n_reads]   0-based reference position of the first cigar op */
+    const int64_t  *seq_off;    /* [n_reads+1] base (nibble) offset of each read in seq / byte offset in qual */
+    const int64_t  *cigar_off;  /* [n_reads+1] */
+    const uint8_t  *flags;      /* [n_reads]   bit0 = is_reverse (type_read_flags, read.h:13) */
+    const uint8_t  *mapq;       /* [n_reads]   mapping_quality (read.h:69) */
+    const uint8_t  *seq;        /* [(seq_off[n]+1)/2] */
+    const uint8_t  *qual;       /* [seq_off[n]] */
+    const uint32_t *cigar;      /* [cigar_off[n]] */
+} pb_reads_t;
+
+/* One encoder region == one RegionalSummaryGenerator / SummaryGenerator object. */
+typedef struct {
+    int64_t ref_start;      /* ctor region_start (inclusive)                     */
+    int64_t ref_end;        /* ctor region_end   (inclusive)                     */
+    int64_t cand_start;     /* generate_summary candidate_region_start (variant) */
+    int64_t cand_end;       /* generate_summary candidate_region_end   (variant) */
+    int64_t ref_off;        /* offset of this region's reference string in `ref` */
+    int64_t ref_len;        /* its length (normally ref_end-ref_start+1)         */
+    int64_t read_begin;     /* reads [read_begin, read_end) belong to the region */
+    int64_t read_end;
+} pb_region_t;
+
+/* generate_summary arguments, region_summary.h:191-206 (same order). */
+typedef struct {
+    double  min_snp_baseq;
+    double  min_indel_baseq;
+    double  snp_freq_threshold;
+    double  insert_freq_threshold;
+    double  delete_freq_threshold;
+    double  min_coverage_threshold;
+    double  snp_candidate_freq_threshold;
+    double  indel_candidate_freq_threshold;
+    double  candidate_support_threshold;
+    int32_t skip_indels;
+    int32_t reserved;
+} pb_variant_params_t;
+
+const char *pb_last_error(void);
+int  pb_version(void);
+/* number of CUDA devices visible (0 on a CPU box); never fails */
+int  pb_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * Variant encoder.  Replaces
+ *   RegionalSummaryGenerator(contig, region_start, region_end, ref_seq)
+ *     .generate_max_insert_summary(reads)
+ *     .generate_summary(reads, ...16 args...) -> list[CandidateImageSummary]
+ * (pepper_variant/modules/cpp/pybind_api.h:55-62, region_summary.cpp:568)
+ * for a BATCH of regions in one call.
+ * ---------------------------------------------------------------------- */
+typedef struct pb_variant_encoder pb_variant_encoder_t;
+
+int pb_variant_encoder_create(pb_variant_encoder_t **out, int device);
+int pb_variant_encoder_destroy(pb_variant_encoder_t *enc);
+
+/* Host-buffer entry point (the one the PEPPER_VARIANT mirror classes call):
+ * copies reads/ref to the device, encodes, copies the candidates back.
+ * Outputs are ordered by region, then position, then allele key (std::set
+ * order, region_summary.cpp:669-670).
+ *   h_images     int8  [cap][33][26]   (DataStore.py:68 stores int8)
+ *   h_positions  int64 [cap]
+ *   h_depths     uint8 [cap]           min(coverage,125)  region_summary.cpp:682
+ *   h_freqs      uint8 [cap]           min(allele_depth,125)          :862
+ *   h_keys       char  [cap][64]       NUL-terminated allele key
+ *   h_region_of  int32 [cap]
+ *   h_n_per_region int64 [n_regions]   (may be NULL)
+ *   n_out        total number of candidates (also set on PB_ERR_CAPACITY)   */
+int pb_variant_encode_host(pb_variant_encoder_t *enc,
+                           const pb_reads_t *h_reads,
+                           const pb_region_t *h_regions, int64_t n_regions,
+                           const char *h_ref, int64_t ref_bytes,
+                           const pb_variant_params_t *params,
+                           int64_t capacity,
+                           int8_t *h_images, int64_t *h_positions,
+                           uint8_t *h_depths, uint8_t *h_freqs,
+                           char *h_keys, int32_t *h_region_of,
+                           int64_t *h_n_per_region, int64_t *n_out,
+                           void *stream);
+
+/* Device-resident entry point: reads/regions/ref already in HBM, outputs stay
+ * in HBM (feeds pb_variant_net_forward without a host round trip).           */
+int pb_variant_encode_device(pb_variant_encoder_t *enc,
+                             const pb_reads_t *d_reads,       /* struct on host, pointers on device */
+                             const pb_region_t *d_regions, int64_t n_regions,
+                             const pb_region_t *h_regions,    /* host copy of the same table */
+                             const char *d_ref, int64_t ref_bytes,
+                             const pb_variant_params_t *params,
+                             int64_t capacity,
+                             int8_t *d_images, int64_t *d_positions,
+                             uint8_t *d_depths, uint8_t *d_freqs,
+                             char *d_keys, int32_t *d_region_of,
+                             int64_t *d_n_per_region, int64_t *n_out,
+                             void *stream);
+
+/* Debug/parity read-back of the intermediate of the LAST encode call:
+ * the [L+1][26] count matrix after the clamp of region_summary.cpp:648-653
+ * (int32, col 0 = reference code) and the coverage/snp/insert/delete vectors
+ * (region_summary.cpp:586-589) of region `region`.                          */
+int pb_variant_encoder_debug_region(pb_variant_encoder_t *enc, int64_t region,
+                                    int32_t *h_matrix, int32_t *h_coverage,
+                                    int32_t *h_snp, int32_t *h_ins, int32_t *h_del);
+
+/* per-kernel device time (ms) of the last encode call, measured with CUDA
+ * events on the call's stream: [prefix, count, sites, alleles, windows]      */
+int pb_variant_encoder_timings(pb_variant_encoder_t *enc, float *ms5);
+
+/* ------------------------------------------------------------------------
+ * Polish encoder.  Replaces
+ *   SummaryGenerator(ref_seq, chrom, ref_start, ref_end)
+ *     .generate_summary(reads, start, end);  .image  .genomic_pos
+ * (pepper/modules/headers/pybind_api.h:18-25, summary_generator.cpp:370)
+ * for a batch of regions.
+ *   h_image   uint8 [cap_cols][10]
+ *   h_pos     int64 [cap_cols]     genomic_pos.first
+ *   h_idx     int32 [cap_cols]     genomic_pos.second
+ *   h_col_off int64 [n_regions+1]  columns of region r are [off[r], off[r+1])
+ * ---------------------------------------------------------------------- */
+typedef struct pb_polish_encoder pb_polish_encoder_t;
+int pb_polish_encoder_create(pb_polish_encoder_t **out, int device);
+int pb_polish_encoder_destroy(pb_polish_encoder_t *enc);
+int pb_polish_encode_host(pb_polish_encoder_t *enc,
+                          const pb_reads_t *h_reads,
+                          const pb_region_t *h_regions, int64_t n_regions,
+                          int64_t capacity_cols,
+                          uint8_t *h_image, int64_t *h_pos, int32_t *h_idx,
+                          int64_t *h_col_off, int64_t *n_cols_out, void *stream);
+int pb_polish_encode_device(pb_polish_encoder_t *enc,
+                            const pb_reads_t *d_reads,
+                            const pb_region_t *d_regions, int64_t n_regions,
+                            const pb_region_t *h_regions,
+                            int64_t capacity_cols,
+                            uint8_t *d_image, int64_t *d_pos, int32_t *d_idx,
+                            int64_t *d_col_off, int64_t *n_cols_out, void *stream);
+int pb_polish_encoder_timings(pb_polish_encoder_t *enc, float *ms3);
+
+/* ------------------------------------------------------------------------
+ * Variant network (bi-LSTM x2 + 5x(Linear+SELU) + Linear + softmax).
+ * Replaces TransducerGRU.forward, pepper_variant/modules/python/models/
+ * simple_model.py:48-82, as driven by predict_distributed_gpu.py:58-70.
+ * Weights are passed as the state_dict tensors (fp32, PyTorch layout) in the
+ * order of pb_variant_net_param_names(); the handle keeps a packed copy.
+ * ---------------------------------------------------------------------- */
+typedef struct pb_variant_net pb_variant_net_t;
+#define PB_VARIANT_NET_N_PARAMS 28
+const char *pb_variant_net_param_name(int i);   /* state_dict key */
+int64_t     pb_variant_net_param_numel(int i);
+int pb_variant_net_create(pb_variant_net_t **out, int device,
+                          const float *const *h_params /* [28] host fp32 */);
+int pb_variant_net_destroy(pb_variant_net_t *net);
+/* d_images int8 [n][33][26] on device -> d_probs float [n][3] on device.
+ * d_hidden_dbg (optional, may be NULL): float [n][33][512] decoder output.   */
+int pb_variant_net_forward_device(pb_variant_net_t *net, const int8_t *d_images,
+                                  int64_t n, float *d_probs, float *d_hidden_dbg,
+                                  void *stream);
+int pb_variant_net_forward_host(pb_variant_net_t *net, const int8_t *h_images,
+                                int64_t n, float *h_probs, float *h_hidden_dbg,
+                                void *stream);
+/* tensor-pipe precision of the dense GEMMs: 0 = fp32 FFMA (reference-exact
+ * ordering), 1 = tcgen05 bf16x3 split (fp32-equivalent)                      */
+int pb_variant_net_set_mode(pb_variant_net_t *net, int mode);
+int pb_variant_net_launches(pb_variant_net_t *net, int64_t *n_launches);
+
+/* ------------------------------------------------------------------------
+ * Polish network (bi-GRU x2 + Linear(256->5)), 19-window sliding loop with
+ * carried hidden state, softmax accumulate, argmax, phred.  Replaces
+ * TransducerGRU.forward (pepper/modules/python/models/simple_model.py:27-42)
+ * and the loop of predict_distributed_cpu.py:50-90 / _gpu.py:63-105.
+ * ---------------------------------------------------------------------- */
+typedef struct pb_polish_net pb_polish_net_t;
+#define PB_POLISH_NET_N_PARAMS 18
+const char *pb_polish_net_param_name(int i);
+int64_t     pb_polish_net_param_numel(int i);
+int pb_polish_net_create(pb_polish_net_t **out, int device,
+                         const float *const *h_params /* [18] host fp32 */);
+int pb_polish_net_destroy(pb_polish_net_t *net);
+/* d_images uint8 [n][1000][10] -> d_bases uint8 [n][1000], d_phred uint8 [n][1000]
+ * d_hidden_dbg (optional): float [19][n][2][128] hidden state returned by each window
+ * d_acc_dbg (optional): float [n][1000][5] accumulated softmax                */
+int pb_polish_net_forward_device(pb_polish_net_t *net, const uint8_t *d_images,
+                                 int64_t n, uint8_t *d_bases, uint8_t *d_phred,
+                                 float *d_hidden_dbg, float *d_acc_dbg, void *stream);
+int pb_polish_net_forward_host(pb_polish_net_t *net, const uint8_t *h_images,
+                               int64_t n, uint8_t *h_bases, uint8_t *h_phred,
+                               float *h_hidden_dbg, float *h_acc_dbg, void *stream);
+int pb_polish_net_launches(pb_polish_net_t *net, int64_t *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEPPER_B200_H */
