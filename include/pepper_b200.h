@@ -105,6 +105,9 @@ typedef struct pb_variant_encoder pb_variant_encoder_t;
 
 int pb_variant_encoder_create(pb_variant_encoder_t **out, int device);
 int pb_variant_encoder_destroy(pb_variant_encoder_t *enc);
+/* keep the snp/insert/delete count vectors of the next encode calls for
+ * pb_variant_encoder_debug_region (off by default: 12 B/position of traffic) */
+int pb_variant_encoder_set_debug(pb_variant_encoder_t *enc, int on);
 
 /* Host-buffer entry point (the one the PEPPER_VARIANT mirror classes call):
  * copies reads/ref to the device, encodes, copies the candidates back.

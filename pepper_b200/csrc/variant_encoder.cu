@@ -1,0 +1,1226 @@
+// Variant pileup-summary encoder for sm_100a.
+//
+// Re-design (not a translation) of RegionalSummaryGenerator::generate_summary
+// (pepper_variant/modules/cpp/region_summary.cpp:337-916).  The reference walks one read at a
+// time and read-modify-writes vector<vector<int>> rows and std::map<string,int> tallies per base.
+// Here a batch of regions is processed by six kernels:
+//
+//   k_cigar_prefix   one warp per read: prefix sums of (reference, read) consumption per CIGAR op
+//   k_tile_count     one CTA per 512-position tile: every warp walks the reads overlapping the
+//                    tile, counts into shared-memory columns with shared atomics, then the CTA
+//                    applies the site thresholds (:634-646) and writes each position's 16 live
+//                    matrix columns once (32 B / position)
+//   k_site_index     per tile: compacts flagged sites, gives each an event segment
+//   k_collect_*      per CIGAR op / per rare base: writes allele events of flagged sites
+//   k_site_alleles   one warp per site: dedup + order alleles as std::set<string> would,
+//                    apply the candidate filters (:682-712)
+//   k_windows        one warp per site: 33x26 int8 window gather + overlay (:828-905), key strings
+//
+// Only columns 4, 8-15, 19-25 of the 26 are ever non-zero in the base matrix (col 0 is the reference
+// code, the rest are written by the per-candidate overlay), so 16 int16 are stored per position.
+#include "common.cuh"
+#include <vector>
+#include <algorithm>
+
+namespace pb {
+
+constexpr int TILE = 512;            // positions per k_tile_count CTA
+constexpr int TC_THREADS = 256;
+constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int MAX_KEY = 61;          // region_summary.cpp:461,511 candidate_string.length() <= 61
+
+// shared-memory counter columns of k_tile_count (int32 [NCNT][TILE])
+enum {
+    C_TOT_F = 0, C_TOT_R,          // M bases with q >= min_snp_baseq per strand
+    C_ANC_F, C_ANC_R,              // ... of which anchor an I/D (excluded from REFF/REFR, :381-391)
+    C_A_F, C_C_F, C_G_F, C_T_F,    // bases whose column differs from the reference column
+    C_A_R, C_C_R, C_G_R, C_T_R,
+    C_NON_F, C_NON_R,              // non-ACGT read bases
+    C_I_F, C_I_R,                  // col 12 / 23
+    C_D_F, C_D_R,                  // col 13 / 24 (deletion anchors + IUPAC 'D' bases)
+    C_S_F, C_S_R,                  // col 14 / 25 ('*' + other bases)
+    C_COVX,                        // coverage increments of :453
+    C_SNP, C_INS, C_DEL,           // snp_count / insert_count / delete_count
+    C_RARE,                        // SNP alleles that cannot be derived from the columns
+    NCNT
+};
+
+// per-position meta word: bit0 snp pass, bit1 insert pass, bit2 delete pass, bit3 site; bits 4.. event slots
+constexpr uint32_t F_SNP = 1, F_INS = 2, F_DEL = 4, F_SITE = 8;
+
+struct RareEv { uint32_t g; uint8_t code; uint8_t strand; uint16_t pad; };
+
+struct Ev {            // 40 B allele event / allele entry
+    uint64_t key;      // order key inside a type (see ins_key / klen / ascii rank)
+    uint32_t read;     // source read (insert bases)
+    uint32_t ridx;     // index of the anchor base in the read
+    uint16_t klen;     // bases in the key after the type digit
+    uint8_t type;      // 1 snp, 2 insert, 3 delete
+    uint8_t strand;
+    uint8_t leader;
+    uint8_t pass;
+    uint8_t code;      // snp: NT16 code
+    uint8_t pad;
+    int32_t total, fwd;
+    int32_t order;
+    int32_t pad2;
+};
+
+struct Cand {          // 32 B candidate record
+    uint32_t read, ridx;
+    int32_t total, fwd, rev;
+    uint16_t klen;
+    uint8_t type, code;
+    uint32_t pad[2];
+};
+
+struct DevReads {
+    const int64_t *pos, *seq_off, *cigar_off;
+    const uint8_t *flags, *mapq, *seq, *qual;
+    const uint32_t *cigar;
+    int64_t n_reads;
+};
+
+struct VParams {
+    int minq_snp;                 // ceil(min_snp_baseq): integer q >= min_snp_baseq  <=>  q >= ceil
+    double min_snp_baseq, min_indel_baseq;
+    double snp_thr, ins_thr, del_thr, min_cov, snp_cand_thr, indel_cand_thr, support_thr;
+    int skip_indels;
+};
+
+// ------------------------------------------------------------------ k_cigar_prefix
+// Consumption rules of the walker (region_summary.cpp:356-563): M/=/X ref+read; I read; D ref;
+// N and P advance ref AND (falling through into S, :556-560) read; S read; H nothing.
+__device__ __forceinline__ void op_consumes(uint32_t w, int &dref, int &drd) {
+    const int op = w & 15, len = (int) (w >> 4);
+    dref = 0; drd = 0;
+    switch (op) {
+        case 0: case 7: case 8: dref = len; drd = len; break;
+        case 1: drd = len; break;
+        case 2: dref = len; break;
+        case 3: case 6: dref = len; drd = len; break;
+        case 4: drd = len; break;
+        default: break;
+    }
+}
+
+__global__ void k_cigar_prefix(DevReads R, int32_t *__restrict__ op_ref, int32_t *__restrict__ op_rd,
+                               int32_t *__restrict__ read_reflen) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R.n_reads) return;
+    const int64_t c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
+    int cref = 0, crd = 0;
+    for (int64_t c = c0; c < c1; c += 32) {
+        int dref = 0, drd = 0;
+        if (c + lane < c1) op_consumes(__ldg(R.cigar + c + lane), dref, drd);
+        int sref = dref, srd = drd;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int a = __shfl_up_sync(0xffffffffu, sref, d), b = __shfl_up_sync(0xffffffffu, srd, d);
+            if (lane >= d) { sref += a; srd += b; }
+        }
+        if (c + lane < c1) {
+            op_ref[c + lane] = cref + sref - dref;
+            op_rd[c + lane] = crd + srd - drd;
+        }
+        cref += __shfl_sync(0xffffffffu, sref, 31);
+        crd += __shfl_sync(0xffffffffu, srd, 31);
+    }
+    if (lane == 0) read_reflen[r] = cref;
+}
+
+// ------------------------------------------------------------------ shared op predicates
+// Insert allele of one I op (region_summary.cpp:431-488).  Returns true when the allele is tallied;
+// cov_extra is the coverage increment of :453.
+__device__ __forceinline__ bool insert_allele(const DevReads &R, int64_t so, int64_t lseq, int rd_idx, int len,
+                                              const VParams &P, int &klen, bool &cov_extra) {
+    const int64_t s = (int64_t) rd_idx - 1;
+    const int64_t n = (int64_t) len + 1;
+    double qsum = 0;
+    for (int64_t i = s; i < s + n; i++) qsum += (double) __ldg(R.qual + so + i);
+    const bool qok = qsum >= P.min_indel_baseq * (double) n;
+    cov_extra = qok && ((double) __ldg(R.qual + so + s) < P.min_snp_baseq);
+    int64_t k = n;
+    if (s + k > lseq) k = lseq - s;          // std::string::substr clamps
+    klen = (int) k;
+    return (1 + k <= MAX_KEY) && qok;
+}
+// Delete allele key length (region_summary.cpp:500,507-511): "3" + reference.substr(x, len+1)
+__device__ __forceinline__ bool delete_allele(int64_t x, int len, int64_t ref_len, int &klen) {
+    int64_t k = (int64_t) len + 1;
+    if (x + k > ref_len) k = ref_len - x;
+    if (k < 0) k = 0;
+    klen = (int) k;
+    return 1 + k <= MAX_KEY;
+}
+
+// class of a read base: 0..3 = A,C,G,T  4 = IUPAC 'D' (lands in the D column, region_summary.cpp:214)  5 = other
+__device__ __forceinline__ int base_class(int code) {
+    // code: 0 1 2 3 4 5 6 7 8 9 10 11 12 13 14 15
+    //       5 0 1 5 2 5 5 5 3 5  5  5  5  4  5  5
+    return (int) ((0x5545555355525105ULL >> (4 * code)) & 15ULL);
+}
+// class of a reference character: 0..3 valid (case-insensitive, check_ref_base :193), 7 invalid
+__device__ __forceinline__ int ref_class(char c) {
+    switch (to_upper(c)) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 7; }
+}
+
+// ------------------------------------------------------------------ k_tile_count
+struct TileArgs {
+    DevReads R;
+    const pb_region_t *regions;
+    const char *ref;
+    const int32_t *op_ref, *op_rd, *read_reflen;
+    const int32_t *tile_region;      // [n_tiles]
+    const int32_t *tile_x0;          // [n_tiles] first position of the tile relative to ref_start
+    const int64_t *region_goff;      // [n_regions] global position index of the region's first position
+    int16_t *M16;                    // [G][16]
+    int32_t *cov;                    // [G]
+    uint32_t *meta;                  // [G]
+    int32_t *dbg_counts;             // optional [G][3] snp, ins, del
+    int32_t *tile_nsites, *tile_nev; // [n_tiles]
+    RareEv *rare; unsigned long long *rare_n; unsigned long long rare_cap;
+    VParams P;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
+    extern __shared__ int32_t smem[];
+    int32_t *cnt = smem;                                   // [NCNT][TILE]
+    char *s_ref = reinterpret_cast<char *>(cnt + NCNT * TILE);   // [TILE]
+    __shared__ int s_red[2];
+
+    const int t = blockIdx.x;
+    const int reg = A.tile_region[t];
+    const pb_region_t rg = A.regions[reg];
+    const int64_t x0 = A.tile_x0[t];
+    const int64_t L1 = rg.ref_end - rg.ref_start + 1;
+    const int npos = (int) min((int64_t) TILE, L1 - x0);
+    const int64_t lo = rg.ref_start + x0, hi = lo + npos - 1;      // absolute, inclusive
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < NCNT * TILE; i += TC_THREADS) cnt[i] = 0;
+    for (int i = tid; i < TILE; i += TC_THREADS) {
+        const int64_t x = x0 + i;
+        s_ref[i] = (i < npos && x < rg.ref_len) ? A.ref[rg.ref_off + x] : '\0';
+    }
+    if (tid < 2) s_red[tid] = 0;
+    __syncthreads();
+
+    const DevReads &R = A.R;
+    const VParams &P = A.P;
+
+    // ---- every warp takes groups of 32 reads of the region, lanes test overlap in parallel
+    for (int64_t rb = rg.read_begin + (int64_t) warp * 32; rb < rg.read_end; rb += (int64_t) TC_WARPS * 32) {
+        const int64_t rmine = rb + lane;
+        bool ov = false;
+        if (rmine < rg.read_end && __ldg(R.mapq + rmine) > 0 && R.seq_off[rmine + 1] > R.seq_off[rmine]) {
+            const int64_t p0 = __ldg(R.pos + rmine);
+            const int64_t p1 = p0 + __ldg(A.read_reflen + rmine);      // exclusive end
+            // ops of interest touch [lo-1 .. hi+1]
+            ov = (p0 <= hi + 1) && (p1 >= lo - 1);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, ov);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t r = rb + src;
+            const int64_t rpos = __ldg(R.pos + r);
+            const int64_t so = R.seq_off[r];
+            const int64_t lseq = R.seq_off[r + 1] - so;
+            const int64_t c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
+            const int nops = (int) (c1 - c0);
+            const int rev = __ldg(R.flags + r) & 1;
+            // --- first op to look at: last op whose start <= lo - rpos (32-ary cooperative search)
+            const int64_t target = lo - rpos;
+            int first = 0;
+            if (target > 0) {
+                int base = 0, n = nops;
+                while (n > 1) {
+                    const int stride = (n + 31) / 32;
+                    const int idx = base + lane * stride;
+                    const bool le = (lane * stride < n) && ((int64_t) __ldg(A.op_ref + c0 + idx) <= target);
+                    const unsigned m = __ballot_sync(0xffffffffu, le);
+                    const int k = __popc(m);                 // op_ref is non-decreasing: a prefix of lanes
+                    if (k == 0) { n = 0; break; }
+                    const int nb = base + (k - 1) * stride;
+                    n = min(stride, base + n - nb);
+                    base = nb;
+                }
+                first = base;
+            }
+            // --- walk chunks of 32 ops
+            for (int j0 = first; j0 < nops; j0 += 32) {
+                const int j = j0 + lane;
+                uint32_t w = 0; int pr = 0, pd = 0;
+                if (j < nops) { w = __ldg(R.cigar + c0 + j); pr = __ldg(A.op_ref + c0 + j); pd = __ldg(A.op_rd + c0 + j); }
+                uint32_t wn = __shfl_down_sync(0xffffffffu, w, 1);
+                if (lane == 31) wn = (j + 1 < nops) ? __ldg(R.cigar + c0 + j + 1) : 0xfu;
+                if (j + 1 >= nops) wn = 0xfu;                   // no next op
+                const int op = (j < nops) ? (int) (w & 15) : 15;
+                const int len = (int) (w >> 4);
+                const int64_t a = rpos + pr;                    // ref position at op start
+                const bool live = (j < nops) && (a <= rg.ref_end);     // walker breaks when ref_position > ref_end (:355)
+                // chunk exit test: every later op starts at or after this chunk's last start
+                const int64_t a_last = __shfl_sync(0xffffffffu, a, 31);
+                const bool is_m = (op == 0 || op == 7 || op == 8);
+                // clipped per-position segment (M bases or deleted positions)
+                int64_t s0 = 0; int scnt = 0;
+                if (live && (is_m || op == 2)) {
+                    const int64_t b0 = max(a, lo), b1 = min(a + len - 1, hi);
+                    if (b1 >= b0) { s0 = b0; scnt = (int) (b1 - b0 + 1); }
+                }
+                // anchor of an I/D after the last base of this M op
+                const int nop = (int) (wn & 15);
+                const bool anchors_next = is_m && (nop == 1 || nop == 2);
+                const int64_t op_last = a + len - 1;
+                // --- I / D ops anchored in this tile (handled by the op's own lane)
+                if (live && (op == 1 || op == 2)) {
+                    const int64_t p = a - 1;
+                    if (p >= lo && p <= hi) {
+                        const int x = (int) (p - lo);
+                        const bool rvalid = ref_class(s_ref[x]) < 4;
+                        if (op == 1) {
+                            if (pd >= 1) {
+                                int klen; bool covx;
+                                const bool ok = insert_allele(R, so, lseq, pd, len, P, klen, covx);
+                                if (covx) atomicAdd(&cnt[C_COVX * TILE + x], 1);
+                                if (ok) {
+                                    if (rvalid) atomicAdd(&cnt[(C_I_F + rev) * TILE + x], 1);
+                                    atomicAdd(&cnt[C_INS * TILE + x], 1);
+                                }
+                            }
+                        } else {
+                            if (rvalid) atomicAdd(&cnt[(C_D_F + rev) * TILE + x], 1);
+                            int klen;
+                            if (delete_allele(p - rg.ref_start, len, rg.ref_len, klen)) atomicAdd(&cnt[C_DEL * TILE + x], 1);
+                        }
+                    }
+                }
+                // --- per-position work, balanced over the warp
+                int incl = scnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                for (int k0 = 0; k0 < total; k0 += 32) {
+                    const int idx = k0 + lane;
+                    // smallest l with incl[l] > idx
+                    int l = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int v = __shfl_sync(0xffffffffu, incl, l + step - 1);
+                        if (v <= idx) l += step;
+                    }
+                    l = min(l, 31);
+                    const int o_incl = __shfl_sync(0xffffffffu, incl, l);
+                    const int o_cnt = __shfl_sync(0xffffffffu, scnt, l);
+                    const int64_t o_s0 = __shfl_sync(0xffffffffu, s0, l);
+                    const int64_t o_a = __shfl_sync(0xffffffffu, a, l);
+                    const int o_pd = __shfl_sync(0xffffffffu, pd, l);
+                    const int o_op = __shfl_sync(0xffffffffu, op, l);
+                    const int64_t o_last = __shfl_sync(0xffffffffu, op_last, l);
+                    const int o_anch = __shfl_sync(0xffffffffu, (int) anchors_next, l);
+                    if (idx < total) {
+                        const int64_t p = o_s0 + (idx - (o_incl - o_cnt));
+                        const int x = (int) (p - lo);
+                        const char rch = s_ref[x];
+                        const int rcls = ref_class(rch);
+                        if (o_op == 2) {
+                            if (rcls < 4) atomicAdd(&cnt[(C_S_F + rev) * TILE + x], 1);
+                        } else {
+                            const int64_t ri = (int64_t) o_pd + (p - o_a);
+                            const int q = __ldg(R.qual + so + ri);
+                            if (q >= P.minq_snp) {
+                                const int code = seq_code_at(R.seq, so + ri);
+                                atomicAdd(&cnt[(C_TOT_F + rev) * TILE + x], 1);
+                                if (o_anch && p == o_last) atomicAdd(&cnt[(C_ANC_F + rev) * TILE + x], 1);
+                                const int cls = base_class(code);
+                                if (rcls < 4) {
+                                    if (cls < 4) {
+                                        if (cls != rcls) atomicAdd(&cnt[(C_A_F + 4 * rev + cls) * TILE + x], 1);
+                                    } else {
+                                        atomicAdd(&cnt[(C_NON_F + rev) * TILE + x], 1);
+                                        atomicAdd(&cnt[((cls == 4 ? C_D_F : C_S_F) + rev) * TILE + x], 1);
+                                    }
+                                }
+                                if (nt16_char(code) != rch) {
+                                    atomicAdd(&cnt[C_SNP * TILE + x], 1);
+                                    if (rcls >= 4 || cls >= 4) {
+                                        atomicAdd(&cnt[C_RARE * TILE + x], 1);
+                                        const unsigned long long slot = atomicAdd(A.rare_n, 1ULL);
+                                        if (slot < A.rare_cap) {
+                                            RareEv e; e.g = (uint32_t) (A.region_goff[reg] + x0 + x); e.code = (uint8_t) code;
+                                            e.strand = (uint8_t) rev; e.pad = 0;
+                                            A.rare[slot] = e;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (a_last > hi + 1) break;      // warp-uniform: later ops cannot touch the tile
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue: derive the columns, site thresholds (region_summary.cpp:634-646), one write per position
+    const int64_t g0 = A.region_goff[reg] + x0;
+    int my_sites = 0, my_ev = 0;
+    for (int x = tid; x < npos; x += TC_THREADS) {
+#define CN(c) cnt[(c) * TILE + x]
+        const int rcls = ref_class(s_ref[x]);
+        const int cov = CN(C_TOT_F) + CN(C_TOT_R) + CN(C_COVX);
+        int16_t row[16];
+        row[0] = (int16_t) -(CN(C_TOT_F) - CN(C_ANC_F));           // col 4  REFF
+        row[8] = (int16_t) -(CN(C_TOT_R) - CN(C_ANC_R));           // col 15 REFR
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            int n[4];
+            int others = CN(C_NON_F + s);
+#pragma unroll
+            for (int b = 0; b < 4; b++) { n[b] = CN(C_A_F + 4 * s + b); others += n[b]; }
+            if (rcls < 4) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) if (b == rcls) n[b] = CN(C_TOT_F + s) - others;
+            }
+            const int o = s ? 9 : 1;                                   // cols 19.. / 8..
+#pragma unroll
+            for (int b = 0; b < 4; b++) row[o + b] = (int16_t) -((rcls < 4) ? n[b] : 0);
+            row[o + 4] = (int16_t) -CN(C_I_F + s);
+            row[o + 5] = (int16_t) -CN(C_D_F + s);
+            row[o + 6] = (int16_t) -CN(C_S_F + s);
+        }
+        const int64_t g = g0 + x;
+        int4 *dst = reinterpret_cast<int4 *>(A.M16 + g * 16);
+        const int4 *srcv = reinterpret_cast<const int4 *>(row);
+        dst[0] = srcv[0];
+        dst[1] = srcv[1];
+        A.cov[g] = cov;
+        const int snp = CN(C_SNP), ins = CN(C_INS), del = CN(C_DEL);
+        if (A.dbg_counts) { A.dbg_counts[g * 3] = snp; A.dbg_counts[g * 3 + 1] = ins; A.dbg_counts[g * 3 + 2] = del; }
+        const double c = fmax(1.0, (double) cov);
+        const double fs = (double) snp / c, fi = (double) ins / c, fd = (double) del / c;
+        uint32_t m = 0;
+        const int64_t pos = lo + x;
+        if ((fs >= P.snp_thr || fi >= P.ins_thr || fd >= P.del_thr) && pos >= rg.cand_start && pos <= rg.cand_end &&
+            (double) cov >= P.min_cov) {
+            m = F_SITE;
+            int ev = 0;
+            if (fs >= P.snp_thr) { m |= F_SNP; ev += 4 + CN(C_RARE); }
+            if (fi >= P.ins_thr) { m |= F_INS; ev += ins; }
+            if (fd >= P.del_thr) { m |= F_DEL; ev += del; }
+            m |= (uint32_t) ev << 4;
+            my_sites += 1;
+            my_ev += ev;
+        }
+        A.meta[g] = m;
+#undef CN
+    }
+    atomicAdd(&s_red[0], my_sites);
+    atomicAdd(&s_red[1], my_ev);
+    __syncthreads();
+    if (tid == 0) { A.tile_nsites[t] = s_red[0]; A.tile_nev[t] = s_red[1]; }
+}
+
+// ------------------------------------------------------------------ single-CTA exclusive scan (n <= a few 1e6)
+__global__ void k_scan_excl(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n, int64_t *__restrict__ total) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry, s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (int) (blockDim.x >> 5);
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < n; b += blockDim.x) {
+        const int64_t i = b + tid;
+        const int64_t v = (i < n) ? (int64_t) in[i] : 0;
+        int64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int64_t w = (lane < nwarps) ? s_warp[lane] : 0;
+            int64_t winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t u = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += u;
+            }
+            s_warp[lane] = winc - w;
+            if (lane == 31) s_total = winc;
+        }
+        __syncthreads();
+        if (i < n) out[i] = s_carry + s_warp[warp] + inc - v;
+        __syncthreads();
+        if (tid == 0) s_carry += s_total;
+        __syncthreads();
+    }
+    if (tid == 0) { out[n] = s_carry; if (total) *total = s_carry; }
+}
+
+// ------------------------------------------------------------------ k_site_index
+struct SiteArgs {
+    const pb_region_t *regions;
+    const int32_t *tile_region, *tile_x0;
+    const int64_t *region_goff;
+    const uint32_t *meta;
+    const int64_t *tile_site_base, *tile_ev_base;
+    uint32_t *site_of;       // [G] (valid where flagged)
+    uint32_t *site_g;        // [n_sites]
+    int64_t *site_evoff;     // [n_sites+1]
+    int64_t n_sites_total, n_ev_total;
+};
+
+__global__ void __launch_bounds__(TILE) k_site_index(SiteArgs A) {
+    __shared__ int s_ws[TILE / 32], s_we[TILE / 32];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int reg = A.tile_region[t];
+    const pb_region_t rg = A.regions[reg];
+    const int64_t x0 = A.tile_x0[t];
+    const int64_t L1 = rg.ref_end - rg.ref_start + 1;
+    const int npos = (int) min((int64_t) TILE, L1 - x0);
+    const int64_t g = A.region_goff[reg] + x0 + tid;
+    uint32_t m = (tid < npos) ? A.meta[g] : 0;
+    int fs = (m & F_SITE) ? 1 : 0, fe = (int) (m >> 4);
+    int is = fs, ie = fe;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, is, d), b = __shfl_up_sync(0xffffffffu, ie, d);
+        if (lane >= d) { is += a; ie += b; }
+    }
+    if (lane == 31) { s_ws[warp] = is; s_we[warp] = ie; }
+    __syncthreads();
+    int bs = 0, be = 0;
+    for (int w = 0; w < warp; w++) { bs += s_ws[w]; be += s_we[w]; }
+    if (fs) {
+        const int64_t s = A.tile_site_base[t] + bs + is - 1;
+        A.site_of[g] = (uint32_t) s;
+        A.site_g[s] = (uint32_t) g;
+        A.site_evoff[s] = A.tile_ev_base[t] + be + ie - fe;
+    }
+    if (t == 0 && tid == 0) A.site_evoff[A.n_sites_total] = A.n_ev_total;
+}
+
+// ------------------------------------------------------------------ k_collect_ops / k_collect_rare
+// 5 bits per base (ascii rank + 1), first 12 bases, most significant first: numeric order == std::string order
+__device__ __forceinline__ uint64_t ins_key(const DevReads &R, int64_t so, int64_t s, int klen) {
+    uint64_t k = 0;
+    const int n = min(klen, 12);
+    for (int i = 0; i < n; i++) {
+        const uint64_t sym = (uint64_t) nt16_ascii_rank(seq_code_at(R.seq, so + s + i)) + 1ULL;
+        k |= sym << (5 * (11 - i));
+    }
+    return k;
+}
+
+struct CollectArgs {
+    DevReads R;
+    const pb_region_t *regions;
+    const int32_t *read_region;
+    const int64_t *region_goff;
+    const int32_t *op_ref, *op_rd;
+    const uint32_t *meta, *site_of;
+    const int64_t *site_evoff;
+    uint32_t *site_cur;
+    Ev *ev;
+    const RareEv *rare; unsigned long long n_rare;
+    VParams P;
+};
+
+__device__ __forceinline__ Ev *claim_slot(const CollectArgs &A, uint32_t m, uint32_t s) {
+    const uint32_t k = atomicAdd(A.site_cur + s, 1u);
+    return A.ev + A.site_evoff[s] + ((m & F_SNP) ? 4 : 0) + k;
+}
+
+__global__ void k_collect_ops(CollectArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const DevReads &R = A.R;
+    if (r >= R.n_reads) return;
+    if (R.mapq[r] == 0) return;
+    const int64_t so = R.seq_off[r], lseq = R.seq_off[r + 1] - so;
+    if (lseq == 0) return;
+    const int reg = A.read_region[r];
+    if (reg < 0) return;
+    const pb_region_t rg = A.regions[reg];
+    const int64_t rpos = R.pos[r];
+    const int64_t c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
+    const int rev = R.flags[r] & 1;
+    for (int64_t c = c0 + lane; c < c1; c += 32) {
+        const uint32_t w = __ldg(R.cigar + c);
+        const int op = w & 15, len = (int) (w >> 4);
+        if (op != 1 && op != 2) continue;
+        const int64_t a = rpos + __ldg(A.op_ref + c);
+        if (a > rg.ref_end) continue;                       // :355
+        const int64_t p = a - 1;
+        if (p < rg.ref_start || p > rg.ref_end) continue;
+        const int64_t x = p - rg.ref_start;
+        const int64_t g = A.region_goff[reg] + x;
+        const uint32_t m = A.meta[g];
+        if (op == 1) {
+            if (!(m & F_INS)) continue;
+            const int pd = __ldg(A.op_rd + c);
+            if (pd < 1) continue;
+            int klen; bool covx;
+            if (!insert_allele(R, so, lseq, pd, len, A.P, klen, covx)) continue;
+            Ev *e = claim_slot(A, m, A.site_of[g]);
+            Ev v; memset(&v, 0, sizeof(v));
+            v.type = 2; v.strand = (uint8_t) rev; v.klen = (uint16_t) klen; v.read = (uint32_t) r; v.ridx = (uint32_t) (pd - 1);
+            v.key = ins_key(R, so, pd - 1, klen);
+            *e = v;
+        } else {
+            if (!(m & F_DEL)) continue;
+            int klen;
+            if (!delete_allele(x, len, rg.ref_len, klen)) continue;
+            Ev *e = claim_slot(A, m, A.site_of[g]);
+            Ev v; memset(&v, 0, sizeof(v));
+            v.type = 3; v.strand = (uint8_t) rev; v.klen = (uint16_t) klen; v.key = (uint64_t) klen;
+            *e = v;
+        }
+    }
+}
+
+__global__ void k_collect_rare(CollectArgs A) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_rare) return;
+    const RareEv re = A.rare[i];
+    const uint32_t m = A.meta[re.g];
+    if (!(m & F_SNP)) return;
+    Ev *e = claim_slot(A, m, A.site_of[re.g]);
+    Ev v; memset(&v, 0, sizeof(v));
+    v.type = 1; v.strand = re.strand; v.klen = 1; v.code = re.code; v.key = (uint64_t) nt16_ascii_rank(re.code);
+    *e = v;
+}
+
+// ------------------------------------------------------------------ k_site_alleles
+struct AlleleArgs {
+    DevReads R;
+    const pb_region_t *regions;
+    const char *ref;
+    const int64_t *region_goff;      // [n_regions+1]
+    int64_t n_regions;
+    const uint32_t *site_g;
+    const int64_t *site_evoff;
+    const int16_t *M16;
+    const int32_t *cov;
+    const uint32_t *meta;
+    Ev *ev;
+    Cand *cand_tmp;                  // same indexing as ev
+    int32_t *site_ncand;
+    int32_t *site_region;            // [n_sites] (written here, reused by k_windows)
+    int64_t n_sites;
+    VParams P;
+};
+
+__device__ __forceinline__ int find_region(const int64_t *goff, int64_t n_regions, int64_t g) {
+    int lo = 0, hi = (int) n_regions - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (goff[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// tails (bases 12..) of two insert alleles: <0, 0, >0 like std::string::compare
+__device__ int ins_tail_cmp(const DevReads &R, const Ev &a, const Ev &b) {
+    const int64_t sa = R.seq_off[a.read] + a.ridx, sb = R.seq_off[b.read] + b.ridx;
+    const int n = min((int) a.klen, (int) b.klen);
+    for (int i = 12; i < n; i++) {
+        const int ra = nt16_ascii_rank(seq_code_at(R.seq, sa + i)), rb = nt16_ascii_rank(seq_code_at(R.seq, sb + i));
+        if (ra != rb) return ra - rb;
+    }
+    return (int) a.klen - (int) b.klen;
+}
+__device__ __forceinline__ int allele_cmp(const DevReads &R, const Ev &a, const Ev &b) {
+    if (a.type != b.type) return (int) a.type - (int) b.type;
+    if (a.key != b.key) return a.key < b.key ? -1 : 1;
+    if (a.type == 2 && a.klen > 12 && b.klen > 12) return ins_tail_cmp(R, a, b);
+    return (int) a.klen - (int) b.klen;
+}
+
+__global__ void k_site_alleles(AlleleArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= A.n_sites) return;
+    const int64_t g = A.site_g[s];
+    const int reg = find_region(A.region_goff, A.n_regions, g);
+    const pb_region_t rg = A.regions[reg];
+    const int64_t x = g - A.region_goff[reg];
+    const uint32_t m = A.meta[g];
+    const int64_t e0 = A.site_evoff[s];
+    const int n = (int) (A.site_evoff[s + 1] - e0);
+    Ev *ev = A.ev + e0;
+    const int npseudo = (m & F_SNP) ? 4 : 0;
+    const char rch = (x < rg.ref_len) ? A.ref[rg.ref_off + x] : '\0';
+    const int rcls = ref_class(rch);
+    const int cov = A.cov[g];
+    const int depth = min(cov, 125);                                   // region_summary.cpp:682
+    const double ddepth = fmax(1.0, (double) depth);
+    const VParams &P = A.P;
+    if (lane == 0) A.site_region[s] = reg;
+
+    // A. SNP alleles of A/C/G/T read straight from the (unclamped) columns
+    if (lane < npseudo) {
+        const int code = 1 << lane;                                    // A=1 C=2 G=4 T=8
+        Ev v; memset(&v, 0, sizeof(v));
+        v.type = 1; v.klen = 1; v.code = (uint8_t) code; v.key = (uint64_t) nt16_ascii_rank(code);
+        if (rcls < 4 && nt16_char(code) != rch) {
+            const int f = -(int) A.M16[g * 16 + 1 + lane], r = -(int) A.M16[g * 16 + 9 + lane];
+            v.total = f + r; v.fwd = f; v.leader = (f + r) > 0;
+        }
+        ev[lane] = v;
+    }
+    __syncwarp();
+    // B. leaders among the real events
+    for (int i = npseudo + lane; i < n; i += 32) {
+        const Ev me = ev[i];
+        bool lead = true;
+        for (int j = npseudo; j < i && lead; j++) if (allele_cmp(A.R, ev[j], me) == 0) lead = false;
+        ev[i].leader = lead;
+    }
+    __syncwarp();
+    // C. totals + filters (region_summary.cpp:686-712)
+    for (int i = lane; i < n; i += 32) {
+        Ev me = ev[i];
+        if (!me.leader) { ev[i].pass = 0; continue; }
+        if (i >= npseudo) {
+            int tot = 0, fwd = 0;
+            for (int j = npseudo; j < n; j++) {
+                const Ev o = ev[j];
+                if (allele_cmp(A.R, o, me) == 0) { tot++; fwd += (o.strand == 0); }
+            }
+            me.total = tot; me.fwd = fwd;
+        }
+        const double freq = (double) me.total / ddepth;
+        bool pass = true;
+        if ((double) me.total < P.support_thr) pass = false;
+        if (me.type != 1 && freq < P.indel_cand_thr) pass = false;
+        if (me.type == 1 && freq < P.snp_cand_thr) pass = false;
+        if (me.type != 1 && P.skip_indels) pass = false;
+        if ((me.type == 1 && !(m & F_SNP)) || (me.type == 2 && !(m & F_INS)) || (me.type == 3 && !(m & F_DEL))) pass = false;
+        me.pass = pass;
+        ev[i] = me;
+    }
+    __syncwarp();
+    // D. order of the passing alleles
+    int npass = 0;
+    for (int i = lane; i < n; i += 32) {
+        const Ev me = ev[i];
+        if (!me.pass) continue;
+        int ord = 0;
+        for (int j = 0; j < n; j++) {
+            const Ev o = ev[j];
+            if (o.pass && allele_cmp(A.R, o, me) < 0) ord++;
+        }
+        Cand c; memset(&c, 0, sizeof(c));
+        c.read = me.read; c.ridx = me.ridx; c.total = me.total; c.fwd = me.fwd; c.rev = me.total - me.fwd;
+        c.klen = me.klen; c.type = me.type; c.code = me.code;
+        A.cand_tmp[e0 + ord] = c;
+        npass++;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) npass += __shfl_xor_sync(0xffffffffu, npass, d);
+    if (lane == 0) A.site_ncand[s] = npass;
+}
+
+// ------------------------------------------------------------------ k_windows
+struct WindowArgs {
+    DevReads R;
+    const pb_region_t *regions;
+    const char *ref;
+    const int64_t *region_goff;
+    const uint32_t *site_g;
+    const int64_t *site_evoff;
+    const int32_t *site_region;
+    const int64_t *site_candoff;     // [n_sites+1]
+    const int16_t *M16;
+    const int32_t *cov;
+    const Cand *cand_tmp;
+    int64_t n_sites, capacity;
+    int8_t *images; int64_t *positions; uint8_t *depths, *freqs; char *keys; int32_t *region_of;
+};
+
+// value of base-matrix cell (row position xr of region, column j) after the clamp of :648-653
+__device__ __forceinline__ int matrix_cell(const WindowArgs &A, const pb_region_t &rg, int64_t gbase, int64_t xr, int64_t L1, int j) {
+    if (xr < 0 || xr >= L1) return 0;          // rows outside [0, region_size) are zero; row region_size is the spare zero row
+    if (j == 0) {
+        const char c = (xr < rg.ref_len) ? to_upper(A.ref[rg.ref_off + xr]) : '\0';
+        return c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 3 : c == 'T' ? 4 : 5;
+    }
+    int k;
+    if (j == 4) k = 0; else if (j >= 8 && j <= 14) k = j - 7; else if (j == 15) k = 8; else if (j >= 19) k = j - 10; else return 0;
+    int v = A.M16[(gbase + xr) * 16 + k];
+    if (j >= 11 && j <= 24) v = v >= 0 ? min(v, 125) : max(v, -125);
+    return v;
+}
+// region_summary.cpp:201-230 for an upper-case class of the reference base
+__device__ __forceinline__ int feat_col(int rcls, char base, int rev) {
+    if (rcls >= 4) return -1;
+    const int start = rev ? 18 : 7;
+    switch (to_upper(base)) {
+        case 'A': return start + 1; case 'C': return start + 2; case 'G': return start + 3; case 'T': return start + 4;
+        case 'I': return start + 5; case 'D': return start + 6; default: return start + 7;
+    }
+}
+
+__global__ void k_windows(WindowArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= A.n_sites) return;
+    const int64_t o0 = A.site_candoff[s];
+    const int nc = (int) (A.site_candoff[s + 1] - o0);
+    if (nc == 0) return;
+    const int64_t g = A.site_g[s];
+    const int reg = A.site_region[s];
+    const pb_region_t rg = A.regions[reg];
+    const int64_t gbase = A.region_goff[reg];
+    const int64_t x = g - gbase;
+    const int64_t L1 = rg.ref_end - rg.ref_start + 1;
+    const char rch = (x < rg.ref_len) ? A.ref[rg.ref_off + x] : '\0';
+    const int rcls = ref_class(rch);
+    const int depth = min(A.cov[g], 125);
+    for (int c = 0; c < nc; c++) {
+        const int64_t o = o0 + c;
+        if (o >= A.capacity) return;
+        const Cand cd = A.cand_tmp[A.site_evoff[s] + c];
+        const int klen = cd.klen;
+        const int fwd = min(cd.fwd, 125), rev = min(cd.rev, 125);
+        char snp_char = 0;
+        int ff, fr, sf = -1, sr = -1, end_index = 16;
+        if (cd.type == 1) {
+            snp_char = nt16_char(cd.code);
+            ff = feat_col(rcls, snp_char, 0); fr = feat_col(rcls, snp_char, 1);
+        } else if (cd.type == 2) {
+            ff = feat_col(rcls, 'I', 0); fr = feat_col(rcls, 'I', 1);
+        } else {
+            ff = feat_col(rcls, 'D', 0); fr = feat_col(rcls, 'D', 1);
+            sf = feat_col(rcls, '*', 0); sr = feat_col(rcls, '*', 1);
+            end_index = min(16 + klen - 1, 31);
+        }
+        int8_t *img = A.images + o * (33 * 26);
+        for (int e = lane; e < 33 * 26; e += 32) {
+            const int i = e / 26, j = e - i * 26;
+            int v = matrix_cell(A, rg, gbase, x - 16 + i, L1, j);
+            if (i == 16) {
+                if (cd.type == 1) {
+                    if (j == 1) v = (snp_char == 'A') ? 1 : (snp_char == 'C') ? 2 : (snp_char == 'G') ? 3 : (snp_char == 'T') ? 4 : 5;
+                    else if (j == 5) v = fwd; else if (j == 16) v = rev;
+                } else if (cd.type == 2) {
+                    if (j == 2) v = min(klen, 125); else if (j == 6) v = fwd; else if (j == 17) v = rev;
+                } else {
+                    if (j == 3) v = min(klen, 125); else if (j == 7) v = fwd; else if (j == 18) v = rev;
+                }
+                if (j == ff || j == fr) v = -v;
+            } else if (cd.type == 3 && i > 16 && i <= end_index) {
+                if (j == 3) v = min(klen, 125); else if (j == 7) v = fwd; else if (j == 18) v = rev;
+                if (j == sf || j == sr) v = -v;
+            }
+            img[e] = (int8_t) v;                     // int8 wrap == DataStore.py:68 astype
+        }
+        // key string, 64 B
+        for (int k = lane; k < PB_ALLELE_STRIDE; k += 32) {
+            char ch = 0;
+            if (k == 0) ch = (char) ('0' + cd.type);
+            else if (k <= klen) {
+                if (cd.type == 1) ch = snp_char;
+                else if (cd.type == 2) ch = nt16_char(seq_code_at(A.R.seq, A.R.seq_off[cd.read] + cd.ridx + (k - 1)));
+                else ch = A.ref[rg.ref_off + x + (k - 1)];
+            }
+            A.keys[o * PB_ALLELE_STRIDE + k] = ch;
+        }
+        if (lane == 0) {
+            A.positions[o] = rg.ref_start + x;
+            A.depths[o] = (uint8_t) depth;
+            A.freqs[o] = (uint8_t) min(cd.total, 125);
+            A.region_of[o] = reg;
+        }
+    }
+}
+
+__global__ void k_region_counts(const int32_t *__restrict__ region_of, int64_t n, int64_t *__restrict__ per_region) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(reinterpret_cast<unsigned long long *>(per_region + region_of[i]), 1ULL);
+}
+
+}  // namespace pb
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+using namespace pb;
+
+struct pb_variant_encoder {
+    int device = 0;
+    DevBuf op_ref, op_rd, read_reflen, read_region, tile_region, tile_x0, region_goff, M16, cov, meta, dbg,
+        tile_nsites, tile_nev, tile_site_base, tile_ev_base, site_of, site_g, site_evoff, site_cur, ev, cand_tmp,
+        site_ncand, site_region, site_candoff, rare, scalars;
+    // host-entry staging
+    DevBuf h_pos, h_seq_off, h_cigar_off, h_flags, h_mapq, h_seq, h_qual, h_cigar, h_regions, h_ref;
+    DevBuf o_images, o_positions, o_depths, o_freqs, o_keys, o_region_of, o_per_region;
+    cudaEvent_t evt[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float ms[5] = {0, 0, 0, 0, 0};
+    bool debug = false;
+    // last-call bookkeeping for the debug read-back
+    std::vector<int64_t> last_goff;
+    std::vector<pb_region_t> last_regions;
+    const char *last_d_ref = nullptr;
+    size_t rare_cap = 1 << 20;
+};
+
+extern "C" int pb_variant_encoder_create(pb_variant_encoder_t **out, int device) {
+    if (!out) { set_error("null out"); return PB_ERR_ARG; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= device) {
+        set_error("no CUDA device %d (found %d): libpepper_b200 has no CPU fallback", device, n);
+        return PB_ERR_CUDA;
+    }
+    PB_CUDA(cudaSetDevice(device));
+    auto *e = new pb_variant_encoder();
+    e->device = device;
+    for (auto &ev : e->evt) PB_CUDA(cudaEventCreate(&ev));
+    PB_CUDA(cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) (NCNT * TILE * sizeof(int32_t) + TILE)));
+    *out = e;
+    return PB_OK;
+}
+
+extern "C" int pb_variant_encoder_destroy(pb_variant_encoder_t *e) {
+    if (!e) return PB_OK;
+    DevBuf *bufs[] = {&e->op_ref, &e->op_rd, &e->read_reflen, &e->read_region, &e->tile_region, &e->tile_x0, &e->region_goff,
+                      &e->M16, &e->cov, &e->meta, &e->dbg, &e->tile_nsites, &e->tile_nev, &e->tile_site_base,
+                      &e->tile_ev_base, &e->site_of, &e->site_g, &e->site_evoff, &e->site_cur, &e->ev, &e->cand_tmp,
+                      &e->site_ncand, &e->site_region, &e->site_candoff, &e->rare, &e->scalars,
+                      &e->h_pos, &e->h_seq_off, &e->h_cigar_off, &e->h_flags, &e->h_mapq, &e->h_seq, &e->h_qual,
+                      &e->h_cigar, &e->h_regions, &e->h_ref, &e->o_images, &e->o_positions, &e->o_depths, &e->o_freqs,
+                      &e->o_keys, &e->o_region_of, &e->o_per_region};
+    for (auto *b : bufs) b->release();
+    for (auto &ev : e->evt) if (ev) cudaEventDestroy(ev);
+    delete e;
+    return PB_OK;
+}
+
+extern "C" int pb_variant_encoder_set_debug(pb_variant_encoder_t *e, int on) {
+    if (!e) return PB_ERR_ARG;
+    e->debug = on != 0;
+    return PB_OK;
+}
+
+static VParams make_params(const pb_variant_params_t *p) {
+    VParams P;
+    P.min_snp_baseq = p->min_snp_baseq;
+    P.min_indel_baseq = p->min_indel_baseq;
+    double c = p->min_snp_baseq;
+    long long ci = (long long) c;
+    if ((double) ci < c) ci++;                     // ceil
+    if (ci < 0) ci = 0;
+    if (ci > 256) ci = 256;
+    P.minq_snp = (int) ci;
+    P.snp_thr = p->snp_freq_threshold; P.ins_thr = p->insert_freq_threshold; P.del_thr = p->delete_freq_threshold;
+    P.min_cov = p->min_coverage_threshold; P.snp_cand_thr = p->snp_candidate_freq_threshold;
+    P.indel_cand_thr = p->indel_candidate_freq_threshold; P.support_thr = p->candidate_support_threshold;
+    P.skip_indels = p->skip_indels;
+    return P;
+}
+
+extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_t *dr, const pb_region_t *d_regions,
+                                        int64_t n_regions, const pb_region_t *h_regions, const char *d_ref,
+                                        int64_t ref_bytes, const pb_variant_params_t *params, int64_t capacity,
+                                        int8_t *d_images, int64_t *d_positions, uint8_t *d_depths, uint8_t *d_freqs,
+                                        char *d_keys, int32_t *d_region_of, int64_t *d_n_per_region, int64_t *n_out,
+                                        void *stream_) {
+    if (!e || !dr || !h_regions || !params || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
+    (void) ref_bytes;
+    cudaStream_t st = (cudaStream_t) stream_;
+    PB_CUDA(cudaSetDevice(e->device));
+    *n_out = 0;
+    if (d_n_per_region && n_regions > 0) PB_CUDA(cudaMemsetAsync(d_n_per_region, 0, sizeof(int64_t) * n_regions, st));
+    if (n_regions <= 0) return PB_OK;
+    const VParams P = make_params(params);
+
+    // ---- host-side tables: tiles, global position offsets, read -> region
+    const int64_t n_reads = dr->n_reads;
+    std::vector<int64_t> goff(n_regions + 1, 0);
+    std::vector<int32_t> tile_region, tile_x0;
+    for (int64_t r = 0; r < n_regions; r++) {
+        const int64_t L1 = h_regions[r].ref_end - h_regions[r].ref_start + 1;
+        if (L1 <= 0) { set_error("region %lld has ref_end < ref_start", (long long) r); return PB_ERR_ARG; }
+        if (h_regions[r].read_begin < 0 || h_regions[r].read_end > n_reads || h_regions[r].read_begin > h_regions[r].read_end) {
+            set_error("region %lld read range out of bounds", (long long) r); return PB_ERR_ARG;
+        }
+        goff[r + 1] = goff[r] + L1;
+        for (int64_t x = 0; x < L1; x += TILE) { tile_region.push_back((int32_t) r); tile_x0.push_back((int32_t) x); }
+    }
+    const int64_t G = goff[n_regions];
+    if (G >= (1LL << 32)) { set_error("batch covers %lld positions (limit 2^32): split the call", (long long) G); return PB_ERR_ARG; }
+    const int64_t n_tiles = (int64_t) tile_region.size();
+    std::vector<int32_t> read_region((size_t) std::max<int64_t>(n_reads, 1), -1);
+    for (int64_t r = 0; r < n_regions; r++)
+        for (int64_t i = h_regions[r].read_begin; i < h_regions[r].read_end; i++) read_region[i] = (int32_t) r;
+
+    // total ops: last cigar_off (device) -> fetch
+    int64_t n_ops = 0;
+    if (n_reads > 0) PB_CUDA(cudaMemcpyAsync(&n_ops, dr->cigar_off + n_reads, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+
+    PB_TRY(e->op_ref.reserve(sizeof(int32_t) * (n_ops + 1)));
+    PB_TRY(e->op_rd.reserve(sizeof(int32_t) * (n_ops + 1)));
+    PB_TRY(e->read_reflen.reserve(sizeof(int32_t) * (n_reads + 1)));
+    PB_TRY(e->read_region.reserve(sizeof(int32_t) * (n_reads + 1)));
+    PB_TRY(e->tile_region.reserve(sizeof(int32_t) * n_tiles));
+    PB_TRY(e->tile_x0.reserve(sizeof(int32_t) * n_tiles));
+    PB_TRY(e->region_goff.reserve(sizeof(int64_t) * (n_regions + 1)));
+    PB_TRY(e->M16.reserve(sizeof(int16_t) * 16 * G));
+    PB_TRY(e->cov.reserve(sizeof(int32_t) * G));
+    PB_TRY(e->meta.reserve(sizeof(uint32_t) * G));
+    PB_TRY(e->site_of.reserve(sizeof(uint32_t) * G));
+    if (e->debug) PB_TRY(e->dbg.reserve(sizeof(int32_t) * 3 * G));
+    PB_TRY(e->tile_nsites.reserve(sizeof(int32_t) * n_tiles));
+    PB_TRY(e->tile_nev.reserve(sizeof(int32_t) * n_tiles));
+    PB_TRY(e->tile_site_base.reserve(sizeof(int64_t) * (n_tiles + 1)));
+    PB_TRY(e->tile_ev_base.reserve(sizeof(int64_t) * (n_tiles + 1)));
+    PB_TRY(e->scalars.reserve(sizeof(int64_t) * 8));
+    PB_TRY(e->rare.reserve(sizeof(RareEv) * e->rare_cap));
+
+    PB_CUDA(cudaMemcpyAsync(e->tile_region.p, tile_region.data(), sizeof(int32_t) * n_tiles, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(e->tile_x0.p, tile_x0.data(), sizeof(int32_t) * n_tiles, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(e->region_goff.p, goff.data(), sizeof(int64_t) * (n_regions + 1), cudaMemcpyHostToDevice, st));
+    if (n_reads > 0)
+        PB_CUDA(cudaMemcpyAsync(e->read_region.p, read_region.data(), sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemsetAsync(e->scalars.p, 0, sizeof(int64_t) * 8, st));
+    int64_t *sc = e->scalars.as<int64_t>();      // [0] n_sites [1] n_ev [2] rare_n [3] n_cand
+
+    DevReads R{dr->pos, dr->seq_off, dr->cigar_off, dr->flags, dr->mapq, dr->seq, dr->qual, dr->cigar, n_reads};
+
+    PB_CUDA(cudaEventRecord(e->evt[0], st));
+    if (n_reads > 0) {
+        const int wpb = 8;
+        k_cigar_prefix<<<(unsigned) ceil_div(n_reads, wpb), wpb * 32, 0, st>>>(R, e->op_ref.as<int32_t>(), e->op_rd.as<int32_t>(),
+                                                                              e->read_reflen.as<int32_t>());
+    }
+    PB_CUDA(cudaEventRecord(e->evt[1], st));
+
+    TileArgs TA;
+    TA.R = R; TA.regions = d_regions; TA.ref = d_ref;
+    TA.op_ref = e->op_ref.as<int32_t>(); TA.op_rd = e->op_rd.as<int32_t>(); TA.read_reflen = e->read_reflen.as<int32_t>();
+    TA.tile_region = e->tile_region.as<int32_t>(); TA.tile_x0 = e->tile_x0.as<int32_t>();
+    TA.region_goff = e->region_goff.as<int64_t>();
+    TA.M16 = e->M16.as<int16_t>(); TA.cov = e->cov.as<int32_t>(); TA.meta = e->meta.as<uint32_t>();
+    TA.dbg_counts = e->debug ? e->dbg.as<int32_t>() : nullptr;
+    TA.tile_nsites = e->tile_nsites.as<int32_t>(); TA.tile_nev = e->tile_nev.as<int32_t>();
+    TA.rare = e->rare.as<RareEv>(); TA.rare_n = reinterpret_cast<unsigned long long *>(sc + 2); TA.rare_cap = e->rare_cap;
+    TA.P = P;
+    const size_t tc_smem = NCNT * TILE * sizeof(int32_t) + TILE;
+    unsigned long long n_rare = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        k_tile_count<<<(unsigned) n_tiles, TC_THREADS, tc_smem, st>>>(TA);
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaMemcpyAsync(&n_rare, sc + 2, sizeof(n_rare), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (n_rare <= e->rare_cap) break;
+        // rare-event list overflowed: grow and recount (the counting itself is idempotent)
+        e->rare_cap = (size_t) n_rare + (size_t) n_rare / 4 + 1024;
+        PB_TRY(e->rare.reserve(sizeof(RareEv) * e->rare_cap));
+        TA.rare = e->rare.as<RareEv>(); TA.rare_cap = e->rare_cap;
+        PB_CUDA(cudaMemsetAsync(sc + 2, 0, sizeof(int64_t), st));
+    }
+    PB_CUDA(cudaEventRecord(e->evt[2], st));
+
+    k_scan_excl<<<1, 1024, 0, st>>>(e->tile_nsites.as<int32_t>(), e->tile_site_base.as<int64_t>(), n_tiles, sc + 0);
+    k_scan_excl<<<1, 1024, 0, st>>>(e->tile_nev.as<int32_t>(), e->tile_ev_base.as<int64_t>(), n_tiles, sc + 1);
+    int64_t hs[2] = {0, 0};
+    PB_CUDA(cudaMemcpyAsync(hs, sc, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_sites = hs[0], n_ev = hs[1];
+
+    e->last_goff = goff;
+    e->last_regions.assign(h_regions, h_regions + n_regions);
+    e->last_d_ref = d_ref;
+
+    int64_t n_cand = 0;
+    if (n_sites > 0) {
+        PB_TRY(e->site_g.reserve(sizeof(uint32_t) * n_sites));
+        PB_TRY(e->site_evoff.reserve(sizeof(int64_t) * (n_sites + 1)));
+        PB_TRY(e->site_cur.reserve(sizeof(uint32_t) * n_sites));
+        PB_TRY(e->site_ncand.reserve(sizeof(int32_t) * n_sites));
+        PB_TRY(e->site_region.reserve(sizeof(int32_t) * n_sites));
+        PB_TRY(e->site_candoff.reserve(sizeof(int64_t) * (n_sites + 1)));
+        PB_TRY(e->ev.reserve(sizeof(Ev) * (n_ev + 1)));
+        PB_TRY(e->cand_tmp.reserve(sizeof(Cand) * (n_ev + 1)));
+        PB_CUDA(cudaMemsetAsync(e->site_cur.p, 0, sizeof(uint32_t) * n_sites, st));
+
+        SiteArgs SA;
+        SA.regions = d_regions; SA.tile_region = TA.tile_region; SA.tile_x0 = TA.tile_x0; SA.region_goff = TA.region_goff;
+        SA.meta = TA.meta; SA.tile_site_base = e->tile_site_base.as<int64_t>(); SA.tile_ev_base = e->tile_ev_base.as<int64_t>();
+        SA.site_of = e->site_of.as<uint32_t>(); SA.site_g = e->site_g.as<uint32_t>(); SA.site_evoff = e->site_evoff.as<int64_t>();
+        SA.n_sites_total = n_sites; SA.n_ev_total = n_ev;
+        k_site_index<<<(unsigned) n_tiles, TILE, 0, st>>>(SA);
+        PB_CUDA(cudaEventRecord(e->evt[3], st));
+
+        CollectArgs CA;
+        CA.R = R; CA.regions = d_regions; CA.read_region = e->read_region.as<int32_t>(); CA.region_goff = TA.region_goff;
+        CA.op_ref = TA.op_ref; CA.op_rd = TA.op_rd; CA.meta = TA.meta; CA.site_of = SA.site_of; CA.site_evoff = SA.site_evoff;
+        CA.site_cur = e->site_cur.as<uint32_t>(); CA.ev = e->ev.as<Ev>(); CA.rare = e->rare.as<RareEv>(); CA.n_rare = n_rare;
+        CA.P = P;
+        if (n_reads > 0) k_collect_ops<<<(unsigned) ceil_div(n_reads, 8), 256, 0, st>>>(CA);
+        if (n_rare > 0) k_collect_rare<<<(unsigned) ceil_div((int64_t) n_rare, 256), 256, 0, st>>>(CA);
+
+        AlleleArgs AA;
+        AA.R = R; AA.regions = d_regions; AA.ref = d_ref; AA.region_goff = TA.region_goff; AA.n_regions = n_regions;
+        AA.site_g = SA.site_g; AA.site_evoff = SA.site_evoff; AA.M16 = TA.M16; AA.cov = TA.cov; AA.meta = TA.meta;
+        AA.ev = CA.ev; AA.cand_tmp = e->cand_tmp.as<Cand>(); AA.site_ncand = e->site_ncand.as<int32_t>();
+        AA.site_region = e->site_region.as<int32_t>(); AA.n_sites = n_sites; AA.P = P;
+        k_site_alleles<<<(unsigned) ceil_div(n_sites, 4), 128, 0, st>>>(AA);
+        k_scan_excl<<<1, 1024, 0, st>>>(AA.site_ncand, e->site_candoff.as<int64_t>(), n_sites, sc + 3);
+        PB_CUDA(cudaMemcpyAsync(&n_cand, sc + 3, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        PB_CUDA(cudaEventRecord(e->evt[4], st));
+
+        *n_out = n_cand;
+        if (n_cand > capacity) {
+            PB_CUDA(cudaEventRecord(e->evt[5], st));
+            set_error("candidate capacity %lld < %lld needed", (long long) capacity, (long long) n_cand);
+            return PB_ERR_CAPACITY;
+        }
+        if (n_cand > 0) {
+            WindowArgs WA;
+            WA.R = R; WA.regions = d_regions; WA.ref = d_ref; WA.region_goff = TA.region_goff; WA.site_g = SA.site_g;
+            WA.site_evoff = SA.site_evoff; WA.site_region = AA.site_region; WA.site_candoff = e->site_candoff.as<int64_t>();
+            WA.M16 = TA.M16; WA.cov = TA.cov; WA.cand_tmp = AA.cand_tmp; WA.n_sites = n_sites; WA.capacity = capacity;
+            WA.images = d_images; WA.positions = d_positions; WA.depths = d_depths; WA.freqs = d_freqs; WA.keys = d_keys;
+            WA.region_of = d_region_of;
+            k_windows<<<(unsigned) ceil_div(n_sites, 4), 128, 0, st>>>(WA);
+            if (d_n_per_region)
+                k_region_counts<<<(unsigned) ceil_div(n_cand, 256), 256, 0, st>>>(d_region_of, n_cand, d_n_per_region);
+        }
+        PB_CUDA(cudaEventRecord(e->evt[5], st));
+    } else {
+        PB_CUDA(cudaEventRecord(e->evt[3], st));
+        PB_CUDA(cudaEventRecord(e->evt[4], st));
+        PB_CUDA(cudaEventRecord(e->evt[5], st));
+    }
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 5; i++) cudaEventElapsedTime(&e->ms[i], e->evt[i], e->evt[i + 1]);
+    return PB_OK;
+}
+
+extern "C" int pb_variant_encoder_timings(pb_variant_encoder_t *e, float *ms5) {
+    if (!e || !ms5) return PB_ERR_ARG;
+    for (int i = 0; i < 5; i++) ms5[i] = e->ms[i];
+    return PB_OK;
+}
+
+namespace pb {
+int upload(DevBuf &b, const void *h, size_t bytes, cudaStream_t st) {
+    PB_TRY(b.reserve(bytes + 16));
+    if (bytes) PB_CUDA(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, st));
+    return PB_OK;
+}
+}  // namespace pb
+
+// shared with the polish encoder: copy a host read batch to device staging buffers
+namespace pb {
+int upload_reads(const pb_reads_t *h, DevBuf *const bufs[8], pb_reads_t *d, cudaStream_t st) {
+    const int64_t n = h->n_reads;
+    const int64_t nb = n ? h->seq_off[n] : 0, nc = n ? h->cigar_off[n] : 0;
+    PB_TRY(upload(*bufs[0], h->pos, sizeof(int64_t) * n, st));
+    PB_TRY(upload(*bufs[1], h->seq_off, sizeof(int64_t) * (n + 1), st));
+    PB_TRY(upload(*bufs[2], h->cigar_off, sizeof(int64_t) * (n + 1), st));
+    PB_TRY(upload(*bufs[3], h->flags, n, st));
+    PB_TRY(upload(*bufs[4], h->mapq, n, st));
+    PB_TRY(upload(*bufs[5], h->seq, (size_t) ((nb + 1) / 2), st));
+    PB_TRY(upload(*bufs[6], h->qual, (size_t) nb, st));
+    PB_TRY(upload(*bufs[7], h->cigar, sizeof(uint32_t) * nc, st));
+    d->n_reads = n;
+    d->pos = bufs[0]->as<int64_t>(); d->seq_off = bufs[1]->as<int64_t>(); d->cigar_off = bufs[2]->as<int64_t>();
+    d->flags = bufs[3]->as<uint8_t>(); d->mapq = bufs[4]->as<uint8_t>(); d->seq = bufs[5]->as<uint8_t>();
+    d->qual = bufs[6]->as<uint8_t>(); d->cigar = bufs[7]->as<uint32_t>();
+    return PB_OK;
+}
+}  // namespace pb
+
+extern "C" int pb_variant_encode_host(pb_variant_encoder_t *e, const pb_reads_t *h_reads, const pb_region_t *h_regions,
+                                      int64_t n_regions, const char *h_ref, int64_t ref_bytes,
+                                      const pb_variant_params_t *params, int64_t capacity, int8_t *h_images,
+                                      int64_t *h_positions, uint8_t *h_depths, uint8_t *h_freqs, char *h_keys,
+                                      int32_t *h_region_of, int64_t *h_n_per_region, int64_t *n_out, void *stream_) {
+    if (!e || !h_reads || !h_regions || !params || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t) stream_;
+    PB_CUDA(cudaSetDevice(e->device));
+    DevBuf *rb[8] = {&e->h_pos, &e->h_seq_off, &e->h_cigar_off, &e->h_flags, &e->h_mapq, &e->h_seq, &e->h_qual, &e->h_cigar};
+    pb_reads_t d;
+    int rc = upload_reads(h_reads, rb, &d, st);
+    if (rc != PB_OK) return rc;
+    PB_TRY(upload(e->h_regions, h_regions, sizeof(pb_region_t) * n_regions, st));
+    PB_TRY(upload(e->h_ref, h_ref, (size_t) ref_bytes, st));
+    const int64_t cap = std::max<int64_t>(capacity, 1);
+    PB_TRY(e->o_images.reserve((size_t) cap * 33 * 26));
+    PB_TRY(e->o_positions.reserve(sizeof(int64_t) * cap));
+    PB_TRY(e->o_depths.reserve(cap));
+    PB_TRY(e->o_freqs.reserve(cap));
+    PB_TRY(e->o_keys.reserve((size_t) cap * PB_ALLELE_STRIDE));
+    PB_TRY(e->o_region_of.reserve(sizeof(int32_t) * cap));
+    PB_TRY(e->o_per_region.reserve(sizeof(int64_t) * std::max<int64_t>(n_regions, 1)));
+    rc = pb_variant_encode_device(e, &d, e->h_regions.as<pb_region_t>(), n_regions, h_regions, e->h_ref.as<char>(), ref_bytes,
+                                  params, capacity, e->o_images.as<int8_t>(), e->o_positions.as<int64_t>(),
+                                  e->o_depths.as<uint8_t>(), e->o_freqs.as<uint8_t>(), e->o_keys.as<char>(),
+                                  e->o_region_of.as<int32_t>(), e->o_per_region.as<int64_t>(), n_out, stream_);
+    if (rc != PB_OK) return rc;
+    const int64_t n = *n_out;
+    if (n > 0) {
+        PB_CUDA(cudaMemcpyAsync(h_images, e->o_images.p, (size_t) n * 33 * 26, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_positions, e->o_positions.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_depths, e->o_depths.p, n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_freqs, e->o_freqs.p, n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_keys, e->o_keys.p, (size_t) n * PB_ALLELE_STRIDE, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_region_of, e->o_region_of.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_n_per_region && n_regions > 0)
+        PB_CUDA(cudaMemcpyAsync(h_n_per_region, e->o_per_region.p, sizeof(int64_t) * n_regions, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+extern "C" int pb_variant_encoder_debug_region(pb_variant_encoder_t *e, int64_t region, int32_t *h_matrix, int32_t *h_coverage,
+                                               int32_t *h_snp, int32_t *h_ins, int32_t *h_del) {
+    if (!e || region < 0 || region >= (int64_t) e->last_regions.size()) { set_error("bad region"); return PB_ERR_ARG; }
+    const pb_region_t &rg = e->last_regions[region];
+    const int64_t L1 = rg.ref_end - rg.ref_start + 1, g0 = e->last_goff[region];
+    std::vector<int16_t> m16((size_t) L1 * 16);
+    std::vector<char> ref((size_t) std::max<int64_t>(rg.ref_len, 1));
+    PB_CUDA(cudaMemcpy(m16.data(), e->M16.as<int16_t>() + g0 * 16, sizeof(int16_t) * 16 * L1, cudaMemcpyDeviceToHost));
+    if (rg.ref_len > 0) PB_CUDA(cudaMemcpy(ref.data(), e->last_d_ref + rg.ref_off, (size_t) rg.ref_len, cudaMemcpyDeviceToHost));
+    if (h_matrix) {
+        for (int64_t x = 0; x < L1; x++) {
+            int32_t *row = h_matrix + x * 26;
+            for (int j = 0; j < 26; j++) row[j] = 0;
+            char c = x < rg.ref_len ? ref[x] : '\0';
+            if (c >= 'a' && c <= 'z') c = (char) (c - 32);
+            row[0] = c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 3 : c == 'T' ? 4 : 5;
+            const int16_t *s = &m16[(size_t) x * 16];
+            row[4] = s[0]; row[15] = s[8];
+            for (int k = 0; k < 7; k++) { row[8 + k] = s[1 + k]; row[19 + k] = s[9 + k]; }
+            for (int j = 11; j < 25; j++) row[j] = row[j] >= 0 ? std::min(row[j], 125) : std::max(row[j], -125);
+        }
+    }
+    if (h_coverage) PB_CUDA(cudaMemcpy(h_coverage, e->cov.as<int32_t>() + g0, sizeof(int32_t) * L1, cudaMemcpyDeviceToHost));
+    if (h_snp || h_ins || h_del) {
+        if (!e->debug) { set_error("call pb_variant_encoder_set_debug(enc,1) before encoding to keep the count vectors"); return PB_ERR_STATE; }
+        std::vector<int32_t> d((size_t) L1 * 3);
+        PB_CUDA(cudaMemcpy(d.data(), e->dbg.as<int32_t>() + g0 * 3, sizeof(int32_t) * 3 * L1, cudaMemcpyDeviceToHost));
+        for (int64_t x = 0; x < L1; x++) {
+            if (h_snp) h_snp[x] = d[x * 3];
+            if (h_ins) h_ins[x] = d[x * 3 + 1];
+            if (h_del) h_del[x] = d[x * 3 + 2];
+        }
+    }
+    return PB_OK;
+}
