@@ -82,6 +82,45 @@ __device__ __forceinline__ int nt16_code_of_rank(int rank) {
 }
 __device__ __forceinline__ bool is_upper_acgt(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 __device__ __forceinline__ char to_upper(char c) { return (c >= 'a' && c <= 'z') ? (char) (c - 32) : c; }
+// ------------------------------------------------------------------ single-CTA exclusive scan (n <= a few 1e6)
+static __global__ void k_scan_excl(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n, int64_t *__restrict__ total) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry, s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (int) (blockDim.x >> 5);
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < n; b += blockDim.x) {
+        const int64_t i = b + tid;
+        const int64_t v = (i < n) ? (int64_t) in[i] : 0;
+        int64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int64_t w = (lane < nwarps) ? s_warp[lane] : 0;
+            int64_t winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t u = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += u;
+            }
+            s_warp[lane] = winc - w;
+            if (lane == 31) s_total = winc;
+        }
+        __syncthreads();
+        if (i < n) out[i] = s_carry + s_warp[warp] + inc - v;
+        __syncthreads();
+        if (tid == 0) s_carry += s_total;
+        __syncthreads();
+    }
+    if (tid == 0) { out[n] = s_carry; if (total) *total = s_carry; }
+}
+
 #endif
 
 }  // namespace pb

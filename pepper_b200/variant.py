@@ -123,3 +123,71 @@ class VariantEncoder:
         ms = (C.c_float * 5)()
         _lib.check(self.L.pb_variant_encoder_timings(self.h, ms), "timings")
         return dict(zip(("prefix", "count", "sites", "alleles", "windows"), [float(x) for x in ms]))
+
+
+def _state_arrays(L, state: dict, n_params: int, name_fn, numel_fn):
+    """state_dict (torch tensors or numpy arrays, optionally with the DataParallel 'module.' prefix the reference
+    strips in ModelHander.py:104-108) -> list of contiguous fp32 arrays in C-ABI order."""
+    arrs = []
+    for i in range(n_params):
+        name = name_fn(i).decode()
+        v = state.get(name, state.get("module." + name))
+        if v is None:
+            raise _lib.PepperB200Error(f"state_dict lacks parameter {name}")
+        if hasattr(v, "detach"):
+            v = v.detach().cpu().numpy()
+        a = np.ascontiguousarray(v, dtype=np.float32)
+        if a.size != numel_fn(i):
+            raise _lib.PepperB200Error(f"parameter {name} has {a.size} elements, expected {numel_fn(i)}")
+        arrs.append(a)
+    return arrs
+
+
+class VariantNet:
+    """bi-LSTM x2 + MLP head on one GPU (pb_variant_net_*)."""
+
+    def __init__(self, state: dict, device: int = 0):
+        _lib.require_gpu()
+        self.L = L = _lib.lib()
+        vp = C.c_void_p
+        L.pb_variant_net_param_name.restype = C.c_char_p
+        L.pb_variant_net_param_name.argtypes = [C.c_int]
+        L.pb_variant_net_param_numel.restype = C.c_int64
+        L.pb_variant_net_param_numel.argtypes = [C.c_int]
+        L.pb_variant_net_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp)]
+        L.pb_variant_net_destroy.argtypes = [vp]
+        L.pb_variant_net_forward_host.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
+        L.pb_variant_net_forward_device.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
+        L.pb_variant_net_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+        n = 28
+        arrs = _state_arrays(L, state, n, L.pb_variant_net_param_name, L.pb_variant_net_param_numel)
+        ptrs = (vp * n)(*[a.ctypes.data for a in arrs])
+        self.h = vp()
+        _lib.check(L.pb_variant_net_create(C.byref(self.h), device, ptrs), "pb_variant_net_create")
+
+    def close(self):
+        if self.h:
+            self.L.pb_variant_net_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def predict(self, images_i8: np.ndarray, return_hidden: bool = False, stream: int = 0):
+        """int8 [N,33,26] host -> float32 probs [N,3] host (== predict_distributed_gpu.py:58-70)."""
+        x = np.ascontiguousarray(images_i8, dtype=np.int8)
+        n = x.shape[0]
+        probs = np.empty((n, 3), dtype=np.float32)
+        hid = np.empty((n, WINDOW, 512), dtype=np.float32) if return_hidden else None
+        _lib.check(self.L.pb_variant_net_forward_host(self.h, x.ctypes.data, n, probs.ctypes.data,
+                                                     hid.ctypes.data if return_hidden else None, C.c_void_p(stream)),
+                   "pb_variant_net_forward_host")
+        return (probs, hid) if return_hidden else probs
+
+    def launches(self) -> int:
+        n = C.c_int64(0)
+        _lib.check(self.L.pb_variant_net_launches(self.h, C.byref(n)), "launches")
+        return int(n.value)
