@@ -159,6 +159,8 @@ int pb_variant_encoder_debug_region(pb_variant_encoder_t *enc, int64_t region,
 /* per-kernel device time (ms) of the last encode call, measured with CUDA
  * events on the call's stream: [prefix, count, sites, alleles, windows]      */
 int pb_variant_encoder_timings(pb_variant_encoder_t *enc, float *ms5);
+/* kernels launched by the last encode call */
+int pb_variant_encoder_launches(pb_variant_encoder_t *enc, int64_t *n_launches);
 
 /* ------------------------------------------------------------------------
  * Polish encoder.  Replaces
@@ -239,6 +241,61 @@ int pb_polish_net_forward_host(pb_polish_net_t *net, const uint8_t *h_images,
                                int64_t n, uint8_t *h_bases, uint8_t *h_phred,
                                float *h_hidden_dbg, float *h_acc_dbg, void *stream);
 int pb_polish_net_launches(pb_polish_net_t *net, int64_t *n_launches);
+
+/* ------------------------------------------------------------------------
+ * Fused make_images + run_inference for the variant path: what
+ * `pepper_variant call_variant` does between the BAM and the prediction HDF5
+ * (CallVariant.py:12 steps 1+2) without the image HDF5 round trip.
+ * Host entry point: H2D of the reads, encode, network, D2H of the candidate
+ * records and probabilities (h_images may be NULL to skip the image copy).
+ * Device entry point: everything already / still in HBM.
+ * ---------------------------------------------------------------------- */
+int pb_variant_call_host(pb_variant_encoder_t *enc, pb_variant_net_t *net,
+                         const pb_reads_t *h_reads,
+                         const pb_region_t *h_regions, int64_t n_regions,
+                         const char *h_ref, int64_t ref_bytes,
+                         const pb_variant_params_t *params, int64_t capacity,
+                         int8_t *h_images /* optional */, int64_t *h_positions,
+                         uint8_t *h_depths, uint8_t *h_freqs, char *h_keys,
+                         int32_t *h_region_of, float *h_probs /* [cap][3] */,
+                         int64_t *n_out, void *stream);
+int pb_variant_call_device(pb_variant_encoder_t *enc, pb_variant_net_t *net,
+                           const pb_reads_t *d_reads,
+                           const pb_region_t *d_regions, int64_t n_regions,
+                           const pb_region_t *h_regions,
+                           const char *d_ref, int64_t ref_bytes,
+                           const pb_variant_params_t *params, int64_t capacity,
+                           int8_t *d_images, int64_t *d_positions,
+                           uint8_t *d_depths, uint8_t *d_freqs, char *d_keys,
+                           int32_t *d_region_of, float *d_probs,
+                           int64_t *n_out, void *stream);
+
+/* Fused make_images + call_consensus for the polish path (polish.py:14 steps
+ * 1+2): encode, chunk into 1000-column images with 50 overlap
+ * (AlignmentSummarizer.py:19-56) on the device, run the network.
+ *   h_bases / h_phred  uint8 [cap_images][1000]
+ *   h_position int64 [cap_images][1000], h_index int32 [cap_images][1000]  ((-1,-1) padding)
+ *   h_image_region int32 [cap_images], h_chunk_id int32 [cap_images]        */
+int pb_polish_call_host(pb_polish_encoder_t *enc, pb_polish_net_t *net,
+                        const pb_reads_t *h_reads,
+                        const pb_region_t *h_regions, int64_t n_regions,
+                        int64_t capacity_images,
+                        uint8_t *h_bases, uint8_t *h_phred,
+                        int64_t *h_position, int32_t *h_index,
+                        int32_t *h_image_region, int32_t *h_chunk_id,
+                        int64_t *n_images_out, void *stream);
+int pb_polish_call_device(pb_polish_encoder_t *enc, pb_polish_net_t *net,
+                          const pb_reads_t *d_reads,
+                          const pb_region_t *d_regions, int64_t n_regions,
+                          const pb_region_t *h_regions,
+                          int64_t capacity_images,
+                          uint8_t *d_bases, uint8_t *d_phred,
+                          int64_t *d_position, int32_t *d_index,
+                          int32_t *d_image_region, int32_t *d_chunk_id,
+                          int64_t *n_images_out, void *stream);
+/* device time (ms) of the last pb_*_call_*: [encode, network] */
+int pb_variant_call_timings(pb_variant_encoder_t *enc, float *ms2);
+int pb_polish_call_timings(pb_polish_encoder_t *enc, float *ms2);
 
 #ifdef __cplusplus
 }

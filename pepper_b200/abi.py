@@ -45,7 +45,9 @@ def _c(a: np.ndarray, dtype) -> np.ndarray:
 class HostReads:
     """Keeps the numpy arrays alive and exposes a pb_reads_t pointing at them."""
 
-    def __init__(self, b: ReadBatch):
+    def __init__(self, b: ReadBatch, pin: bool = False):
+        self._pin = pin
+        self._pinned = []
         self.pos = _c(b.pos, np.int64)
         self.seq_off = _c(b.seq_off, np.int64)
         self.cigar_off = _c(b.cigar_off, np.int64)
@@ -57,6 +59,17 @@ class HostReads:
         self.cigar = _c(np.concatenate([b.cigar, np.zeros(1, np.uint32)]), np.uint32)
         self.n_bases = int(b.seq_off[-1])
         self.n_ops = int(b.cigar_off[-1])
+        if pin:
+            # page-locked copies (torch is used only as the pinned allocator)
+            import torch
+            for name in ("pos", "seq_off", "cigar_off", "flags", "mapq", "seq", "qual", "cigar"):
+                a = getattr(self, name)
+                src = a.view(np.int32) if a.dtype == np.uint32 else a
+                t = torch.from_numpy(src).pin_memory()
+                self._pinned.append(t)
+                v = t.numpy()
+                setattr(self, name, v.view(np.uint32) if a.dtype == np.uint32 else v)
+        self.nbytes = sum(getattr(self, n).nbytes for n in ("pos", "seq_off", "cigar_off", "flags", "mapq", "seq", "qual", "cigar"))
         self.struct = PbReads(b.n_reads, self.pos.ctypes.data, self.seq_off.ctypes.data,
                               self.cigar_off.ctypes.data, self.flags.ctypes.data, self.mapq.ctypes.data,
                               self.seq.ctypes.data, self.qual.ctypes.data, self.cigar.ctypes.data)

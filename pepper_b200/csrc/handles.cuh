@@ -1,0 +1,67 @@
+// Opaque handle layouts shared by the translation units of libpepper_b200.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace pb {
+struct DevRnn { DevBuf W, bias; int K0, K0p, K1, Kp, H; };
+struct DevLin { DevBuf W, bias; int N, K, Kp; };
+}  // namespace pb
+
+struct pb_variant_encoder {
+    int device = 0;
+    pb::DevBuf op_ref, op_rd, read_reflen, read_region, tile_region, tile_x0, region_goff, M16, cov, meta, dbg,
+        tile_nsites, tile_nev, tile_site_base, tile_ev_base, site_of, site_g, site_evoff, site_cur, ev, cand_tmp,
+        site_ncand, site_region, site_candoff, rare, scalars;
+    // host-entry staging
+    pb::DevBuf h_pos, h_seq_off, h_cigar_off, h_flags, h_mapq, h_seq, h_qual, h_cigar, h_regions, h_ref;
+    pb::DevBuf o_images, o_positions, o_depths, o_freqs, o_keys, o_region_of, o_per_region;
+    cudaEvent_t evt[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float ms[5] = {0, 0, 0, 0, 0};
+    bool debug = false;
+    // last-call bookkeeping for the debug read-back
+    std::vector<int64_t> last_goff;
+    std::vector<pb_region_t> last_regions;
+    const char *last_d_ref = nullptr;
+    size_t rare_cap = 1 << 20;
+    // fused call scratch (pipeline.cu)
+    pb::DevBuf p_images, p_positions, p_depths, p_freqs, p_keys, p_region_of, p_probs, p_per_region;
+    cudaEvent_t pevt[3] = {nullptr, nullptr, nullptr};
+    float pms[2] = {0, 0};
+    int64_t launches = 0;
+};
+
+struct pb_polish_encoder {
+    int device = 0;
+    pb::DevBuf op_ref, op_rd, read_reflen, read_region, tile_region, tile_x0, region_goff, basecnt, cov, longest, tile_ncols,
+        tile_col_base, col_of, inscnt, scalars;
+    pb::DevBuf h_pos, h_seq_off, h_cigar_off, h_flags, h_mapq, h_seq, h_qual, h_cigar, h_regions;
+    pb::DevBuf o_image, o_pos, o_idx, o_col_off;
+    cudaEvent_t evt[4] = {nullptr, nullptr, nullptr, nullptr};
+    float ms[3] = {0, 0, 0};
+    // fused call scratch (pipeline.cu)
+    pb::DevBuf p_image, p_pos, p_idx, p_col_off, p_chunks, p_imgs, p_position, p_index, p_bases, p_phred, p_iregion, p_cid;
+    cudaEvent_t pevt[3] = {nullptr, nullptr, nullptr};
+    float pms[2] = {0, 0};
+    int64_t launches = 0;
+};
+
+struct pb_variant_net {
+    int device = 0;
+    int mode = 0;
+    pb::DevRnn enc[2], dec[2];
+    pb::DevLin lin[5], outl;
+    // scratch for one chunk
+    int64_t chunk = 0;
+    pb::DevBuf h[2], c, yenc, ydec, l[2], img, probs;
+    int64_t launches = 0;
+};
+
+struct pb_polish_net {
+    int device = 0;
+    pb::DevRnn enc[2], dec[2];
+    pb::DevBuf dW, dB;
+    int64_t chunk = 0;
+    pb::DevBuf h[2], yenc, ydec, acc, img, bases, phred;
+    int64_t launches = 0;
+};

@@ -12,7 +12,7 @@
 //  * the MLP head is the same GEMM with a bias+SELU epilogue; 512->3 + softmax is a warp-per-row kernel;
 //  * polish: Linear(256->5) + softmax + window accumulate is one warp-per-column kernel per window, argmax +
 //    phred one kernel at the end (predict_distributed_cpu.py:77-90).
-#include "common.cuh"
+#include "handles.cuh"
 #include <vector>
 #include <algorithm>
 #include <math.h>
@@ -308,8 +308,6 @@ static PackedRnn pack_gru(const float *w_ih, const float *w_hh, const float *b_i
     return P;
 }
 
-struct DevRnn { DevBuf W, bias; int K0, K0p, K1, Kp, H; };
-struct DevLin { DevBuf W, bias; int N, K, Kp; };
 
 static int upload_rnn(DevRnn &d, const PackedRnn &p) {
     d.K0 = p.K0; d.K0p = p.K0p; d.K1 = p.K1; d.Kp = p.Kp; d.H = p.H;
@@ -358,16 +356,6 @@ static const int64_t VARIANT_NUMEL[PB_VARIANT_NET_N_PARAMS] = {
 extern "C" const char *pb_variant_net_param_name(int i) { return (i >= 0 && i < PB_VARIANT_NET_N_PARAMS) ? VARIANT_PARAMS[i] : nullptr; }
 extern "C" int64_t pb_variant_net_param_numel(int i) { return (i >= 0 && i < PB_VARIANT_NET_N_PARAMS) ? VARIANT_NUMEL[i] : -1; }
 
-struct pb_variant_net {
-    int device = 0;
-    int mode = 0;
-    DevRnn enc[2], dec[2];
-    DevLin lin[5], outl;
-    // scratch for one chunk
-    int64_t chunk = 0;
-    DevBuf h[2], c, yenc, ydec, l[2], img, probs;
-    int64_t launches = 0;
-};
 
 constexpr int VT = 33, VH = 256;
 constexpr int64_t VARIANT_CHUNK = 8192;
@@ -532,14 +520,6 @@ extern "C" int64_t pb_polish_net_param_numel(int i) { return (i >= 0 && i < PB_P
 constexpr int PH = 128, PWIN = 100, PJUMP = 50, PSEQ = 1000, PNWIN = 19;
 constexpr int64_t POLISH_CHUNK = 8192;
 
-struct pb_polish_net {
-    int device = 0;
-    DevRnn enc[2], dec[2];
-    DevBuf dW, dB;
-    int64_t chunk = 0;
-    DevBuf h[2], yenc, ydec, acc, img, bases, phred;
-    int64_t launches = 0;
-};
 
 extern "C" int pb_polish_net_create(pb_polish_net_t **out, int device, const float *const *P) {
     if (!out || !P) { set_error("null argument"); return PB_ERR_ARG; }

@@ -1,0 +1,206 @@
+// Fused make_images + inference entry points (the path `pepper_variant call_variant` steps 1+2 and
+// `pepper polish` steps 1+2 take, without the intermediate image HDF5 files): encoder output stays in HBM and
+// feeds the network directly.
+#include "handles.cuh"
+#include <algorithm>
+
+using namespace pb;
+
+namespace pb {
+
+// AlignmentSummarizer.chunk_images (pepper AlignmentSummarizer.py:19-56) on the device:
+// image k = columns [start, start+nvalid) of its region, zero padded to 1000, positions padded with (-1,-1)
+struct ChunkRow { int64_t col_start; int32_t nvalid; int32_t region; int32_t chunk_id; int32_t pad; };
+
+__global__ void k_polish_chunk(const ChunkRow *__restrict__ rows, const uint8_t *__restrict__ image, const int64_t *__restrict__ pos,
+                               const int32_t *__restrict__ idx, uint8_t *__restrict__ imgs, int64_t *__restrict__ position,
+                               int32_t *__restrict__ index, int32_t *__restrict__ iregion, int32_t *__restrict__ cid) {
+    const int64_t k = blockIdx.x;
+    const ChunkRow r = rows[k];
+    for (int i = threadIdx.x; i < PB_POLISH_SEQ_LEN * PB_POLISH_FEATURES; i += blockDim.x) {
+        const int c = i / PB_POLISH_FEATURES;
+        imgs[k * PB_POLISH_SEQ_LEN * PB_POLISH_FEATURES + i] = (c < r.nvalid) ? image[(r.col_start + c) * PB_POLISH_FEATURES + (i - c * PB_POLISH_FEATURES)] : 0;
+    }
+    for (int c = threadIdx.x; c < PB_POLISH_SEQ_LEN; c += blockDim.x) {
+        position[k * PB_POLISH_SEQ_LEN + c] = (c < r.nvalid) ? pos[r.col_start + c] : -1;
+        index[k * PB_POLISH_SEQ_LEN + c] = (c < r.nvalid) ? idx[r.col_start + c] : -1;
+    }
+    if (threadIdx.x == 0) { iregion[k] = r.region; cid[k] = r.chunk_id; }
+}
+
+}  // namespace pb
+
+static int ensure_events(cudaEvent_t *ev, int n) {
+    for (int i = 0; i < n; i++) if (!ev[i]) PB_CUDA(cudaEventCreate(&ev[i]));
+    return PB_OK;
+}
+
+extern "C" int pb_variant_call_device(pb_variant_encoder_t *enc, pb_variant_net_t *net, const pb_reads_t *d_reads,
+                                      const pb_region_t *d_regions, int64_t n_regions, const pb_region_t *h_regions,
+                                      const char *d_ref, int64_t ref_bytes, const pb_variant_params_t *params,
+                                      int64_t capacity, int8_t *d_images, int64_t *d_positions, uint8_t *d_depths,
+                                      uint8_t *d_freqs, char *d_keys, int32_t *d_region_of, float *d_probs,
+                                      int64_t *n_out, void *stream_) {
+    if (!enc || !net) { set_error("null handle"); return PB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t) stream_;
+    PB_TRY(ensure_events(enc->pevt, 3));
+    PB_CUDA(cudaEventRecord(enc->pevt[0], st));
+    PB_TRY(pb_variant_encode_device(enc, d_reads, d_regions, n_regions, h_regions, d_ref, ref_bytes, params, capacity,
+                                    d_images, d_positions, d_depths, d_freqs, d_keys, d_region_of, nullptr, n_out, stream_));
+    PB_CUDA(cudaEventRecord(enc->pevt[1], st));
+    PB_TRY(pb_variant_net_forward_device(net, d_images, *n_out, d_probs, nullptr, stream_));
+    PB_CUDA(cudaEventRecord(enc->pevt[2], st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&enc->pms[0], enc->pevt[0], enc->pevt[1]);
+    cudaEventElapsedTime(&enc->pms[1], enc->pevt[1], enc->pevt[2]);
+    return PB_OK;
+}
+
+extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *net, const pb_reads_t *h_reads,
+                                    const pb_region_t *h_regions, int64_t n_regions, const char *h_ref, int64_t ref_bytes,
+                                    const pb_variant_params_t *params, int64_t capacity, int8_t *h_images,
+                                    int64_t *h_positions, uint8_t *h_depths, uint8_t *h_freqs, char *h_keys,
+                                    int32_t *h_region_of, float *h_probs, int64_t *n_out, void *stream_) {
+    if (!e || !net || !h_reads || !h_regions || !params || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t) stream_;
+    PB_CUDA(cudaSetDevice(e->device));
+    DevBuf *rb[8] = {&e->h_pos, &e->h_seq_off, &e->h_cigar_off, &e->h_flags, &e->h_mapq, &e->h_seq, &e->h_qual, &e->h_cigar};
+    pb_reads_t d;
+    PB_TRY(upload_reads(h_reads, rb, &d, st));
+    PB_TRY(upload(e->h_regions, h_regions, sizeof(pb_region_t) * n_regions, st));
+    PB_TRY(upload(e->h_ref, h_ref, (size_t) ref_bytes, st));
+    const int64_t cap = std::max<int64_t>(capacity, 1);
+    PB_TRY(e->p_images.reserve((size_t) cap * 33 * 26));
+    PB_TRY(e->p_positions.reserve(sizeof(int64_t) * cap));
+    PB_TRY(e->p_depths.reserve(cap));
+    PB_TRY(e->p_freqs.reserve(cap));
+    PB_TRY(e->p_keys.reserve((size_t) cap * PB_ALLELE_STRIDE));
+    PB_TRY(e->p_region_of.reserve(sizeof(int32_t) * cap));
+    PB_TRY(e->p_probs.reserve(sizeof(float) * 3 * cap));
+    PB_TRY(pb_variant_call_device(e, net, &d, e->h_regions.as<pb_region_t>(), n_regions, h_regions, e->h_ref.as<char>(), ref_bytes,
+                                  params, capacity, e->p_images.as<int8_t>(), e->p_positions.as<int64_t>(), e->p_depths.as<uint8_t>(),
+                                  e->p_freqs.as<uint8_t>(), e->p_keys.as<char>(), e->p_region_of.as<int32_t>(), e->p_probs.as<float>(),
+                                  n_out, stream_));
+    const int64_t n = *n_out;
+    if (n > 0) {
+        if (h_images) PB_CUDA(cudaMemcpyAsync(h_images, e->p_images.p, (size_t) n * 33 * 26, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_positions, e->p_positions.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_depths, e->p_depths.p, n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_freqs, e->p_freqs.p, n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_keys, e->p_keys.p, (size_t) n * PB_ALLELE_STRIDE, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_region_of, e->p_region_of.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_probs, e->p_probs.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+    }
+    PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+extern "C" int pb_variant_call_timings(pb_variant_encoder_t *e, float *ms2) {
+    if (!e || !ms2) return PB_ERR_ARG;
+    ms2[0] = e->pms[0]; ms2[1] = e->pms[1];
+    return PB_OK;
+}
+
+extern "C" int pb_polish_call_device(pb_polish_encoder_t *e, pb_polish_net_t *net, const pb_reads_t *d_reads,
+                                     const pb_region_t *d_regions, int64_t n_regions, const pb_region_t *h_regions,
+                                     int64_t capacity_images, uint8_t *d_bases, uint8_t *d_phred, int64_t *d_position,
+                                     int32_t *d_index, int32_t *d_image_region, int32_t *d_chunk_id, int64_t *n_images_out,
+                                     void *stream_) {
+    if (!e || !net || !n_images_out) { set_error("null argument"); return PB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t) stream_;
+    PB_TRY(ensure_events(e->pevt, 3));
+    PB_CUDA(cudaEventRecord(e->pevt[0], st));
+    *n_images_out = 0;
+    // encode into library scratch; column capacity: positions + generous insert allowance, retried on demand
+    int64_t span = 0;
+    for (int64_t r = 0; r < n_regions; r++) span += h_regions[r].ref_end - h_regions[r].ref_start + 1;
+    int64_t cap_cols = 2 * span + 1024, n_cols = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        PB_TRY(e->p_image.reserve((size_t) cap_cols * 10));
+        PB_TRY(e->p_pos.reserve(sizeof(int64_t) * cap_cols));
+        PB_TRY(e->p_idx.reserve(sizeof(int32_t) * cap_cols));
+        PB_TRY(e->p_col_off.reserve(sizeof(int64_t) * (n_regions + 1)));
+        int rc = pb_polish_encode_device(e, d_reads, d_regions, n_regions, h_regions, cap_cols, e->p_image.as<uint8_t>(),
+                                         e->p_pos.as<int64_t>(), e->p_idx.as<int32_t>(), e->p_col_off.as<int64_t>(), &n_cols, stream_);
+        if (rc == PB_ERR_CAPACITY && attempt == 0) { cap_cols = n_cols + 16; continue; }
+        if (rc != PB_OK) return rc;
+        break;
+    }
+    std::vector<int64_t> col_off((size_t) n_regions + 1, 0);
+    if (n_regions > 0) PB_CUDA(cudaMemcpyAsync(col_off.data(), e->p_col_off.p, sizeof(int64_t) * (n_regions + 1), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    std::vector<ChunkRow> rows;
+    for (int64_t r = 0; r < n_regions; r++) {
+        const int64_t n = col_off[r + 1] - col_off[r];
+        int64_t start = 0, end = std::min<int64_t>(n, PB_POLISH_SEQ_LEN);
+        int cid = 0;
+        while (true) {
+            ChunkRow c; c.col_start = col_off[r] + start; c.nvalid = (int32_t) (end - start); c.region = (int32_t) r; c.chunk_id = cid++; c.pad = 0;
+            rows.push_back(c);
+            if (end == n) break;
+            start = end - 50;                                                  // SEQ_OVERLAP
+            end = std::min<int64_t>(n, start + PB_POLISH_SEQ_LEN);
+        }
+    }
+    const int64_t n_img = (int64_t) rows.size();
+    *n_images_out = n_img;
+    if (n_img > capacity_images) {
+        set_error("image capacity %lld < %lld needed", (long long) capacity_images, (long long) n_img);
+        return PB_ERR_CAPACITY;
+    }
+    if (n_img > 0) {
+        PB_TRY(upload(e->p_chunks, rows.data(), sizeof(ChunkRow) * n_img, st));
+        PB_TRY(e->p_imgs.reserve((size_t) n_img * PB_POLISH_SEQ_LEN * PB_POLISH_FEATURES));
+        k_polish_chunk<<<(unsigned) n_img, 256, 0, st>>>(e->p_chunks.as<ChunkRow>(), e->p_image.as<uint8_t>(), e->p_pos.as<int64_t>(),
+                                                        e->p_idx.as<int32_t>(), e->p_imgs.as<uint8_t>(), d_position, d_index,
+                                                        d_image_region, d_chunk_id);
+        PB_CUDA(cudaGetLastError());
+    }
+    PB_CUDA(cudaEventRecord(e->pevt[1], st));
+    if (n_img > 0) PB_TRY(pb_polish_net_forward_device(net, e->p_imgs.as<uint8_t>(), n_img, d_bases, d_phred, nullptr, nullptr, stream_));
+    PB_CUDA(cudaEventRecord(e->pevt[2], st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&e->pms[0], e->pevt[0], e->pevt[1]);
+    cudaEventElapsedTime(&e->pms[1], e->pevt[1], e->pevt[2]);
+    return PB_OK;
+}
+
+extern "C" int pb_polish_call_host(pb_polish_encoder_t *e, pb_polish_net_t *net, const pb_reads_t *h_reads,
+                                   const pb_region_t *h_regions, int64_t n_regions, int64_t capacity_images, uint8_t *h_bases,
+                                   uint8_t *h_phred, int64_t *h_position, int32_t *h_index, int32_t *h_image_region,
+                                   int32_t *h_chunk_id, int64_t *n_images_out, void *stream_) {
+    if (!e || !net || !h_reads || !h_regions || !n_images_out) { set_error("null argument"); return PB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t) stream_;
+    PB_CUDA(cudaSetDevice(e->device));
+    DevBuf *rb[8] = {&e->h_pos, &e->h_seq_off, &e->h_cigar_off, &e->h_flags, &e->h_mapq, &e->h_seq, &e->h_qual, &e->h_cigar};
+    pb_reads_t d;
+    PB_TRY(upload_reads(h_reads, rb, &d, st));
+    PB_TRY(upload(e->h_regions, h_regions, sizeof(pb_region_t) * n_regions, st));
+    const int64_t cap = std::max<int64_t>(capacity_images, 1);
+    PB_TRY(e->p_bases.reserve((size_t) cap * PB_POLISH_SEQ_LEN));
+    PB_TRY(e->p_phred.reserve((size_t) cap * PB_POLISH_SEQ_LEN));
+    PB_TRY(e->p_position.reserve(sizeof(int64_t) * cap * PB_POLISH_SEQ_LEN));
+    PB_TRY(e->p_index.reserve(sizeof(int32_t) * cap * PB_POLISH_SEQ_LEN));
+    PB_TRY(e->p_iregion.reserve(sizeof(int32_t) * cap));
+    PB_TRY(e->p_cid.reserve(sizeof(int32_t) * cap));
+    PB_TRY(pb_polish_call_device(e, net, &d, e->h_regions.as<pb_region_t>(), n_regions, h_regions, capacity_images,
+                                 e->p_bases.as<uint8_t>(), e->p_phred.as<uint8_t>(), e->p_position.as<int64_t>(),
+                                 e->p_index.as<int32_t>(), e->p_iregion.as<int32_t>(), e->p_cid.as<int32_t>(), n_images_out, stream_));
+    const int64_t n = *n_images_out;
+    if (n > 0) {
+        PB_CUDA(cudaMemcpyAsync(h_bases, e->p_bases.p, (size_t) n * PB_POLISH_SEQ_LEN, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_phred, e->p_phred.p, (size_t) n * PB_POLISH_SEQ_LEN, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_position, e->p_position.p, sizeof(int64_t) * n * PB_POLISH_SEQ_LEN, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_index, e->p_index.p, sizeof(int32_t) * n * PB_POLISH_SEQ_LEN, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_image_region, e->p_iregion.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_chunk_id, e->p_cid.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    }
+    PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+extern "C" int pb_polish_call_timings(pb_polish_encoder_t *e, float *ms2) {
+    if (!e || !ms2) return PB_ERR_ARG;
+    ms2[0] = e->pms[0]; ms2[1] = e->pms[1];
+    return PB_OK;
+}

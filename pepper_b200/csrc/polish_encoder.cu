@@ -13,7 +13,7 @@
 //                     genomic_pos (:381-388)
 //   k_polish_inserts  one warp per read: insert bases -> int32 counters indexed by output column
 //   k_polish_image    per column: (uint8)(int)((count / max(1.0, coverage)) * 254) in fp64 (:281,:295)
-#include "common.cuh"
+#include "handles.cuh"
 #include <vector>
 #include <algorithm>
 
@@ -344,15 +344,6 @@ __global__ void k_polish_image(PImgArgs A) {
 
 using namespace pb;
 
-struct pb_polish_encoder {
-    int device = 0;
-    DevBuf op_ref, op_rd, read_reflen, read_region, tile_region, tile_x0, region_goff, basecnt, cov, longest, tile_ncols,
-        tile_col_base, col_of, inscnt, scalars;
-    DevBuf h_pos, h_seq_off, h_cigar_off, h_flags, h_mapq, h_seq, h_qual, h_cigar, h_regions;
-    DevBuf o_image, o_pos, o_idx, o_col_off;
-    cudaEvent_t evt[4] = {nullptr, nullptr, nullptr, nullptr};
-    float ms[3] = {0, 0, 0};
-};
 
 extern "C" int pb_polish_encoder_create(pb_polish_encoder_t **out, int device) {
     if (!out) { set_error("null out"); return PB_ERR_ARG; }
@@ -374,9 +365,12 @@ extern "C" int pb_polish_encoder_destroy(pb_polish_encoder_t *e) {
     DevBuf *bufs[] = {&e->op_ref, &e->op_rd, &e->read_reflen, &e->read_region, &e->tile_region, &e->tile_x0, &e->region_goff,
                       &e->basecnt, &e->cov, &e->longest, &e->tile_ncols, &e->tile_col_base, &e->col_of, &e->inscnt, &e->scalars,
                       &e->h_pos, &e->h_seq_off, &e->h_cigar_off, &e->h_flags, &e->h_mapq, &e->h_seq, &e->h_qual, &e->h_cigar,
-                      &e->h_regions, &e->o_image, &e->o_pos, &e->o_idx, &e->o_col_off};
+                      &e->h_regions, &e->o_image, &e->o_pos, &e->o_idx, &e->o_col_off, &e->p_image, &e->p_pos, &e->p_idx,
+                      &e->p_col_off, &e->p_chunks, &e->p_imgs, &e->p_position, &e->p_index, &e->p_bases, &e->p_phred, &e->p_iregion,
+                      &e->p_cid};
     for (auto *b : bufs) b->release();
     for (auto &ev : e->evt) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->pevt) if (ev) cudaEventDestroy(ev);
     delete e;
     return PB_OK;
 }

@@ -18,7 +18,7 @@
 //
 // Only columns 4, 8-15, 19-25 of the 26 are ever non-zero in the base matrix (col 0 is the reference
 // code, the rest are written by the per-candidate overlay), so 16 int16 are stored per position.
-#include "common.cuh"
+#include "handles.cuh"
 #include <vector>
 #include <algorithm>
 
@@ -818,23 +818,6 @@ __global__ void k_region_counts(const int32_t *__restrict__ region_of, int64_t n
 // =====================================================================================================
 using namespace pb;
 
-struct pb_variant_encoder {
-    int device = 0;
-    DevBuf op_ref, op_rd, read_reflen, read_region, tile_region, tile_x0, region_goff, M16, cov, meta, dbg,
-        tile_nsites, tile_nev, tile_site_base, tile_ev_base, site_of, site_g, site_evoff, site_cur, ev, cand_tmp,
-        site_ncand, site_region, site_candoff, rare, scalars;
-    // host-entry staging
-    DevBuf h_pos, h_seq_off, h_cigar_off, h_flags, h_mapq, h_seq, h_qual, h_cigar, h_regions, h_ref;
-    DevBuf o_images, o_positions, o_depths, o_freqs, o_keys, o_region_of, o_per_region;
-    cudaEvent_t evt[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float ms[5] = {0, 0, 0, 0, 0};
-    bool debug = false;
-    // last-call bookkeeping for the debug read-back
-    std::vector<int64_t> last_goff;
-    std::vector<pb_region_t> last_regions;
-    const char *last_d_ref = nullptr;
-    size_t rare_cap = 1 << 20;
-};
 
 extern "C" int pb_variant_encoder_create(pb_variant_encoder_t **out, int device) {
     if (!out) { set_error("null out"); return PB_ERR_ARG; }
@@ -861,9 +844,11 @@ extern "C" int pb_variant_encoder_destroy(pb_variant_encoder_t *e) {
                       &e->site_ncand, &e->site_region, &e->site_candoff, &e->rare, &e->scalars,
                       &e->h_pos, &e->h_seq_off, &e->h_cigar_off, &e->h_flags, &e->h_mapq, &e->h_seq, &e->h_qual,
                       &e->h_cigar, &e->h_regions, &e->h_ref, &e->o_images, &e->o_positions, &e->o_depths, &e->o_freqs,
-                      &e->o_keys, &e->o_region_of, &e->o_per_region};
+                      &e->o_keys, &e->o_region_of, &e->o_per_region, &e->p_images, &e->p_positions, &e->p_depths, &e->p_freqs,
+                      &e->p_keys, &e->p_region_of, &e->p_probs, &e->p_per_region};
     for (auto *b : bufs) b->release();
     for (auto &ev : e->evt) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->pevt) if (ev) cudaEventDestroy(ev);
     delete e;
     return PB_OK;
 }
@@ -905,6 +890,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
     if (d_n_per_region && n_regions > 0) PB_CUDA(cudaMemsetAsync(d_n_per_region, 0, sizeof(int64_t) * n_regions, st));
     if (n_regions <= 0) return PB_OK;
     const VParams P = make_params(params);
+    e->launches = 0;
 
     // ---- host-side tables: tiles, global position offsets, read -> region
     const int64_t n_reads = dr->n_reads;
@@ -965,6 +951,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
         const int wpb = 8;
         k_cigar_prefix<<<(unsigned) ceil_div(n_reads, wpb), wpb * 32, 0, st>>>(R, e->op_ref.as<int32_t>(), e->op_rd.as<int32_t>(),
                                                                               e->read_reflen.as<int32_t>());
+        e->launches++;
     }
     PB_CUDA(cudaEventRecord(e->evt[1], st));
 
@@ -982,6 +969,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
     unsigned long long n_rare = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         k_tile_count<<<(unsigned) n_tiles, TC_THREADS, tc_smem, st>>>(TA);
+        e->launches++;
         PB_CUDA(cudaGetLastError());
         PB_CUDA(cudaMemcpyAsync(&n_rare, sc + 2, sizeof(n_rare), cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
@@ -996,6 +984,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
 
     k_scan_excl<<<1, 1024, 0, st>>>(e->tile_nsites.as<int32_t>(), e->tile_site_base.as<int64_t>(), n_tiles, sc + 0);
     k_scan_excl<<<1, 1024, 0, st>>>(e->tile_nev.as<int32_t>(), e->tile_ev_base.as<int64_t>(), n_tiles, sc + 1);
+    e->launches += 2;
     int64_t hs[2] = {0, 0};
     PB_CUDA(cudaMemcpyAsync(hs, sc, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
@@ -1023,6 +1012,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
         SA.site_of = e->site_of.as<uint32_t>(); SA.site_g = e->site_g.as<uint32_t>(); SA.site_evoff = e->site_evoff.as<int64_t>();
         SA.n_sites_total = n_sites; SA.n_ev_total = n_ev;
         k_site_index<<<(unsigned) n_tiles, TILE, 0, st>>>(SA);
+        e->launches++;
         PB_CUDA(cudaEventRecord(e->evt[3], st));
 
         CollectArgs CA;
@@ -1030,8 +1020,8 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
         CA.op_ref = TA.op_ref; CA.op_rd = TA.op_rd; CA.meta = TA.meta; CA.site_of = SA.site_of; CA.site_evoff = SA.site_evoff;
         CA.site_cur = e->site_cur.as<uint32_t>(); CA.ev = e->ev.as<Ev>(); CA.rare = e->rare.as<RareEv>(); CA.n_rare = n_rare;
         CA.P = P;
-        if (n_reads > 0) k_collect_ops<<<(unsigned) ceil_div(n_reads, 8), 256, 0, st>>>(CA);
-        if (n_rare > 0) k_collect_rare<<<(unsigned) ceil_div((int64_t) n_rare, 256), 256, 0, st>>>(CA);
+        if (n_reads > 0) { k_collect_ops<<<(unsigned) ceil_div(n_reads, 8), 256, 0, st>>>(CA); e->launches++; }
+        if (n_rare > 0) { k_collect_rare<<<(unsigned) ceil_div((int64_t) n_rare, 256), 256, 0, st>>>(CA); e->launches++; }
 
         AlleleArgs AA;
         AA.R = R; AA.regions = d_regions; AA.ref = d_ref; AA.region_goff = TA.region_goff; AA.n_regions = n_regions;
@@ -1040,6 +1030,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
         AA.site_region = e->site_region.as<int32_t>(); AA.n_sites = n_sites; AA.P = P;
         k_site_alleles<<<(unsigned) ceil_div(n_sites, 4), 128, 0, st>>>(AA);
         k_scan_excl<<<1, 1024, 0, st>>>(AA.site_ncand, e->site_candoff.as<int64_t>(), n_sites, sc + 3);
+        e->launches += 2;
         PB_CUDA(cudaMemcpyAsync(&n_cand, sc + 3, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
         PB_CUDA(cudaEventRecord(e->evt[4], st));
@@ -1058,8 +1049,9 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
             WA.images = d_images; WA.positions = d_positions; WA.depths = d_depths; WA.freqs = d_freqs; WA.keys = d_keys;
             WA.region_of = d_region_of;
             k_windows<<<(unsigned) ceil_div(n_sites, 4), 128, 0, st>>>(WA);
+            e->launches++;
             if (d_n_per_region)
-                k_region_counts<<<(unsigned) ceil_div(n_cand, 256), 256, 0, st>>>(d_region_of, n_cand, d_n_per_region);
+            { k_region_counts<<<(unsigned) ceil_div(n_cand, 256), 256, 0, st>>>(d_region_of, n_cand, d_n_per_region); e->launches++; }
         }
         PB_CUDA(cudaEventRecord(e->evt[5], st));
     } else {
@@ -1070,6 +1062,12 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < 5; i++) cudaEventElapsedTime(&e->ms[i], e->evt[i], e->evt[i + 1]);
+    return PB_OK;
+}
+
+extern "C" int pb_variant_encoder_launches(pb_variant_encoder_t *e, int64_t *n) {
+    if (!e || !n) return PB_ERR_ARG;
+    *n = e->launches;
     return PB_OK;
 }
 

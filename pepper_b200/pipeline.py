@@ -1,0 +1,207 @@
+"""Public API of the fused hot path: make_images + inference in one call.
+
+``VariantCaller.call``  == `pepper_variant call_variant` steps 1+2 (CallVariant.py:12: generate_images ->
+run_inference) for a batch of regions; returns what DataStorePredict.write_prediction stores
+(pepper_variant/modules/python/DataStorePredict.py:49-66): contig positions, depths, candidate keys, candidate
+frequencies and the float32 [N,3] genotype probabilities.
+
+``PolishCaller.call``   == `pepper polish` steps 1+2 (polish.py:14: make_images -> call_consensus); returns what
+pepper/modules/python/DataStorePredict.py:49-76 stores: per image position/index/bases/phred.
+
+Both take HOST buffers (numpy) and do the host<->device copies themselves (pb_*_call_host); `call_device`
+variants take torch CUDA tensors that already live in HBM (used by bench.py's device-resident leg).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+import numpy as np
+
+from . import _lib
+from .abi import (HostReads, PbReads, PbRegion, PbVariantParams, regions_array, variant_params, WINDOW, FEATURES,
+                  ALLELE_STRIDE, POLISH_SEQ_LEN, PB_ERR_CAPACITY)
+from .synth import ReadBatch, RegionTable
+from .variant import VariantEncoder, VariantNet, _bind as _bind_variant
+from .polish import PolishEncoder, PolishNet, _bind as _bind_polish
+
+
+@dataclass
+class VariantCalls:
+    positions: np.ndarray    # int64 [N]
+    depths: np.ndarray       # uint8 [N]
+    freqs: np.ndarray        # uint8 [N]
+    keys_raw: np.ndarray     # uint8 [N,64]
+    region_of: np.ndarray    # int32 [N]
+    probs: np.ndarray        # float32 [N,3]
+    images: np.ndarray | None = None
+
+    @property
+    def keys(self):
+        return [bytes(k).split(b"\0", 1)[0].decode() for k in self.keys_raw]
+
+    def __len__(self):
+        return int(self.positions.shape[0])
+
+
+@dataclass
+class PolishCalls:
+    bases: np.ndarray        # uint8 [n_img,1000]
+    phred: np.ndarray        # uint8 [n_img,1000]
+    position: np.ndarray     # int64 [n_img,1000]
+    index: np.ndarray        # int32 [n_img,1000]
+    image_region: np.ndarray  # int32 [n_img]
+    chunk_id: np.ndarray     # int32 [n_img]
+
+
+def _bind_calls(L):
+    if getattr(L, "_calls_bound", False):
+        return
+    vp = C.c_void_p
+    L.pb_variant_call_host.argtypes = [vp, vp, C.POINTER(PbReads), C.POINTER(PbRegion), C.c_int64, vp, C.c_int64,
+                                       C.POINTER(PbVariantParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp,
+                                       C.POINTER(C.c_int64), vp]
+    L.pb_variant_call_device.argtypes = [vp, vp, C.POINTER(PbReads), vp, C.c_int64, C.POINTER(PbRegion), vp, C.c_int64,
+                                         C.POINTER(PbVariantParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp,
+                                         C.POINTER(C.c_int64), vp]
+    L.pb_variant_call_timings.argtypes = [vp, vp]
+    L.pb_polish_call_host.argtypes = [vp, vp, C.POINTER(PbReads), C.POINTER(PbRegion), C.c_int64, C.c_int64, vp, vp, vp, vp,
+                                      vp, vp, C.POINTER(C.c_int64), vp]
+    L.pb_polish_call_device.argtypes = [vp, vp, C.POINTER(PbReads), vp, C.c_int64, C.POINTER(PbRegion), C.c_int64, vp, vp,
+                                        vp, vp, vp, vp, C.POINTER(C.c_int64), vp]
+    L.pb_polish_call_timings.argtypes = [vp, vp]
+    L._calls_bound = True
+
+
+class DeviceReads:
+    """A ReadBatch (+ region table + reference) resident in HBM as torch tensors; builds the pb_reads_t whose
+    pointers are device pointers."""
+
+    def __init__(self, reads: ReadBatch, regions: RegionTable, device: int = 0):
+        import torch
+        dev = torch.device("cuda", device)
+        hr = HostReads(reads)
+        self._keep = []
+
+        def up(a):
+            t = torch.from_numpy(a).to(dev)
+            self._keep.append(t)
+            return t.data_ptr()
+        self.struct = PbReads(reads.n_reads, up(hr.pos), up(hr.seq_off), up(hr.cigar_off), up(hr.flags), up(hr.mapq),
+                              up(hr.seq), up(hr.qual), up(hr.cigar.view(np.int32)))
+        self.h_regions, self._tab = regions_array(regions)
+        self.d_regions = up(self._tab)
+        ref = np.ascontiguousarray(regions.ref, dtype=np.uint8)
+        self.d_ref = up(ref)
+        self.ref_bytes = int(ref.shape[0])
+        self.n_regions = regions.n_regions
+        self.nbytes = sum(t.numel() * t.element_size() for t in self._keep)
+
+
+class VariantCaller:
+    def __init__(self, state: dict, device: int = 0):
+        self.enc = VariantEncoder(device)
+        self.net = VariantNet(state, device)
+        self.L = _lib.lib()
+        _bind_calls(self.L)
+        self.device = device
+
+    def close(self):
+        self.enc.close()
+        self.net.close()
+
+    def call(self, reads: ReadBatch, regions: RegionTable, params: dict, capacity: int | None = None,
+             want_images: bool = False, stream: int = 0) -> VariantCalls:
+        hr = HostReads(reads)
+        return self.call_prepared(hr, regions, params, capacity, want_images, stream)
+
+    def call_prepared(self, hr: HostReads, regions: RegionTable, params: dict, capacity: int | None = None,
+                      want_images: bool = False, stream: int = 0) -> VariantCalls:
+        regs, keep = regions_array(regions)
+        ref = np.ascontiguousarray(regions.ref, dtype=np.uint8)
+        p = variant_params(**params)
+        if capacity is None:
+            span = int((regions.col("cand_end") - regions.col("cand_start") + 1).sum())
+            capacity = max(1024, span // 16)
+        while True:
+            img = np.empty((capacity, WINDOW, FEATURES), dtype=np.int8) if want_images else None
+            pos = np.empty(capacity, dtype=np.int64)
+            dep = np.empty(capacity, dtype=np.uint8)
+            frq = np.empty(capacity, dtype=np.uint8)
+            keys = np.empty((capacity, ALLELE_STRIDE), dtype=np.uint8)
+            rof = np.empty(capacity, dtype=np.int32)
+            probs = np.empty((capacity, 3), dtype=np.float32)
+            n = C.c_int64(0)
+            rc = self.L.pb_variant_call_host(self.enc.h, self.net.h, C.byref(hr.struct), regs, regions.n_regions,
+                                             ref.ctypes.data, ref.shape[0], C.byref(p), capacity,
+                                             img.ctypes.data if want_images else None, pos.ctypes.data, dep.ctypes.data,
+                                             frq.ctypes.data, keys.ctypes.data, rof.ctypes.data, probs.ctypes.data,
+                                             C.byref(n), C.c_void_p(stream))
+            if rc == PB_ERR_CAPACITY:
+                capacity = int(n.value) + 16
+                continue
+            _lib.check(rc, "pb_variant_call_host")
+            k = int(n.value)
+            return VariantCalls(pos[:k], dep[:k], frq[:k], keys[:k], rof[:k], probs[:k], img[:k] if want_images else None)
+
+    def call_device(self, dreads: DeviceReads, params: dict, out: dict, stream: int = 0) -> int:
+        """Everything in HBM.  `out` holds torch CUDA tensors: images int8 [cap,33,26], positions int64 [cap],
+        depths/freqs uint8 [cap], keys uint8 [cap,64], region_of int32 [cap], probs float32 [cap,3]."""
+        p = variant_params(**params)
+        n = C.c_int64(0)
+        cap = int(out["positions"].shape[0])
+        rc = self.L.pb_variant_call_device(self.enc.h, self.net.h, C.byref(dreads.struct), dreads.d_regions,
+                                           dreads.n_regions, dreads.h_regions, dreads.d_ref, dreads.ref_bytes, C.byref(p),
+                                           cap, out["images"].data_ptr(), out["positions"].data_ptr(),
+                                           out["depths"].data_ptr(), out["freqs"].data_ptr(), out["keys"].data_ptr(),
+                                           out["region_of"].data_ptr(), out["probs"].data_ptr(), C.byref(n),
+                                           C.c_void_p(stream))
+        _lib.check(rc, "pb_variant_call_device")
+        return int(n.value)
+
+    def timings(self) -> dict:
+        ms = (C.c_float * 2)()
+        _lib.check(self.L.pb_variant_call_timings(self.enc.h, ms), "timings")
+        d = dict(encode_ms=float(ms[0]), network_ms=float(ms[1]))
+        d.update({"enc_" + k: v for k, v in self.enc.timings().items()})
+        return d
+
+
+class PolishCaller:
+    def __init__(self, state: dict, device: int = 0):
+        self.enc = PolishEncoder(device)
+        self.net = PolishNet(state, device)
+        self.L = _lib.lib()
+        _bind_calls(self.L)
+
+    def close(self):
+        self.enc.close()
+        self.net.close()
+
+    def call(self, reads: ReadBatch, regions: RegionTable, capacity: int | None = None, stream: int = 0) -> PolishCalls:
+        hr = HostReads(reads)
+        regs, keep = regions_array(regions)
+        if capacity is None:
+            span = int((regions.col("ref_end") - regions.col("ref_start") + 1).sum())
+            capacity = 3 * (span // 950 + regions.n_regions) + 8
+        while True:
+            bases = np.empty((capacity, POLISH_SEQ_LEN), dtype=np.uint8)
+            phred = np.empty((capacity, POLISH_SEQ_LEN), dtype=np.uint8)
+            position = np.empty((capacity, POLISH_SEQ_LEN), dtype=np.int64)
+            index = np.empty((capacity, POLISH_SEQ_LEN), dtype=np.int32)
+            ireg = np.empty(capacity, dtype=np.int32)
+            cid = np.empty(capacity, dtype=np.int32)
+            n = C.c_int64(0)
+            rc = self.L.pb_polish_call_host(self.enc.h, self.net.h, C.byref(hr.struct), regs, regions.n_regions, capacity,
+                                            bases.ctypes.data, phred.ctypes.data, position.ctypes.data, index.ctypes.data,
+                                            ireg.ctypes.data, cid.ctypes.data, C.byref(n), C.c_void_p(stream))
+            if rc == PB_ERR_CAPACITY:
+                capacity = int(n.value) + 4
+                continue
+            _lib.check(rc, "pb_polish_call_host")
+            k = int(n.value)
+            return PolishCalls(bases[:k], phred[:k], position[:k], index[:k], ireg[:k], cid[:k])
+
+    def timings(self) -> dict:
+        ms = (C.c_float * 2)()
+        _lib.check(self.L.pb_polish_call_timings(self.enc.h, ms), "timings")
+        return dict(encode_ms=float(ms[0]), network_ms=float(ms[1]))

@@ -1,0 +1,55 @@
+"""GPU: the fused public API (pb_*_call_host) equals encoder-then-network run separately and the oracle."""
+import numpy as np
+import pytest
+
+from pepper_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_variant_call_matches_separate_stages(oracle_built):
+    from oracle import nets
+    from pepper_b200.pipeline import VariantCaller
+    state = nets.make_variant_weights(1)
+    reads, regions = synth.make_variant_workload(3, 7000, 30, synth.ONT, seed=31)
+    caller = VariantCaller(state)
+    calls = caller.call(reads, regions, synth.ont_params(), want_images=True)
+    want = oracle_built.variant_encode(reads, regions, synth.ont_params(), "port")
+    assert calls.keys == want["keys"]
+    assert np.array_equal(calls.images, oracle_built.images_to_int8(want["images"]))
+    assert np.array_equal(calls.region_of, want["region_of"])
+    probs = nets.variant_predict(state, calls.images, threads=8)
+    assert np.abs(probs - calls.probs).max() < 1e-3
+    sep = caller.net.predict(calls.images)
+    assert np.array_equal(sep, calls.probs)          # same kernels, same order -> bitwise
+    t = caller.timings()
+    assert t["encode_ms"] > 0 and t["network_ms"] > 0
+    small = caller.call(reads, regions, synth.ont_params(), capacity=5)
+    assert np.array_equal(small.probs, calls.probs)
+    caller.close()
+
+
+def test_polish_call_matches_separate_stages(oracle_built):
+    from oracle import nets
+    from pepper_b200.pipeline import PolishCaller
+    from pepper_b200.polish import PolishSummary, chunk_images
+    state = nets.make_polish_weights(2)
+    reads, regions = synth.make_polish_workload(6, 35, synth.ONT, seed=32)
+    pc = PolishCaller(state)
+    calls = pc.call(reads, regions)
+    w = oracle_built.polish_encode(reads, regions, "port")
+    imgs, pos, idx, cids, regs = chunk_images(PolishSummary(w["image"], w["pos"], w["idx"], w["col_off"]))
+    assert np.array_equal(calls.position, pos) and np.array_equal(calls.index.astype(np.int64), idx)
+    assert np.array_equal(calls.chunk_id, cids) and np.array_equal(calls.image_region, regs)
+    b, p = pc.net.predict(imgs)
+    assert np.array_equal(b, calls.bases) and np.array_equal(p, calls.phred)
+    wb, wp, wh, wa = nets.polish_predict(state, imgs, threads=8)
+    srt = np.sort(wa, axis=2)
+    clear = (srt[:, :, -1] - srt[:, :, -2]) > 1e-4
+    assert np.array_equal(calls.bases[clear], wb[clear]) and clear.mean() > 0.99
+    pc.close()
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()
