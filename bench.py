@@ -270,77 +270,120 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_sample(args, n_regions: int, threads: int):
-    """The oracle (reference algorithm on CPU) over `n_regions` regions of the same workload."""
-    from pepper_b200 import synth
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/): the reference's algorithm on the host cores, organised the way
+# the reference organises its CPU run — P single-threaded worker processes over regions for make_images
+# (pepper_variant ImageGenerationUI.py:326) and over candidate slices for inference with 1 intra-op thread per
+# caller (pepper_variant predict_distributed_cpu.py:47-57).
+# ---------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _worker_init():
+    import torch
+    torch.set_num_threads(1)
     from oracle import oracle, nets
-    reads, regions = synth.make_variant_workload(n_regions, args.region_size, args.coverage, synth.ONT, seed=args.seed)
-    impl = "ref" if oracle.have_ref() else "port"
-    t0 = time.perf_counter()
-    if threads > 1 and n_regions > 1:
-        import multiprocessing as mp
-        with mp.get_context("fork").Pool(min(threads, n_regions)) as pool:
-            parts = pool.starmap(_enc_one, [(args.region_size, args.coverage, args.seed, n_regions, r, impl) for r in range(n_regions)])
-        images = np.concatenate(parts)
-    else:
-        c = oracle.variant_encode(reads, regions, synth.ont_params(), impl)
-        images = oracle.images_to_int8(c["images"])
-    t_enc = time.perf_counter() - t0
-    state = nets.make_variant_weights(0)
-    t0 = time.perf_counter()
-    nets.variant_predict(state, images, batch=512, threads=threads)
-    t_net = time.perf_counter() - t0
-    return regions.genomic_bases(), t_enc, t_net, images.shape[0], impl
+    oracle.lib("port")
+    _W["impl"] = "ref" if oracle.have_ref() else "port"
+    if _W["impl"] == "ref":
+        oracle.lib("ref_variant")
+    _W["state"] = nets.make_variant_weights(0)
+    _W["oracle"], _W["nets"] = oracle, nets
 
 
-def _enc_one(region_size, coverage, seed, n_regions, r, impl):
+def _worker_encode(task):
     from pepper_b200 import synth
-    from oracle import oracle
-    reads, regions = synth.make_variant_workload(n_regions, region_size, coverage, synth.ONT, seed=seed)
-    one = synth.RegionTable(regions.table[r:r + 1].copy(), regions.ref)
-    c = oracle.variant_encode(reads, one, synth.ont_params(), impl)
-    return oracle.images_to_int8(c["images"])
+    sub, tab = task
+    c = _W["oracle"].variant_encode(sub, tab, synth.ont_params(), _W["impl"])
+    return _W["oracle"].images_to_int8(c["images"])
+
+
+def _worker_net(images):
+    return _W["nets"].variant_predict(_W["state"], images, batch=512, threads=1)
+
+
+def _worker_ready(_):
+    return _W["impl"]
+
+
+class CpuReference:
+    def __init__(self, args, procs: int):
+        from pepper_b200 import synth
+        self.procs = procs
+        self.nreg = 1 if procs == 1 else max(2, min(32, procs // 8))
+        reads, regions = synth.make_variant_workload(self.nreg, args.region_size, args.coverage, synth.ONT, seed=args.seed)
+        self.tasks = [synth.region_batch(reads, regions, r) for r in range(self.nreg)]
+        self.genomic_bases = regions.genomic_bases()
+        if procs == 1:
+            _worker_init()
+            self.pool = None
+            self.impl = _W["impl"]
+        else:
+            import multiprocessing as mp
+            self.pool = mp.get_context("spawn").Pool(procs, initializer=_worker_init)
+            self.impl = self.pool.map(_worker_ready, range(procs))[0]
+
+    def step(self):
+        t0 = time.perf_counter()
+        if self.pool is None:
+            parts = [_worker_encode(t) for t in self.tasks]
+        else:
+            parts = self.pool.map(_worker_encode, self.tasks, chunksize=1)
+        images = np.concatenate(parts)
+        t_enc = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if self.pool is None:
+            _worker_net(images)
+        else:
+            per = max(64, -(-images.shape[0] // self.procs))
+            self.pool.map(_worker_net, [images[i:i + per] for i in range(0, images.shape[0], per)], chunksize=1)
+        t_net = time.perf_counter() - t0
+        return t_enc, t_net, images.shape[0]
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+    def describe(self, t_enc, t_net, n_cand):
+        enc = "reference C++ compiled into oracle/_ref" if self.impl == "ref" else "oracle/port_encoders.c"
+        return (f"{self.nreg} region(s) x 100 kb of the same workload ({n_cand} candidates) per step over {self.procs} single-threaded "
+                f"worker process(es): encoder = {enc} {t_enc:.2f}s, network = oracle/nets.py (PyTorch CPU, bit-identical to the "
+                f"reference nn.Module) {t_net:.2f}s")
 
 
 def cpu_baseline(args, threads: int):
-    nreg = 1 if threads == 1 else max(2, min(8, threads // 8))
-    gb, t_enc, t_net, n_cand, impl = cpu_sample(args, nreg, threads)
-    return {"value": gb / (t_enc + t_net), "unit": "bases/s", "cores": threads,
-            "kind": "reference" if impl == "ref" else "port",
-            "sample": f"{nreg} region(s) x {args.region_size} bp of the same workload ({n_cand} candidates): encoder = "
-                      + ("reference C++ compiled into oracle/_ref" if impl == "ref" else "oracle/port_encoders.c")
-                      + f" {t_enc:.2f}s, network = oracle/nets.py (PyTorch CPU, bit-identical to the reference nn.Module) {t_net:.2f}s",
+    ref = CpuReference(args, threads)
+    t_enc, t_net, n_cand = ref.step()
+    ref.close()
+    return {"value": ref.genomic_bases / (t_enc + t_net), "unit": "bases/s", "cores": threads,
+            "kind": "reference" if ref.impl == "ref" else "port", "sample": ref.describe(t_enc, t_net, n_cand),
             "encoder_s": t_enc, "network_s": t_net}
 
 
 def run_reference(args):
-    """The reference's CPU implementation of the path on the host cores (oracle/_ref encoders when present, else the
-    port; the PyTorch CPU restatement of the network), all host threads."""
+    """The reference's CPU implementation of the path on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    vals = []
-    info = None
+    procs = os.cpu_count() or 1
+    ref = CpuReference(args, procs)
+    tot_t, last = 0.0, None
     for i in range(args.warmup + args.steps):
-        nreg = max(2, min(8, threads // 8))
-        gb, t_enc, t_net, n_cand, impl = cpu_sample(args, nreg, threads)
+        t_enc, t_net, n_cand = ref.step()
         if i >= args.warmup:
-            vals.append((gb, t_enc + t_net))
-        info = (nreg, n_cand, impl, t_enc, t_net)
-    tot_b = sum(v[0] for v in vals); tot_t = sum(v[1] for v in vals)
-    value = tot_b / tot_t
-    nreg, n_cand, impl, t_enc, t_net = info
+            tot_t += t_enc + t_net
+        last = (t_enc, t_net, n_cand)
+    ref.close()
+    value = ref.genomic_bases * args.steps / tot_t
     line = {"impl": "reference", "metric": "genomic bases/sec (make_images+inference)", "value": value, "unit": "bases/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * tot_t / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/f64 (encoder), f32 (network)", "data": "synthetic",
             "config": {"workload": "pepper_variant make_images + run_inference, synthetic ONT R9.4.1 30x (BASELINE configs[1])",
-                       "region_size": args.region_size, "coverage": args.coverage, "sample_regions_per_step": nreg},
-            "cpu_baseline": {"value": value, "unit": "bases/s", "cores": threads, "kind": "reference" if impl == "ref" else "port",
-                             "sample": f"{nreg} regions x {args.region_size} bp per step ({n_cand} candidates); encoder "
-                                       f"{'oracle/_ref (reference C++)' if impl == 'ref' else 'oracle port'} over {min(threads, nreg)} processes "
-                                       f"{t_enc:.2f}s + PyTorch CPU network with {threads} threads {t_net:.2f}s"},
+                       "region_size": args.region_size, "coverage": args.coverage, "sample_regions_per_step": ref.nreg},
+            "cpu_baseline": {"value": value, "unit": "bases/s", "cores": procs, "kind": "reference" if ref.impl == "ref" else "port",
+                             "sample": ref.describe(*last)},
             "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

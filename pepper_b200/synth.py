@@ -373,6 +373,22 @@ def tile_workload(reads: ReadBatch, regions: RegionTable, times: int):
     return concat_batches(batches), RegionTable(np.concatenate(tabs), ref)
 
 
+def region_batch(reads: ReadBatch, regions: RegionTable, r: int):
+    """The reads / table / reference of region r alone (re-based offsets)."""
+    row = regions.table[r].copy()
+    rb, re_ = int(row[6]), int(row[7])
+    b0, b1 = int(reads.seq_off[rb]), int(reads.seq_off[re_])
+    c0, c1 = int(reads.cigar_off[rb]), int(reads.cigar_off[re_])
+    codes = reads.codes()[b0:b1]
+    sub = ReadBatch(reads.pos[rb:re_].copy(), reads.seq_off[rb:re_ + 1] - b0, reads.cigar_off[rb:re_ + 1] - c0,
+                    reads.flags[rb:re_].copy(), reads.mapq[rb:re_].copy(), pack_codes(codes), reads.qual[b0:b1].copy(),
+                    reads.cigar[c0:c1].copy())
+    ref = regions.ref[int(row[4]):int(row[4] + row[5])].copy() if regions.ref.shape[0] > 1 else regions.ref
+    row[4] = 0
+    row[6], row[7] = 0, re_ - rb
+    return sub, RegionTable(row[None, :], ref)
+
+
 def ont_params() -> dict:
     """--ont_r9_guppy5_sup image-generation thresholds, SetParameters.py:16-37."""
     return dict(min_snp_baseq=1, min_indel_baseq=1, snp_freq_threshold=0.10, insert_freq_threshold=0.15,
