@@ -56,7 +56,7 @@ struct DevBuf {
 int upload(DevBuf &b, const void *h, size_t bytes, cudaStream_t st);
 int upload_reads(const pb_reads_t *h, DevBuf *const bufs[8], pb_reads_t *d, cudaStream_t st);
 
-static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

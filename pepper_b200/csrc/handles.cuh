@@ -6,6 +6,20 @@
 namespace pb {
 struct DevRnn { DevBuf W, bias; int K0, K0p, K1, Kp, H; };
 struct DevLin { DevBuf W, bias; int N, K, Kp; };
+// tcgen05 path (nets_tc.cu): weights as bf16 hi/lo tile images + per-chunk tiled operands
+struct TcRnn { DevBuf w_hi, w_lo; int nkt_x = 0, nkt_h = 0; };
+struct TcLin { DevBuf w_hi, w_lo; int nkt = 0; };
+struct TcVariant {
+    TcRnn enc[2], dec[2];
+    TcLin lin[5];
+    DevBuf img_op, yenc_hi, yenc_lo, ydec_hi, ydec_lo, c, act_hi[2], act_lo[2], final_f32;
+};
+struct TcPolish {
+    TcRnn enc[2], dec[2];
+    DevBuf img_op, yenc_hi, yenc_lo, ydec_hi, ydec_lo, zero;
+};
+int tc_upload_rnn(TcRnn &T, const float *Wp, int K0, int K0p_src, int H, int Kp_src);
+int tc_upload_lin(TcLin &T, const float *w, int N, int K);
 }  // namespace pb
 
 struct pb_variant_encoder {
@@ -49,6 +63,7 @@ struct pb_polish_encoder {
 struct pb_variant_net {
     int device = 0;
     int mode = 0;
+    pb::TcVariant *tc = nullptr;
     pb::DevRnn enc[2], dec[2];
     pb::DevLin lin[5], outl;
     // scratch for one chunk
@@ -59,9 +74,18 @@ struct pb_variant_net {
 
 struct pb_polish_net {
     int device = 0;
+    int mode = 0;
+    pb::TcPolish *tc = nullptr;
     pb::DevRnn enc[2], dec[2];
     pb::DevBuf dW, dB;
     int64_t chunk = 0;
     pb::DevBuf h[2], yenc, ydec, acc, img, bases, phred;
     int64_t launches = 0;
 };
+
+namespace pb {
+int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, float *d_probs, float *d_hidden_dbg, cudaStream_t st,
+                       void (*out_kernel)(const float *, const float *, const float *, float *, int64_t, cudaStream_t));
+int polish_forward_tc(pb_polish_net *N, const uint8_t *d_images, int64_t B, int64_t n_total, int64_t b0, float *d_hidden_dbg,
+                      float *ydec_f32, void (*dense_kernel)(pb_polish_net *, const float *, int64_t, int, cudaStream_t), cudaStream_t st);
+}  // namespace pb

@@ -371,12 +371,21 @@ extern "C" int pb_variant_net_create(pb_variant_net_t **out, int device, const f
     PB_CUDA(cudaSetDevice(device));
     auto *N = new pb_variant_net();
     N->device = device;
+    N->tc = new TcVariant();
     for (int d = 0; d < 2; d++) {
-        PB_TRY(upload_rnn(N->enc[d], pack_lstm(P[4 * d + 0], P[4 * d + 1], P[4 * d + 2], P[4 * d + 3], 26, VH)));
-        PB_TRY(upload_rnn(N->dec[d], pack_lstm(P[8 + 4 * d + 0], P[8 + 4 * d + 1], P[8 + 4 * d + 2], P[8 + 4 * d + 3], 512, VH)));
+        const PackedRnn pe = pack_lstm(P[4 * d + 0], P[4 * d + 1], P[4 * d + 2], P[4 * d + 3], 26, VH);
+        const PackedRnn pd = pack_lstm(P[8 + 4 * d + 0], P[8 + 4 * d + 1], P[8 + 4 * d + 2], P[8 + 4 * d + 3], 512, VH);
+        PB_TRY(upload_rnn(N->enc[d], pe));
+        PB_TRY(upload_rnn(N->dec[d], pd));
+        PB_TRY(tc_upload_rnn(N->tc->enc[d], pe.W.data(), pe.K0, pe.K0p, VH, pe.Kp));
+        PB_TRY(tc_upload_rnn(N->tc->dec[d], pd.W.data(), pd.K0, pd.K0p, VH, pd.Kp));
     }
     PB_TRY(upload_lin(N->lin[0], P[16], P[17], 512, VT * 512));
-    for (int i = 1; i < 5; i++) PB_TRY(upload_lin(N->lin[i], P[16 + 2 * i], P[17 + 2 * i], 512, 512));
+    PB_TRY(tc_upload_lin(N->tc->lin[0], P[16], 512, VT * 512));
+    for (int i = 1; i < 5; i++) {
+        PB_TRY(upload_lin(N->lin[i], P[16 + 2 * i], P[17 + 2 * i], 512, 512));
+        PB_TRY(tc_upload_lin(N->tc->lin[i], P[16 + 2 * i], 512, 512));
+    }
     PB_TRY(upload_lin(N->outl, P[26], P[27], 3, 512));
     *out = N;
     return PB_OK;
@@ -389,13 +398,21 @@ extern "C" int pb_variant_net_destroy(pb_variant_net_t *N) {
     N->outl.W.release(); N->outl.bias.release();
     DevBuf *bufs[] = {&N->h[0], &N->h[1], &N->c, &N->yenc, &N->ydec, &N->l[0], &N->l[1], &N->img, &N->probs};
     for (auto *b : bufs) b->release();
+    if (N->tc) {
+        TcVariant &T = *N->tc;
+        for (int d = 0; d < 2; d++) { T.enc[d].w_hi.release(); T.enc[d].w_lo.release(); T.dec[d].w_hi.release(); T.dec[d].w_lo.release(); }
+        for (auto &l : T.lin) { l.w_hi.release(); l.w_lo.release(); }
+        DevBuf *tb[] = {&T.img_op, &T.yenc_hi, &T.yenc_lo, &T.ydec_hi, &T.ydec_lo, &T.c, &T.act_hi[0], &T.act_hi[1], &T.act_lo[0], &T.act_lo[1], &T.final_f32};
+        for (auto *b : tb) b->release();
+        delete N->tc;
+    }
     delete N;
     return PB_OK;
 }
 
 extern "C" int pb_variant_net_set_mode(pb_variant_net_t *N, int mode) {
     if (!N) return PB_ERR_ARG;
-    if (mode != 0) { set_error("mode %d not available in this build (0 = fp32 FFMA)", mode); return PB_ERR_ARG; }
+    if (mode != 0 && mode != 1) { set_error("mode %d unknown (0 = fp32 FFMA, 1 = tcgen05 bf16x3)", mode); return PB_ERR_ARG; }
     N->mode = mode;
     return PB_OK;
 }
@@ -403,6 +420,10 @@ extern "C" int pb_variant_net_launches(pb_variant_net_t *N, int64_t *n) {
     if (!N || !n) return PB_ERR_ARG;
     *n = N->launches;
     return PB_OK;
+}
+
+static void launch_variant_out(const float *x, const float *W, const float *b, float *probs, int64_t n, cudaStream_t st) {
+    k_variant_out<<<(unsigned) ceil_div(n, 8), 256, 0, st>>>(x, W, b, probs, n);
 }
 
 static int variant_reserve(pb_variant_net *N, int64_t B) {
@@ -452,8 +473,12 @@ extern "C" int pb_variant_net_forward_device(pb_variant_net_t *N, const int8_t *
     N->launches = 0;
     for (int64_t b0 = 0; b0 < n; b0 += VARIANT_CHUNK) {
         const int64_t B = std::min(VARIANT_CHUNK, n - b0);
-        PB_TRY(variant_reserve(N, B));
         const int8_t *img = d_images + b0 * VT * 26;
+        if (N->mode == 1) {
+            PB_TRY(variant_forward_tc(N, img, B, d_probs + b0 * 3, d_hidden_dbg ? d_hidden_dbg + b0 * VT * 512 : nullptr, st, launch_variant_out));
+            continue;
+        }
+        PB_TRY(variant_reserve(N, B));
         PB_TRY(lstm_layer<A_I8>(N, N->enc, img, (int64_t) VT * 26, 26, 26, B, N->yenc.as<float>(), st));
         PB_TRY(lstm_layer<A_F32>(N, N->dec, N->yenc.p, (int64_t) VT * 512, 512 * sizeof(float), 512, B, N->ydec.as<float>(), st));
         if (d_hidden_dbg)
@@ -532,9 +557,14 @@ extern "C" int pb_polish_net_create(pb_polish_net_t **out, int device, const flo
     PB_CUDA(cudaSetDevice(device));
     auto *N = new pb_polish_net();
     N->device = device;
+    N->tc = new TcPolish();
     for (int d = 0; d < 2; d++) {
-        PB_TRY(upload_rnn(N->enc[d], pack_gru(P[4 * d + 0], P[4 * d + 1], P[4 * d + 2], P[4 * d + 3], 10, PH)));
-        PB_TRY(upload_rnn(N->dec[d], pack_gru(P[8 + 4 * d + 0], P[8 + 4 * d + 1], P[8 + 4 * d + 2], P[8 + 4 * d + 3], 256, PH)));
+        const PackedRnn pe = pack_gru(P[4 * d + 0], P[4 * d + 1], P[4 * d + 2], P[4 * d + 3], 10, PH);
+        const PackedRnn pd = pack_gru(P[8 + 4 * d + 0], P[8 + 4 * d + 1], P[8 + 4 * d + 2], P[8 + 4 * d + 3], 256, PH);
+        PB_TRY(upload_rnn(N->enc[d], pe));
+        PB_TRY(upload_rnn(N->dec[d], pd));
+        PB_TRY(tc_upload_rnn(N->tc->enc[d], pe.W.data(), pe.K0, pe.K0p, PH, pe.Kp));
+        PB_TRY(tc_upload_rnn(N->tc->dec[d], pd.W.data(), pd.K0, pd.K0p, PH, pd.Kp));
     }
     PB_TRY(N->dW.reserve(sizeof(float) * 5 * 256));
     PB_TRY(N->dB.reserve(sizeof(float) * 8));
@@ -549,8 +579,24 @@ extern "C" int pb_polish_net_destroy(pb_polish_net_t *N) {
     for (int d = 0; d < 2; d++) { N->enc[d].W.release(); N->enc[d].bias.release(); N->dec[d].W.release(); N->dec[d].bias.release(); }
     DevBuf *bufs[] = {&N->dW, &N->dB, &N->h[0], &N->h[1], &N->yenc, &N->ydec, &N->acc, &N->img, &N->bases, &N->phred};
     for (auto *b : bufs) b->release();
+    if (N->tc) {
+        TcPolish &T = *N->tc;
+        for (int d = 0; d < 2; d++) { T.enc[d].w_hi.release(); T.enc[d].w_lo.release(); T.dec[d].w_hi.release(); T.dec[d].w_lo.release(); }
+        DevBuf *tb[] = {&T.img_op, &T.yenc_hi, &T.yenc_lo, &T.ydec_hi, &T.ydec_lo, &T.zero};
+        for (auto *b : tb) b->release();
+        delete N->tc;
+    }
     delete N;
     return PB_OK;
+}
+extern "C" int pb_polish_net_set_mode(pb_polish_net_t *N, int mode) {
+    if (!N) return PB_ERR_ARG;
+    if (mode != 0 && mode != 1) { set_error("mode %d unknown (0 = fp32 FFMA, 1 = tcgen05 bf16x3)", mode); return PB_ERR_ARG; }
+    N->mode = mode;
+    return PB_OK;
+}
+static void launch_polish_dense(pb_polish_net *N, const float *ydec, int64_t B, int win_start, cudaStream_t st) {
+    k_polish_dense_acc<<<(unsigned) ceil_div(B * PWIN, 8), 256, 0, st>>>(ydec, N->dW.as<float>(), N->dB.as<float>(), N->acc.as<float>(), B, win_start);
 }
 extern "C" int pb_polish_net_launches(pb_polish_net_t *N, int64_t *n) {
     if (!N || !n) return PB_ERR_ARG;
@@ -601,6 +647,9 @@ extern "C" int pb_polish_net_forward_device(pb_polish_net_t *N, const uint8_t *d
         const uint8_t *img = d_images + b0 * PSEQ * 10;
         PB_CUDA(cudaMemsetAsync(N->h[0].p, 0, sizeof(float) * 2 * B * PH, st));       // hidden = zeros (cpu.py:53)
         PB_CUDA(cudaMemsetAsync(N->acc.p, 0, sizeof(float) * B * PSEQ * 5, st));
+        if (N->mode == 1) {
+            PB_TRY(polish_forward_tc(N, img, B, n, b0, d_hidden_dbg, N->ydec.as<float>(), launch_polish_dense, st));
+        } else
         for (int w = 0; w < PNWIN; w++) {
             const int i = w * PJUMP;
             // encoder: h0 = carried hidden; decoder: h0 = encoder's final state; its final state is carried on

@@ -1,0 +1,339 @@
+// Host side of the tcgen05 network path (mode 1): weight / operand tiling, per-layer launch sequences, and a
+// GEMM self-test entry point.  Device code: tc_gemm.cuh.
+#include "handles.cuh"
+#include "tc_gemm.cuh"
+#include <vector>
+#include <algorithm>
+
+using namespace pb;
+using tc::Args;
+using tc::Dir;
+using tc::Seg;
+using tc::TILE_ELEMS;
+typedef __nv_bfloat16 bf16;
+
+namespace pb {
+
+static inline uint16_t f2bf(float f) {           // round to nearest even
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t lsb = (x >> 16) & 1u;
+    x += 0x7FFFu + lsb;
+    return (uint16_t) (x >> 16);
+}
+static inline float bf2f(uint16_t h) {
+    uint32_t x = (uint32_t) h << 16;
+    float f;
+    memcpy(&f, &x, 4);
+    return f;
+}
+
+// row-major [rows][K] fp32 (rows % 128 == 0 after padding, K % 32 == 0 after padding) -> hi / lo tiles [rt][kt][4][128][8]
+static void tile_matrix(const float *src, int64_t rows, int64_t K, int64_t rows_p, int64_t Kp, std::vector<uint16_t> &hi, std::vector<uint16_t> &lo) {
+    const int64_t RT = rows_p / 128, KT = Kp / 32;
+    hi.assign((size_t) (RT * KT * TILE_ELEMS), 0);
+    lo.assign((size_t) (RT * KT * TILE_ELEMS), 0);
+    for (int64_t r = 0; r < rows; r++)
+        for (int64_t k = 0; k < K; k++) {
+            const float v = src[r * K + k];
+            const uint16_t h = f2bf(v);
+            const uint16_t l = f2bf(v - bf2f(h));
+            const int64_t o = ((r / 128) * KT + k / 32) * TILE_ELEMS + ((k % 32) / 8) * 1024 + (r % 128) * 8 + (k % 8);
+            hi[(size_t) o] = h;
+            lo[(size_t) o] = l;
+        }
+}
+
+static int upload_tiles(DevBuf &dhi, DevBuf &dlo, const std::vector<uint16_t> &hi, const std::vector<uint16_t> &lo) {
+    PB_TRY(dhi.reserve(hi.size() * 2));
+    PB_TRY(dlo.reserve(lo.size() * 2));
+    PB_CUDA(cudaMemcpy(dhi.p, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(dlo.p, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+// weights of one RNN direction, packed rows 4j+g (host copy kept by nets.cu) with K = [x | pad32 | h]
+int tc_upload_rnn(TcRnn &T, const float *Wp /* [4H][Kp_src] */, int K0, int K0p_src, int H, int Kp_src) {
+    const int K0p = (K0 + 31) / 32 * 32;
+    const int Kp = K0p + H;
+    std::vector<float> W((size_t) 4 * H * Kp, 0.f);
+    for (int n = 0; n < 4 * H; n++) {
+        for (int k = 0; k < K0; k++) W[(size_t) n * Kp + k] = Wp[(size_t) n * Kp_src + k];
+        for (int k = 0; k < H; k++) W[(size_t) n * Kp + K0p + k] = Wp[(size_t) n * Kp_src + K0p_src + k];
+    }
+    std::vector<uint16_t> hi, lo;
+    tile_matrix(W.data(), 4 * H, Kp, 4 * H, Kp, hi, lo);
+    T.nkt_x = K0p / 32; T.nkt_h = H / 32;
+    return upload_tiles(T.w_hi, T.w_lo, hi, lo);
+}
+int tc_upload_lin(TcLin &T, const float *w, int N, int K) {
+    std::vector<uint16_t> hi, lo;
+    const int Np = (N + 127) / 128 * 128, Kp = (K + 31) / 32 * 32;
+    tile_matrix(w, N, K, Np, Kp, hi, lo);
+    T.nkt = Kp / 32;
+    return upload_tiles(T.w_hi, T.w_lo, hi, lo);
+}
+
+template <int EPI>
+static int launch_tc(const Args &A, int mt, int nt, int ndir, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(tc::k_tc_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        attr_set = true;
+    }
+    tc::k_tc_gemm<EPI><<<dim3((unsigned) mt, (unsigned) nt, (unsigned) ndir), tc::THREADS, tc::SMEM_BYTES, st>>>(A);
+    return PB_OK;
+}
+
+static Dir empty_dir() {
+    Dir D;
+    memset(&D, 0, sizeof(D));
+    return D;
+}
+
+// ------------------------------------------------------------------------------------------------- variant
+constexpr int VT = 33, VH = 256;
+
+int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, float *d_probs, float *d_hidden_dbg, cudaStream_t st,
+                       void (*out_kernel)(const float *, const float *, const float *, float *, int64_t, cudaStream_t)) {
+    TcVariant &T = *N->tc;
+    const int64_t Mt = ceil_div(B, 128), Bp = Mt * 128;
+    const int64_t seq_tiles = Mt * VT * 16;                 // [mt][t][16 k-tiles] of a 512-feature sequence operand
+    PB_TRY(T.img_op.reserve((size_t) (Mt * VT * TILE_ELEMS) * 2));
+    PB_TRY(T.yenc_hi.reserve((size_t) (seq_tiles * TILE_ELEMS) * 2));
+    PB_TRY(T.yenc_lo.reserve((size_t) (seq_tiles * TILE_ELEMS) * 2));
+    PB_TRY(T.ydec_hi.reserve((size_t) (seq_tiles * TILE_ELEMS) * 2));
+    PB_TRY(T.ydec_lo.reserve((size_t) (seq_tiles * TILE_ELEMS) * 2));
+    PB_TRY(T.c.reserve(sizeof(float) * 2 * VH * Bp));
+    for (int i = 0; i < 2; i++) {
+        PB_TRY(T.act_hi[i].reserve((size_t) (Mt * 16 * TILE_ELEMS) * 2));
+        PB_TRY(T.act_lo[i].reserve((size_t) (Mt * 16 * TILE_ELEMS) * 2));
+    }
+    PB_TRY(T.final_f32.reserve(sizeof(float) * Bp * 512));
+
+    tc::k_tc_pack_images<<<(unsigned) ceil_div(Bp * VT * 4, 256), 256, 0, st>>>(d_images, T.img_op.as<bf16>(), B, VT, 26);
+    N->launches++;
+
+    for (int layer = 0; layer < 2; layer++) {
+        PB_CUDA(cudaMemsetAsync(T.c.p, 0, sizeof(float) * 2 * VH * Bp, st));
+        bf16 *y_hi = layer == 0 ? T.yenc_hi.as<bf16>() : T.ydec_hi.as<bf16>();
+        bf16 *y_lo = layer == 0 ? T.yenc_lo.as<bf16>() : T.ydec_lo.as<bf16>();
+        for (int t = 0; t < VT; t++) {
+            Args A;
+            A.M = (int) B; A.N = 4 * VH; A.c_ld = Bp;
+            for (int d = 0; d < 2; d++) {
+                const int tt = d == 0 ? t : VT - 1 - t;
+                const int tp = d == 0 ? tt - 1 : tt + 1;
+                Dir D = empty_dir();
+                TcRnn &W = layer == 0 ? T.enc[d] : T.dec[d];
+                if (layer == 0) {
+                    D.seg[0].hi = T.img_op.as<bf16>() + (int64_t) tt * TILE_ELEMS; D.seg[0].lo = nullptr;
+                    D.seg[0].mt_stride = (int64_t) VT * TILE_ELEMS; D.seg[0].nkt = 1;
+                } else {
+                    D.seg[0].hi = T.yenc_hi.as<bf16>() + (int64_t) tt * 16 * TILE_ELEMS; D.seg[0].lo = T.yenc_lo.as<bf16>() + (int64_t) tt * 16 * TILE_ELEMS;
+                    D.seg[0].mt_stride = (int64_t) VT * 16 * TILE_ELEMS; D.seg[0].nkt = 16;
+                }
+                if (t > 0) {
+                    D.seg[1].hi = y_hi + ((int64_t) tp * 16 + d * 8) * TILE_ELEMS; D.seg[1].lo = y_lo + ((int64_t) tp * 16 + d * 8) * TILE_ELEMS;
+                    D.seg[1].mt_stride = (int64_t) VT * 16 * TILE_ELEMS; D.seg[1].nkt = 8;
+                }
+                D.w_hi = W.w_hi.as<bf16>(); D.w_lo = W.w_lo.as<bf16>(); D.w_nkt = W.nkt_x + W.nkt_h;
+                D.bias = (layer == 0 ? N->enc[d] : N->dec[d]).bias.as<float>();
+                D.c = T.c.as<float>() + (int64_t) d * VH * Bp;
+                D.y_hi = y_hi; D.y_lo = y_lo; D.y_mt_stride = (int64_t) VT * 16 * TILE_ELEMS; D.y_kt0 = tt * 16 + d * 8;
+                if (layer == 1 && d_hidden_dbg) { D.y_f32 = d_hidden_dbg + (int64_t) tt * 512 + d * VH; D.ldy = (int64_t) VT * 512; }
+                A.d[d] = D;
+            }
+            PB_TRY(launch_tc<tc::EPI_LSTM>(A, (int) Mt, 4 * VH / 128, 2, st));
+            N->launches++;
+        }
+    }
+    // MLP head
+    for (int i = 0; i < 5; i++) {
+        Args A;
+        A.M = (int) B; A.N = 512; A.c_ld = 0;
+        Dir D = empty_dir();
+        if (i == 0) {
+            D.seg[0].hi = T.ydec_hi.as<bf16>(); D.seg[0].lo = T.ydec_lo.as<bf16>();
+            D.seg[0].mt_stride = (int64_t) VT * 16 * TILE_ELEMS; D.seg[0].nkt = VT * 16;
+        } else {
+            D.seg[0].hi = T.act_hi[(i - 1) & 1].as<bf16>(); D.seg[0].lo = T.act_lo[(i - 1) & 1].as<bf16>();
+            D.seg[0].mt_stride = (int64_t) 16 * TILE_ELEMS; D.seg[0].nkt = 16;
+        }
+        D.w_hi = T.lin[i].w_hi.as<bf16>(); D.w_lo = T.lin[i].w_lo.as<bf16>(); D.w_nkt = T.lin[i].nkt;
+        D.bias = N->lin[i].bias.as<float>();
+        D.y_hi = T.act_hi[i & 1].as<bf16>(); D.y_lo = T.act_lo[i & 1].as<bf16>(); D.y_mt_stride = (int64_t) 16 * TILE_ELEMS; D.y_kt0 = 0;
+        if (i == 4) { D.y_f32 = T.final_f32.as<float>(); D.ldy = 512; }
+        A.d[0] = D; A.d[1] = D;
+        PB_TRY(launch_tc<tc::EPI_SELU>(A, (int) Mt, 4, 1, st));
+        N->launches++;
+    }
+    out_kernel(T.final_f32.as<float>(), N->outl.W.as<float>(), N->outl.bias.as<float>(), d_probs, B, st);
+    N->launches++;
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- polish
+constexpr int PH = 128, PWIN = 100;
+
+// uint8 image window -> tiled operand [mt][100][1 k-tile] (values <= 254 are exact in bf16)
+__global__ void k_tc_pack_polish(const uint8_t *__restrict__ img /* [B][1000][10] */, bf16 *__restrict__ op, int64_t B, int win_start) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;     // (row, t, kc)
+    const int64_t total = ceil_div(B, 128) * 128 * PWIN * 4;
+    if (i >= total) return;
+    const int kc = (int) (i & 3);
+    const int64_t rt = i >> 2;
+    const int t = (int) (rt % PWIN);
+    const int64_t row = rt / PWIN;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (row < B) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int k = kc * 8 + e;
+            const float v = (k < 10) ? (float) img[(row * 1000 + win_start + t) * 10 + k] : 0.f;
+            w[e >> 1] |= (uint32_t) __bfloat16_as_ushort(__float2bfloat16_rn(v)) << (16 * (e & 1));
+        }
+    }
+    const int64_t o = ((row >> 7) * PWIN + t) * TILE_ELEMS + kc * 1024 + (row & 127) * 8;
+    *reinterpret_cast<uint4 *>(op + o) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// hidden state [B][2][128] fp32 out of a sequence operand (fwd: time 99, bwd: time 0), for the debug read-back
+__global__ void k_tc_unpack_hidden(const bf16 *__restrict__ y_hi, const bf16 *__restrict__ y_lo, float *__restrict__ out, int64_t B) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 2 * PH) return;
+    const int j = (int) (i % PH);
+    const int d = (int) ((i / PH) % 2);
+    const int64_t b = i / (2 * PH);
+    const int tt = d == 0 ? PWIN - 1 : 0;
+    const int64_t o = (((b >> 7) * PWIN + tt) * 8 + d * 4 + (j >> 5)) * TILE_ELEMS + ((j & 31) >> 3) * 1024 + (b & 127) * 8 + (j & 7);
+    out[i] = __bfloat162float(y_hi[o]) + __bfloat162float(y_lo[o]);
+}
+// fp32 [B][100][256] decoder output out of its sequence operand (input of the dense+softmax kernel)
+__global__ void k_tc_unpack_seq(const bf16 *__restrict__ y_hi, const bf16 *__restrict__ y_lo, float *__restrict__ out, int64_t B) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;      // (b, t, f/8)
+    if (i >= B * PWIN * 32) return;
+    const int f8 = (int) (i & 31);
+    const int t = (int) ((i >> 5) % PWIN);
+    const int64_t b = i / (32 * PWIN);
+    const int64_t o = (((b >> 7) * PWIN + t) * 8 + (f8 >> 2)) * TILE_ELEMS + (f8 & 3) * 1024 + (b & 127) * 8;
+    const uint4 h = *reinterpret_cast<const uint4 *>(y_hi + o), l = *reinterpret_cast<const uint4 *>(y_lo + o);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const uint16_t hb = (uint16_t) (hw[e >> 1] >> (16 * (e & 1))), lb = (uint16_t) (lw[e >> 1] >> (16 * (e & 1)));
+        v[e] = __uint_as_float((uint32_t) hb << 16) + __uint_as_float((uint32_t) lb << 16);
+    }
+    float4 *dst = reinterpret_cast<float4 *>(out + (b * PWIN + t) * 256 + f8 * 8);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// one bidirectional GRU layer over the 100 steps of a window.
+//   x operand: [mt][100][xkt] tiles (hi, lo or hi only); h0 operand: tiles (mt, 100 steps, 8) of another sequence operand
+//   (its fwd state at time 99 / bwd state at time 0) or the zero operand.
+static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi, const bf16 *x_lo, int xkt, const bf16 *h0_hi,
+                        const bf16 *h0_lo, bool h0_is_seq, bf16 *y_hi, bf16 *y_lo, int64_t B, cudaStream_t st) {
+    const int64_t Mt = ceil_div(B, 128);
+    const int64_t ystride = (int64_t) PWIN * 8 * TILE_ELEMS;
+    for (int t = 0; t < PWIN; t++) {
+        Args A;
+        A.M = (int) B; A.N = 4 * PH; A.c_ld = 0;
+        for (int d = 0; d < 2; d++) {
+            const int tt = d == 0 ? t : PWIN - 1 - t;
+            const int tp = d == 0 ? tt - 1 : tt + 1;
+            Dir D = empty_dir();
+            D.seg[0].hi = x_hi + (int64_t) tt * xkt * TILE_ELEMS; D.seg[0].lo = x_lo ? x_lo + (int64_t) tt * xkt * TILE_ELEMS : nullptr;
+            D.seg[0].mt_stride = (int64_t) PWIN * xkt * TILE_ELEMS; D.seg[0].nkt = xkt;
+            const bf16 *hh, *hl; int64_t hs;
+            if (t > 0) {
+                hh = y_hi + ((int64_t) tp * 8 + d * 4) * TILE_ELEMS; hl = y_lo + ((int64_t) tp * 8 + d * 4) * TILE_ELEMS; hs = ystride;
+            } else if (h0_is_seq) {
+                const int t0 = d == 0 ? PWIN - 1 : 0;
+                hh = h0_hi + ((int64_t) t0 * 8 + d * 4) * TILE_ELEMS; hl = h0_lo + ((int64_t) t0 * 8 + d * 4) * TILE_ELEMS; hs = ystride;
+            } else {
+                hh = h0_hi; hl = h0_lo; hs = 0;          // zero operand (4 tiles, shared by every row tile)
+            }
+            D.seg[1].hi = hh; D.seg[1].lo = hl; D.seg[1].mt_stride = hs; D.seg[1].nkt = 4;
+            D.hp_hi = hh; D.hp_lo = hl; D.hp_mt_stride = hs;
+            D.w_hi = W[d].w_hi.as<bf16>(); D.w_lo = W[d].w_lo.as<bf16>(); D.w_nkt = W[d].nkt_x + W[d].nkt_h;
+            D.bias = Wb[d].bias.as<float>();
+            D.y_hi = y_hi; D.y_lo = y_lo; D.y_mt_stride = ystride; D.y_kt0 = tt * 8 + d * 4;
+            A.d[d] = D;
+        }
+        PB_TRY(launch_tc<tc::EPI_GRU>(A, (int) Mt, 4 * PH / 128, 2, st));
+        N->launches++;
+    }
+    return PB_OK;
+}
+
+int polish_forward_tc(pb_polish_net *N, const uint8_t *d_images, int64_t B, int64_t n_total, int64_t b0, float *d_hidden_dbg,
+                      float *ydec_f32, void (*dense_kernel)(pb_polish_net *, const float *, int64_t, int, cudaStream_t), cudaStream_t st) {
+    TcPolish &T = *N->tc;
+    const int64_t Mt = ceil_div(B, 128);
+    const int64_t seq = Mt * PWIN * 8 * TILE_ELEMS;
+    PB_TRY(T.img_op.reserve((size_t) (Mt * PWIN * TILE_ELEMS) * 2));
+    PB_TRY(T.yenc_hi.reserve((size_t) seq * 2)); PB_TRY(T.yenc_lo.reserve((size_t) seq * 2));
+    PB_TRY(T.ydec_hi.reserve((size_t) seq * 2)); PB_TRY(T.ydec_lo.reserve((size_t) seq * 2));
+    PB_TRY(T.zero.reserve((size_t) 4 * TILE_ELEMS * 2));
+    PB_CUDA(cudaMemsetAsync(T.zero.p, 0, (size_t) 4 * TILE_ELEMS * 2, st));
+    for (int w = 0; w < 19; w++) {
+        const int i = w * 50;
+        k_tc_pack_polish<<<(unsigned) ceil_div(Mt * 128 * PWIN * 4, 256), 256, 0, st>>>(d_images, T.img_op.as<bf16>(), B, i);
+        N->launches++;
+        // encoder: h0 = carried state (decoder's final state of the previous window, zeros for the first)
+        PB_TRY(gru_layer_tc(N, T.enc, N->enc, T.img_op.as<bf16>(), nullptr, 1, w == 0 ? T.zero.as<bf16>() : T.ydec_hi.as<bf16>(),
+                            w == 0 ? T.zero.as<bf16>() : T.ydec_lo.as<bf16>(), w != 0, T.yenc_hi.as<bf16>(), T.yenc_lo.as<bf16>(), B, st));
+        // decoder: h0 = encoder's final state
+        PB_TRY(gru_layer_tc(N, T.dec, N->dec, T.yenc_hi.as<bf16>(), T.yenc_lo.as<bf16>(), 8, T.yenc_hi.as<bf16>(), T.yenc_lo.as<bf16>(), true,
+                            T.ydec_hi.as<bf16>(), T.ydec_lo.as<bf16>(), B, st));
+        if (d_hidden_dbg) {
+            k_tc_unpack_hidden<<<(unsigned) ceil_div(B * 2 * PH, 256), 256, 0, st>>>(T.ydec_hi.as<bf16>(), T.ydec_lo.as<bf16>(),
+                                                                                    d_hidden_dbg + ((int64_t) w * n_total + b0) * 2 * PH, B);
+            N->launches++;
+        }
+        k_tc_unpack_seq<<<(unsigned) ceil_div(B * PWIN * 32, 256), 256, 0, st>>>(T.ydec_hi.as<bf16>(), T.ydec_lo.as<bf16>(), ydec_f32, B);
+        N->launches++;
+        dense_kernel(N, ydec_f32, B, i, st);
+        N->launches++;
+    }
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // namespace pb
+
+// ------------------------------------------------------------------------------------------------- self test
+// C[M][N] = A[M][K] W[N][K]^T + bias through the tcgen05 kernel (EPI_BIAS, fp32 output).  N % 128 == 0, K % 32 == 0.
+extern "C" int pb_test_tc_gemm(int M, int N, int K, const float *h_A, const float *h_W, const float *h_bias, float *h_out) {
+    if (N % 128 || K % 32 || M <= 0) { set_error("pb_test_tc_gemm: N %% 128 and K %% 32 must be 0"); return PB_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { set_error("no CUDA device: libpepper_b200 has no CPU fallback"); return PB_ERR_CUDA; }
+    const int64_t Mt = ceil_div(M, 128);
+    std::vector<uint16_t> ahi, alo, whi, wlo;
+    tile_matrix(h_A, M, K, Mt * 128, K, ahi, alo);
+    tile_matrix(h_W, N, K, N, K, whi, wlo);
+    DevBuf dahi, dalo, dwhi, dwlo, dbias, dout;
+    PB_TRY(upload_tiles(dahi, dalo, ahi, alo));
+    PB_TRY(upload_tiles(dwhi, dwlo, whi, wlo));
+    PB_TRY(dbias.reserve(sizeof(float) * N));
+    PB_TRY(dout.reserve(sizeof(float) * (size_t) M * N));
+    PB_CUDA(cudaMemcpy(dbias.p, h_bias, sizeof(float) * N, cudaMemcpyHostToDevice));
+    Args A;
+    A.M = M; A.N = N; A.c_ld = 0;
+    Dir D = empty_dir();
+    D.seg[0].hi = dahi.as<bf16>(); D.seg[0].lo = dalo.as<bf16>(); D.seg[0].mt_stride = (int64_t) (K / 32) * TILE_ELEMS; D.seg[0].nkt = K / 32;
+    D.w_hi = dwhi.as<bf16>(); D.w_lo = dwlo.as<bf16>(); D.w_nkt = K / 32;
+    D.bias = dbias.as<float>();
+    D.y_f32 = dout.as<float>(); D.ldy = N;
+    A.d[0] = D; A.d[1] = D;
+    PB_TRY(launch_tc<tc::EPI_BIAS>(A, (int) Mt, N / 128, 1, 0));
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaDeviceSynchronize());
+    PB_CUDA(cudaMemcpy(h_out, dout.p, sizeof(float) * (size_t) M * N, cudaMemcpyDeviceToHost));
+    DevBuf *bufs[] = {&dahi, &dalo, &dwhi, &dwlo, &dbias, &dout};
+    for (auto *b : bufs) b->release();
+    return PB_OK;
+}

@@ -21,7 +21,7 @@ namespace pb {
 
 constexpr int PTILE = 512;
 constexpr int PC_THREADS = 256;
-constexpr int PC_WARPS = PC_THREADS / 32;
+constexpr int PLIST_CAP = 1024;
 
 struct PReads {
     const int64_t *pos, *seq_off, *cigar_off;
@@ -85,6 +85,8 @@ struct PCountArgs {
 __global__ void __launch_bounds__(PC_THREADS, 2) k_polish_count(PCountArgs A) {
     __shared__ int32_t cnt[12 * PTILE];          // 0..9 features, 10 coverage, 11 longest insert
     __shared__ int s_cols;
+    __shared__ int s_list[PLIST_CAP];
+    __shared__ int s_nlist, s_next;
     const int t = blockIdx.x;
     const int reg = A.tile_region[t];
     const pb_region_t rg = A.regions[reg];
@@ -92,25 +94,30 @@ __global__ void __launch_bounds__(PC_THREADS, 2) k_polish_count(PCountArgs A) {
     const int64_t L1 = rg.ref_end - rg.ref_start + 1;
     const int npos = (int) min((int64_t) PTILE, L1 - x0);
     const int64_t lo = rg.ref_start + x0, hi = lo + npos - 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 12 * PTILE; i += PC_THREADS) cnt[i] = 0;
-    if (tid == 0) s_cols = 0;
+    if (tid == 0) { s_cols = 0; s_nlist = 0; s_next = 0; }
     __syncthreads();
     const PReads &R = A.R;
 
-    for (int64_t rb = rg.read_begin + (int64_t) warp * 32; rb < rg.read_end; rb += (int64_t) PC_WARPS * 32) {
-        const int64_t rmine = rb + lane;
-        bool ov = false;
-        if (rmine < rg.read_end && __ldg(R.mapq + rmine) > 0) {                  // :375
-            const int64_t p0 = __ldg(R.pos + rmine);
-            const int64_t p1 = p0 + __ldg(A.read_reflen + rmine);
-            ov = (p0 <= hi + 1) && (p1 >= lo - 1);
+    for (int64_t blk = rg.read_begin; blk < rg.read_end; blk += PLIST_CAP) {
+        const int64_t blk_end = min(rg.read_end, blk + (int64_t) PLIST_CAP);
+        for (int64_t rmine = blk + tid; rmine < blk_end; rmine += PC_THREADS) {
+            if (__ldg(R.mapq + rmine) > 0) {                                     // :375
+                const int64_t p0 = __ldg(R.pos + rmine);
+                const int64_t p1 = p0 + __ldg(A.read_reflen + rmine);
+                if ((p0 <= hi + 1) && (p1 >= lo - 1)) s_list[atomicAdd(&s_nlist, 1)] = (int) (rmine - blk);
+            }
         }
-        unsigned todo = __ballot_sync(0xffffffffu, ov);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int64_t r = rb + src;
+        __syncthreads();
+        const int nlist = s_nlist;
+        while (true) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&s_next, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= nlist) break;
+            const int64_t r = blk + s_list[item];
+            {
             const int64_t rpos = __ldg(R.pos + r);
             const int64_t so = R.seq_off[r];
             const int64_t lseq = R.seq_off[r + 1] - so;
@@ -199,9 +206,12 @@ __global__ void __launch_bounds__(PC_THREADS, 2) k_polish_count(PCountArgs A) {
                 }
                 if (a_last > hi + 1) break;
             }
+            }
         }
+        __syncthreads();
+        if (tid == 0) { s_nlist = 0; s_next = 0; }
+        __syncthreads();
     }
-    __syncthreads();
     const int64_t g0 = A.region_goff[reg] + x0;
     int cols = 0;
     for (int x = tid; x < npos; x += PC_THREADS) {

@@ -1,0 +1,306 @@
+// tcgen05 GEMM with fused LSTM / GRU / SELU epilogues for sm_100a.
+//
+//   D[128 x 128] (fp32, TMEM)  +=  A[128 x 32] (bf16, smem)  x  B[128 x 32]^T (bf16, smem)      per k-tile
+//
+// fp32-equivalent precision comes from a bf16 hi/lo split of BOTH operands and three tensor-core products per
+// k-tile accumulated into the same TMEM tile:  a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi   (error ~2^-16 relative).
+//
+// Every operand lives in HBM already in the shared-memory image of its tile ("tiled operand": for a tile of 128
+// rows x 32 k, element (r, k) sits at  (k/8)*1024 + r*8 + k%8  — the UMMA K-major no-swizzle canonical layout with
+// core matrices of 8 rows x 16 B, SBO = 128 B between 8-row groups, LBO = 2048 B between the two 8-element K chunks
+// of one MMA).  The producer warp therefore moves whole tiles with cp.async.bulk (TMA engine, no tensor map) onto an
+// mbarrier; one elected thread issues tcgen05.mma; tcgen05.commit releases the stage / signals the epilogue; four
+// epilogue warps read the accumulator with tcgen05.ld (one TMEM lane = one batch row per thread), apply bias + cell,
+// and write the NEXT operand (h_t as bf16 hi/lo tiles) straight from registers, so activations never exist in fp32
+// in HBM between layers.
+#pragma once
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace pb {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int TILE_ELEMS = 128 * BK;                 // 4096 bf16
+constexpr int TILE_BYTES = TILE_ELEMS * 2;           // 8192
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
+constexpr int THREADS = 192;                         // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int TMEM_COLS = 128;
+
+enum { EPI_BIAS = 0, EPI_SELU = 1, EPI_LSTM = 2, EPI_GRU = 3 };
+
+struct Seg {                       // one K-segment of the A operand
+    const __nv_bfloat16 *hi, *lo;  // lo == nullptr: exactly representable operand (int8 images), a_lo*w_hi product skipped
+    int64_t mt_stride;             // elements between consecutive row tiles
+    int nkt;                       // k-tiles in this segment
+};
+struct Dir {
+    Seg seg[2];
+    const __nv_bfloat16 *w_hi, *w_lo;   // [n_tile][w_nkt][TILE_ELEMS]
+    int w_nkt;                          // k-tiles per n-tile of the packed weight (>= k-tiles of this launch)
+    const float *bias;                  // [N]
+    float *c;                           // LSTM cell state [H][c_ld]
+    const __nv_bfloat16 *hp_hi, *hp_lo; // GRU: previous hidden state as a tiled operand (k-tile = unit/32)
+    int64_t hp_mt_stride;
+    __nv_bfloat16 *y_hi, *y_lo;         // output operand tiles: tile (mt, y_kt0 + col/32)
+    int64_t y_mt_stride;
+    int y_kt0;
+    float *y_f32; int64_t ldy;          // optional fp32 copy  y_f32[row*ldy + col]
+};
+struct Args {
+    Dir d[2];
+    int M, N;                           // valid rows; N = columns of the packed weight (multiple of 128)
+    int64_t c_ld;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+// K-major, no swizzle: LBO = 2048 B (K chunk stride), SBO = 128 B (8-row group stride), version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((addr >> 4) & 0x3FFF);
+    d |= (uint64_t) ((2048u >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t) ((128u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t) 1 << 46;
+    return d;
+}
+// kind::f16, A = B = BF16, D = F32, both K-major, M = 128, N = 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float selu(float x) {
+    const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+    return x > 0.f ? scale * x : scale * alpha * (expf(x) - 1.0f);
+}
+// 8 fp32 -> 8 bf16 hi + 8 bf16 lo, 16 B each
+__device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+        h[i] = (uint32_t) __bfloat16_as_ushort(h0) | ((uint32_t) __bfloat16_as_ushort(h1) << 16);
+        l[i] = (uint32_t) __bfloat16_as_ushort(l0) | ((uint32_t) __bfloat16_as_ushort(l1) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES), bar_acc = smem_u32(bars + 2 * STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Dir &D = G.d[blockIdx.z];
+    const int mt = blockIdx.x, nt = blockIdx.y;
+    const int nkt0 = D.seg[0].nkt, nkt = nkt0 + D.seg[1].nkt;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kt = 0; kt < nkt; kt++) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (uint32_t) ((kt / STAGES) & 1);
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                const Seg &S = (kt < nkt0) ? D.seg[0] : D.seg[1];
+                const int64_t off = (int64_t) mt * S.mt_stride + (int64_t) ((kt < nkt0) ? kt : kt - nkt0) * TILE_ELEMS;
+                const uint32_t st = smem_base + s * STAGE_BYTES;
+                mbar_expect_tx(bar_full + 8 * s, (S.lo ? 4u : 3u) * TILE_BYTES);
+                bulk_g2s(st, S.hi + off, TILE_BYTES, bar_full + 8 * s);
+                if (S.lo) bulk_g2s(st + TILE_BYTES, S.lo + off, TILE_BYTES, bar_full + 8 * s);
+                const int64_t woff = ((int64_t) nt * D.w_nkt + kt) * TILE_ELEMS;
+                bulk_g2s(st + 2 * TILE_BYTES, D.w_hi + woff, TILE_BYTES, bar_full + 8 * s);
+                bulk_g2s(st + 3 * TILE_BYTES, D.w_lo + woff, TILE_BYTES, bar_full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kt = 0; kt < nkt; kt++) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (uint32_t) ((kt / STAGES) & 1);
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+                const bool has_lo = ((kt < nkt0) ? D.seg[0].lo : D.seg[1].lo) != nullptr;
+                const uint32_t st = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ks++) {
+                    const uint64_t a_hi = smem_desc(st + ks * 4096), a_lo = smem_desc(st + TILE_BYTES + ks * 4096);
+                    const uint64_t b_hi = smem_desc(st + 2 * TILE_BYTES + ks * 4096), b_lo = smem_desc(st + 3 * TILE_BYTES + ks * 4096);
+                    tc_mma(tmem_base, a_hi, b_hi, IDESC, (kt > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma(tmem_base, a_hi, b_lo, IDESC, 1u);
+                    if (has_lo) tc_mma(tmem_base, a_lo, b_hi, IDESC, 1u);
+                }
+                tc_commit(bar_empty + 8 * s);          // frees the stage when these MMAs have read it
+            }
+            tc_commit(bar_acc);                         // accumulator complete
+        }
+    } else {
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int row = mt * BM + q * 32 + lane;
+        const bool valid = row < G.M;
+        const int r128 = q * 32 + lane;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; cc++) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
+            const int col0 = nt * BN + cc * 32;
+            if (EPI == EPI_BIAS || EPI == EPI_SELU) {
+#pragma unroll
+                for (int g8 = 0; g8 < 4; g8++) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float x = __uint_as_float(acc[g8 * 8 + i]) + __ldg(D.bias + col0 + g8 * 8 + i);
+                        v[i] = (EPI == EPI_SELU) ? selu(x) : x;
+                    }
+                    if (valid) {
+                        if (D.y_hi) {
+                            uint4 hi, lo;
+                            split8(v, hi, lo);
+                            const int64_t o = (int64_t) mt * D.y_mt_stride + (int64_t) (D.y_kt0 + col0 / 32) * TILE_ELEMS + g8 * 1024 + r128 * 8;
+                            *reinterpret_cast<uint4 *>(D.y_hi + o) = hi;
+                            *reinterpret_cast<uint4 *>(D.y_lo + o) = lo;
+                        }
+                        if (D.y_f32) {
+                            float4 *dst = reinterpret_cast<float4 *>(D.y_f32 + (int64_t) row * D.ldy + col0 + g8 * 8);
+                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        }
+                    }
+                }
+            } else {
+                // 32 columns = 8 hidden units x 4 gate columns
+                const int j0 = col0 >> 2;
+                float hn[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float4 bz = __ldg(reinterpret_cast<const float4 *>(D.bias + col0 + 4 * u));
+                    const float v0 = __uint_as_float(acc[4 * u + 0]) + bz.x, v1 = __uint_as_float(acc[4 * u + 1]) + bz.y;
+                    const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
+                    if (EPI == EPI_LSTM) {
+                        const float ig = sigm(v0), fg = sigm(v1), gg = tanhf(v2), og = sigm(v3);
+                        const int64_t ci = (int64_t) (j0 + u) * G.c_ld + row;
+                        const float cp = valid ? D.c[ci] : 0.f;
+                        const float cn = fg * cp + ig * gg;
+                        if (valid) D.c[ci] = cn;
+                        hn[u] = og * tanhf(cn);
+                    } else {
+                        const float r = sigm(v0), z = sigm(v1);
+                        const float n = tanhf(v2 + r * v3);
+                        float hp = 0.f;
+                        if (valid && D.hp_hi) {
+                            const int j = j0 + u;
+                            const int64_t o = (int64_t) mt * D.hp_mt_stride + (int64_t) (j >> 5) * TILE_ELEMS + ((j & 31) >> 3) * 1024 + r128 * 8 + (j & 7);
+                            hp = __bfloat162float(D.hp_hi[o]) + __bfloat162float(D.hp_lo[o]);
+                        }
+                        hn[u] = (1.0f - z) * n + z * hp;
+                    }
+                }
+                if (valid) {
+                    uint4 hi, lo;
+                    split8(hn, hi, lo);
+                    const int64_t o = (int64_t) mt * D.y_mt_stride + (int64_t) (D.y_kt0 + (j0 >> 5)) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                    *reinterpret_cast<uint4 *>(D.y_hi + o) = hi;
+                    *reinterpret_cast<uint4 *>(D.y_lo + o) = lo;
+                    if (D.y_f32) {
+                        float4 *dst = reinterpret_cast<float4 *>(D.y_f32 + (int64_t) row * D.ldy + j0);
+                        dst[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                        dst[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- operand preparation kernels
+// int8 images [B][T][F] -> tiled operand [mt][T][1 k-tile] (hi only; |v| <= 128 is exact in bf16)
+__global__ void k_tc_pack_images(const int8_t *__restrict__ img, __nv_bfloat16 *__restrict__ op, int64_t B, int T, int F) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;     // one thread per (row, t, kc)
+    const int64_t total = ceil_div(B, 128) * 128 * T * 4;
+    if (i >= total) return;
+    const int kc = (int) (i & 3);
+    const int64_t rt = i >> 2;
+    const int t = (int) (rt % T);
+    const int64_t row = rt / T;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (row < B) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int k = kc * 8 + e;
+            const float v = (k < F) ? (float) img[(row * T + t) * F + k] : 0.f;
+            w[e >> 1] |= (uint32_t) __bfloat16_as_ushort(__float2bfloat16_rn(v)) << (16 * (e & 1));
+        }
+    }
+    const int64_t o = ((row >> 7) * T + t) * TILE_ELEMS + kc * 1024 + (row & 127) * 8;
+    *reinterpret_cast<uint4 *>(op + o) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+}  // namespace tc
+}  // namespace pb

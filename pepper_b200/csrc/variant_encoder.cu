@@ -26,7 +26,7 @@ namespace pb {
 
 constexpr int TILE = 512;            // positions per k_tile_count CTA
 constexpr int TC_THREADS = 256;
-constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int LIST_CAP = 1024;       // reads scanned per round of k_tile_count
 constexpr int MAX_KEY = 61;          // region_summary.cpp:461,511 candidate_string.length() <= 61
 
 // shared-memory counter columns of k_tile_count (int32 [NCNT][TILE])
@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
     int32_t *cnt = smem;                                   // [NCNT][TILE]
     char *s_ref = reinterpret_cast<char *>(cnt + NCNT * TILE);   // [TILE]
     __shared__ int s_red[2];
+    __shared__ int s_list[LIST_CAP];
+    __shared__ int s_nlist, s_next;
 
     const int t = blockIdx.x;
     const int reg = A.tile_region[t];
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
     const int64_t L1 = rg.ref_end - rg.ref_start + 1;
     const int npos = (int) min((int64_t) TILE, L1 - x0);
     const int64_t lo = rg.ref_start + x0, hi = lo + npos - 1;      // absolute, inclusive
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     for (int i = tid; i < NCNT * TILE; i += TC_THREADS) cnt[i] = 0;
     for (int i = tid; i < TILE; i += TC_THREADS) {
@@ -205,26 +207,34 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
         s_ref[i] = (i < npos && x < rg.ref_len) ? A.ref[rg.ref_off + x] : '\0';
     }
     if (tid < 2) s_red[tid] = 0;
+    if (tid == 0) { s_nlist = 0; s_next = 0; }
     __syncthreads();
 
     const DevReads &R = A.R;
     const VParams &P = A.P;
 
-    // ---- every warp takes groups of 32 reads of the region, lanes test overlap in parallel
-    for (int64_t rb = rg.read_begin + (int64_t) warp * 32; rb < rg.read_end; rb += (int64_t) TC_WARPS * 32) {
-        const int64_t rmine = rb + lane;
-        bool ov = false;
-        if (rmine < rg.read_end && __ldg(R.mapq + rmine) > 0 && R.seq_off[rmine + 1] > R.seq_off[rmine]) {
-            const int64_t p0 = __ldg(R.pos + rmine);
-            const int64_t p1 = p0 + __ldg(A.read_reflen + rmine);      // exclusive end
-            // ops of interest touch [lo-1 .. hi+1]
-            ov = (p0 <= hi + 1) && (p1 >= lo - 1);
+    // ---- overlapping reads are first compacted into a shared list (reads are position sorted, so the ones touching a
+    //      tile are neighbours: handing out groups of 32 consecutive reads per warp would leave most warps idle),
+    //      then warps take reads from the list dynamically
+    for (int64_t blk = rg.read_begin; blk < rg.read_end; blk += LIST_CAP) {
+        const int64_t blk_end = min(rg.read_end, blk + (int64_t) LIST_CAP);
+        for (int64_t rmine = blk + tid; rmine < blk_end; rmine += TC_THREADS) {
+            if (__ldg(R.mapq + rmine) > 0 && R.seq_off[rmine + 1] > R.seq_off[rmine]) {
+                const int64_t p0 = __ldg(R.pos + rmine);
+                const int64_t p1 = p0 + __ldg(A.read_reflen + rmine);      // exclusive end
+                // ops of interest touch [lo-1 .. hi+1]
+                if ((p0 <= hi + 1) && (p1 >= lo - 1)) s_list[atomicAdd(&s_nlist, 1)] = (int) (rmine - blk);
+            }
         }
-        unsigned todo = __ballot_sync(0xffffffffu, ov);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int64_t r = rb + src;
+        __syncthreads();
+        const int nlist = s_nlist;
+        while (true) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&s_next, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= nlist) break;
+            const int64_t r = blk + s_list[item];
+            {
             const int64_t rpos = __ldg(R.pos + r);
             const int64_t so = R.seq_off[r];
             const int64_t lseq = R.seq_off[r + 1] - so;
@@ -364,9 +374,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
                 }
                 if (a_last > hi + 1) break;      // warp-uniform: later ops cannot touch the tile
             }
+            }
         }
+        __syncthreads();
+        if (tid == 0) { s_nlist = 0; s_next = 0; }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- epilogue: derive the columns, site thresholds (region_summary.cpp:634-646), one write per position
     const int64_t g0 = A.region_goff[reg] + x0;

@@ -133,6 +133,7 @@ class PolishNet:
         L.pb_polish_net_destroy.argtypes = [vp]
         L.pb_polish_net_forward_host.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp]
         L.pb_polish_net_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.pb_polish_net_set_mode.argtypes = [vp, C.c_int]
         n = 18
         arrs = _state_arrays(L, state, n, L.pb_polish_net_param_name, L.pb_polish_net_param_numel)
         ptrs = (vp * n)(*[a.ctypes.data for a in arrs])
@@ -164,6 +165,10 @@ class PolishNet:
                                                     acc.ctypes.data if debug else None, C.c_void_p(stream)),
                    "pb_polish_net_forward_host")
         return (bases, phred, hid, acc) if debug else (bases, phred)
+
+    def set_mode(self, mode: int) -> None:
+        """0 = fp32 FFMA GEMMs, 1 = tcgen05 bf16x3 GEMMs (fp32-equivalent)."""
+        _lib.check(self.L.pb_polish_net_set_mode(self.h, mode), "pb_polish_net_set_mode")
 
     def launches(self) -> int:
         n = C.c_int64(0)

@@ -159,6 +159,7 @@ class VariantNet:
         L.pb_variant_net_forward_host.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
         L.pb_variant_net_forward_device.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
         L.pb_variant_net_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.pb_variant_net_set_mode.argtypes = [vp, C.c_int]
         n = 28
         arrs = _state_arrays(L, state, n, L.pb_variant_net_param_name, L.pb_variant_net_param_numel)
         ptrs = (vp * n)(*[a.ctypes.data for a in arrs])
@@ -186,6 +187,10 @@ class VariantNet:
                                                      hid.ctypes.data if return_hidden else None, C.c_void_p(stream)),
                    "pb_variant_net_forward_host")
         return (probs, hid) if return_hidden else probs
+
+    def set_mode(self, mode: int) -> None:
+        """0 = fp32 FFMA GEMMs, 1 = tcgen05 bf16x3 GEMMs (fp32-equivalent)."""
+        _lib.check(self.L.pb_variant_net_set_mode(self.h, mode), "pb_variant_net_set_mode")
 
     def launches(self) -> int:
         n = C.c_int64(0)
