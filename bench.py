@@ -126,6 +126,7 @@ def run_ours(args):
     from pepper_b200 import synth, weights, _lib
     from pepper_b200.abi import HostReads
     from pepper_b200.pipeline import VariantCaller, DeviceReads
+    from pepper_b200.dist import gather_predictions
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -150,15 +151,9 @@ def run_ours(args):
                probs=torch.empty((cap, 3), dtype=torch.float32, device=dev))
 
     def gather(n_cand):
-        """north_star: one NCCL all-gather of the per-region predictions (padded to the max count)."""
-        if world == 1:
-            return
-        cnt = torch.tensor([n_cand], dtype=torch.int64, device=dev)
-        cnts = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(cnts, cnt)
-        m = int(cnts.max().item())
-        allp = torch.empty((world, m, 3), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(allp, out["probs"][:m].contiguous())
+        """north_star: one NCCL all-gather of the per-region predictions (ragged counts, padded to the max)."""
+        if world > 1:
+            gather_predictions(out["probs"], n_cand, world)
 
     def step_device():
         n = caller.call_device(dreads, params, out)
@@ -238,7 +233,7 @@ def run_ours(args):
                     algorithmic_bytes_per_launch=alg_bytes, launch_ms=count_s * 1e3,
                     note="algorithmic bytes of the whole encoder (SURVEY 8d) over the pileup-count kernel's time")
     tf = n_cand * FLOP_PER_CAND / net_s / 1e12
-    roof_net = dict(bound="tensor", kernel="k_gemm_fused (LSTM step / MLP GEMMs, all launches of the step)", achieved=tf,
+    roof_net = dict(bound="tensor", kernel="k_tc_gemm (tcgen05 LSTM-step / MLP GEMMs, all launches of the step; 3 bf16 products per algorithmic FLOP)", achieved=tf,
                     peak=peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], unit="TFLOP/s",
                     frac=tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), traffic=None, peak_source=peaks["source"] + ", sustained bf16",
                     flops_per_step=n_cand * FLOP_PER_CAND, step_ms=net_s * 1e3)
@@ -246,7 +241,7 @@ def run_ours(args):
     line = {
         "metric": "genomic bases/sec (make_images+inference)", "value": value, "unit": "bases/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32 counts / int8 images (encoder), f32 (networks)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "int32 counts / int8 images (encoder); networks f32-equivalent (bf16 hi/lo split x3 on tcgen05, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": "pepper_variant make_images + run_inference, synthetic ONT R9.4.1 30x (BASELINE configs[1])",
                    "regions_per_gpu": regions.n_regions, "region_size": args.region_size, "coverage": args.coverage,
                    "genomic_bases_per_gpu": genomic_bases, "aligned_bases_per_gpu": reads.n_bases, "reads_per_gpu": reads.n_reads,

@@ -62,7 +62,7 @@ struct pb_polish_encoder {
 
 struct pb_variant_net {
     int device = 0;
-    int mode = 0;
+    int mode = 1;          // 1 = tcgen05 bf16x3 (default), 0 = fp32 FFMA
     pb::TcVariant *tc = nullptr;
     pb::DevRnn enc[2], dec[2];
     pb::DevLin lin[5], outl;
@@ -74,7 +74,7 @@ struct pb_variant_net {
 
 struct pb_polish_net {
     int device = 0;
-    int mode = 0;
+    int mode = 1;          // 1 = tcgen05 bf16x3 (default), 0 = fp32 FFMA
     pb::TcPolish *tc = nullptr;
     pb::DevRnn enc[2], dec[2];
     pb::DevBuf dW, dB;

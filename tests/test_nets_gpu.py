@@ -26,6 +26,7 @@ def test_variant_net_golden():
     from pepper_b200.variant import VariantNet
     g = np.load(os.path.join(GOLD, "variant_net_seed0.npz"))
     net = VariantNet(nets.make_variant_weights(0))
+    net.set_mode(0)
     probs, hid = net.predict(g["images"], return_hidden=True)
     assert np.abs(hid[:4] - g["hidden"]).max() < TOL
     assert np.abs(probs - g["probs"]).max() < TOL
@@ -35,14 +36,16 @@ def test_variant_net_golden():
     assert net.launches() == 33 * 2 + 5 + 1
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("n,seed", [(1, 1), (130, 2), (700, 3)])
-def test_variant_net_vs_oracle(n, seed):
+def test_variant_net_vs_oracle(n, seed, mode):
     from oracle import nets
     from pepper_b200.variant import VariantNet
     state = nets.make_variant_weights(seed)
     x = _variant_images(n, seed)
     want, whid = nets.variant_predict(state, x, threads=8, return_hidden=True)
     net = VariantNet(state)
+    net.set_mode(mode)
     got, hid = net.predict(x, return_hidden=True)
     assert np.abs(hid - whid).max() < TOL, np.abs(hid - whid).max()
     assert np.abs(got - want).max() < TOL, np.abs(got - want).max()
@@ -68,6 +71,7 @@ def test_polish_net_golden():
     from pepper_b200.polish import PolishNet
     g = np.load(os.path.join(GOLD, "polish_net_seed0.npz"))
     net = PolishNet(nets.make_polish_weights(0))
+    net.set_mode(0)
     bases, phred, hid, acc = net.predict(g["images"], debug=True)
     assert np.abs(hid[:, :, :, ::8] - g["hidden"]).max() < TOL
     assert np.abs(acc[:, ::10] - g["acc"]).max() < TOL
@@ -87,18 +91,20 @@ def _check_bases(bases, want_bases, want_acc, phred, want_phred, acc_full):
     assert (d <= 1).mean() > 0.999
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("n,seed", [(1, 4), (5, 5), (140, 6)])
-def test_polish_net_vs_oracle(n, seed):
+def test_polish_net_vs_oracle(n, seed, mode):
     from oracle import nets
     from pepper_b200.polish import PolishNet
     state = nets.make_polish_weights(seed)
     x = _polish_images(n, seed)
     wb, wp, wh, wa = nets.polish_predict(state, x, threads=8)
     net = PolishNet(state)
+    net.set_mode(mode)
     bases, phred, hid, acc = net.predict(x, debug=True)
     assert np.abs(hid - wh).max() < TOL, np.abs(hid - wh).max()        # hidden carried through all 19 windows
     assert np.abs(acc - wa).max() < TOL, np.abs(acc - wa).max()
     _check_bases(bases, wb, wa, phred, wp, acc)
     b2, p2 = net.predict(x)
     assert np.array_equal(b2, bases) and np.array_equal(p2, phred)
-    assert net.launches() == 19 * 201 + 1
+    assert net.launches() == (19 * 201 + 1 if mode == 0 else 19 * 203 + 1)
