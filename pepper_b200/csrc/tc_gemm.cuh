@@ -108,10 +108,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+// exp via ex2.approx (2 ulp) + fast divide: absolute error ~1e-6, far inside the 1e-3 parity tolerance
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
 __device__ __forceinline__ float selu(float x) {
     const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
-    return x > 0.f ? scale * x : scale * alpha * (expf(x) - 1.0f);
+    return x > 0.f ? scale * x : scale * alpha * (__expf(x) - 1.0f);
 }
 // 8 fp32 -> 8 bf16 hi + 8 bf16 lo, 16 B each
 __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
@@ -194,13 +199,35 @@ __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
             tc_commit(bar_acc);                         // accumulator complete
         }
     } else {
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
         const int row = mt * BM + q * 32 + lane;
         const bool valid = row < G.M;
         const int r128 = q * 32 + lane;
-#pragma unroll 1
+        // state that does not depend on the accumulator is fetched while the main loop runs:
+        // LSTM cell state c / GRU previous hidden state of this row's 32 units
+        float st[BN / 4];
+        if (EPI == EPI_LSTM) {
+#pragma unroll
+            for (int u = 0; u < BN / 4; u++) st[u] = valid ? D.c[(int64_t) (nt * (BN / 4) + u) * G.c_ld + row] : 0.f;
+        } else if (EPI == EPI_GRU) {
+#pragma unroll
+            for (int u8 = 0; u8 < BN / 32; u8++) {
+                uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+                if (valid && D.hp_hi) {
+                    const int j0 = nt * (BN / 4) + u8 * 8;
+                    const int64_t o = (int64_t) mt * D.hp_mt_stride + (int64_t) (j0 >> 5) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                    h = *reinterpret_cast<const uint4 *>(D.hp_hi + o);
+                    l = *reinterpret_cast<const uint4 *>(D.hp_lo + o);
+                }
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    st[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+            }
+        }
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+#pragma unroll
         for (int cc = 0; cc < BN / 32; cc++) {
             uint32_t acc[32];
             tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
@@ -239,22 +266,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
                     const float v0 = __uint_as_float(acc[4 * u + 0]) + bz.x, v1 = __uint_as_float(acc[4 * u + 1]) + bz.y;
                     const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
                     if (EPI == EPI_LSTM) {
-                        const float ig = sigm(v0), fg = sigm(v1), gg = tanhf(v2), og = sigm(v3);
-                        const int64_t ci = (int64_t) (j0 + u) * G.c_ld + row;
-                        const float cp = valid ? D.c[ci] : 0.f;
-                        const float cn = fg * cp + ig * gg;
-                        if (valid) D.c[ci] = cn;
-                        hn[u] = og * tanhf(cn);
+                        const float ig = sigm(v0), fg = sigm(v1), gg = tanh_fast(v2), og = sigm(v3);
+                        const float cn = fg * st[cc * 8 + u] + ig * gg;
+                        st[cc * 8 + u] = cn;
+                        hn[u] = og * tanh_fast(cn);
                     } else {
                         const float r = sigm(v0), z = sigm(v1);
-                        const float n = tanhf(v2 + r * v3);
-                        float hp = 0.f;
-                        if (valid && D.hp_hi) {
-                            const int j = j0 + u;
-                            const int64_t o = (int64_t) mt * D.hp_mt_stride + (int64_t) (j >> 5) * TILE_ELEMS + ((j & 31) >> 3) * 1024 + r128 * 8 + (j & 7);
-                            hp = __bfloat162float(D.hp_hi[o]) + __bfloat162float(D.hp_lo[o]);
-                        }
-                        hn[u] = (1.0f - z) * n + z * hp;
+                        const float n = tanh_fast(v2 + r * v3);
+                        hn[u] = (1.0f - z) * n + z * st[cc * 8 + u];
                     }
                 }
                 if (valid) {
@@ -270,6 +289,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
                     }
                 }
             }
+        }
+        if (EPI == EPI_LSTM && valid) {
+#pragma unroll
+            for (int u = 0; u < BN / 4; u++) D.c[(int64_t) (nt * (BN / 4) + u) * G.c_ld + row] = st[u];
         }
     }
     tc_fence_before();

@@ -184,7 +184,7 @@ struct TileArgs {
     VParams P;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
+__global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
     extern __shared__ int32_t smem[];
     int32_t *cnt = smem;                                   // [NCNT][TILE]
     char *s_ref = reinterpret_cast<char *>(cnt + NCNT * TILE);   // [TILE]
@@ -259,7 +259,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
                 }
                 first = base;
             }
-            // --- walk chunks of 32 ops
+            // --- walk chunks of 32 ops (all positions below are int32, relative to the tile start `lo`)
+            const int rpos_rel = (int) (rpos - lo);
+            const int end_rel = (int) (rg.ref_end - lo);
+            const int hi_rel = npos - 1;
             for (int j0 = first; j0 < nops; j0 += 32) {
                 const int j = j0 + lane;
                 uint32_t w = 0; int pr = 0, pd = 0;
@@ -269,26 +272,24 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
                 if (j + 1 >= nops) wn = 0xfu;                   // no next op
                 const int op = (j < nops) ? (int) (w & 15) : 15;
                 const int len = (int) (w >> 4);
-                const int64_t a = rpos + pr;                    // ref position at op start
-                const bool live = (j < nops) && (a <= rg.ref_end);     // walker breaks when ref_position > ref_end (:355)
+                const int a = rpos_rel + pr;                    // ref position at op start, relative to lo
+                const bool live = (j < nops) && (a <= end_rel);        // walker breaks when ref_position > ref_end (:355)
                 // chunk exit test: every later op starts at or after this chunk's last start
-                const int64_t a_last = __shfl_sync(0xffffffffu, a, 31);
+                const int a_last = __shfl_sync(0xffffffffu, a, 31);
                 const bool is_m = (op == 0 || op == 7 || op == 8);
                 // clipped per-position segment (M bases or deleted positions)
-                int64_t s0 = 0; int scnt = 0;
+                int s0 = 0, scnt = 0;
                 if (live && (is_m || op == 2)) {
-                    const int64_t b0 = max(a, lo), b1 = min(a + len - 1, hi);
-                    if (b1 >= b0) { s0 = b0; scnt = (int) (b1 - b0 + 1); }
+                    const int b0 = max(a, 0), b1 = min(a + len - 1, hi_rel);
+                    if (b1 >= b0) { s0 = b0; scnt = b1 - b0 + 1; }
                 }
                 // anchor of an I/D after the last base of this M op
                 const int nop = (int) (wn & 15);
-                const bool anchors_next = is_m && (nop == 1 || nop == 2);
-                const int64_t op_last = a + len - 1;
+                const int op_last = (is_m && (nop == 1 || nop == 2)) ? a + len - 1 : -0x40000000;
                 // --- I / D ops anchored in this tile (handled by the op's own lane)
                 if (live && (op == 1 || op == 2)) {
-                    const int64_t p = a - 1;
-                    if (p >= lo && p <= hi) {
-                        const int x = (int) (p - lo);
+                    const int x = a - 1;
+                    if (x >= 0 && x <= hi_rel) {
                         const bool rvalid = ref_class(s_ref[x]) < 4;
                         if (op == 1) {
                             if (pd >= 1) {
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
                         } else {
                             if (rvalid) atomicAdd(&cnt[(C_D_F + rev) * TILE + x], 1);
                             int klen;
-                            if (delete_allele(p - rg.ref_start, len, rg.ref_len, klen)) atomicAdd(&cnt[C_DEL * TILE + x], 1);
+                            if (delete_allele(x0 + x, len, rg.ref_len, klen)) atomicAdd(&cnt[C_DEL * TILE + x], 1);
                         }
                     }
                 }
@@ -315,6 +316,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
                     if (lane >= d) incl += v;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
+                // per-op record for the per-position loop: x = base + idx, read index = rdb + idx
+                const int excl = incl - scnt;
+                const int base_x = s0 - excl;                               // x of position idx
+                const int base_rd = pd + (s0 - a) - excl;                   // read index of position idx (M ops)
+                const int tag = (op == 2) ? -1 : op_last;                   // -1: deleted positions; else anchor x (or none)
                 for (int k0 = 0; k0 < total; k0 += 32) {
                     const int idx = k0 + lane;
                     // smallest l with incl[l] > idx
@@ -325,28 +331,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
                         if (v <= idx) l += step;
                     }
                     l = min(l, 31);
-                    const int o_incl = __shfl_sync(0xffffffffu, incl, l);
-                    const int o_cnt = __shfl_sync(0xffffffffu, scnt, l);
-                    const int64_t o_s0 = __shfl_sync(0xffffffffu, s0, l);
-                    const int64_t o_a = __shfl_sync(0xffffffffu, a, l);
-                    const int o_pd = __shfl_sync(0xffffffffu, pd, l);
-                    const int o_op = __shfl_sync(0xffffffffu, op, l);
-                    const int64_t o_last = __shfl_sync(0xffffffffu, op_last, l);
-                    const int o_anch = __shfl_sync(0xffffffffu, (int) anchors_next, l);
+                    const int o_bx = __shfl_sync(0xffffffffu, base_x, l);
+                    const int o_brd = __shfl_sync(0xffffffffu, base_rd, l);
+                    const int o_tag = __shfl_sync(0xffffffffu, tag, l);
                     if (idx < total) {
-                        const int64_t p = o_s0 + (idx - (o_incl - o_cnt));
-                        const int x = (int) (p - lo);
+                        const int x = o_bx + idx;
                         const char rch = s_ref[x];
                         const int rcls = ref_class(rch);
-                        if (o_op == 2) {
+                        if (o_tag == -1) {
                             if (rcls < 4) atomicAdd(&cnt[(C_S_F + rev) * TILE + x], 1);
                         } else {
-                            const int64_t ri = (int64_t) o_pd + (p - o_a);
-                            const int q = __ldg(R.qual + so + ri);
+                            const int64_t ri = so + (int64_t) (o_brd + idx);
+                            const int q = __ldg(R.qual + ri);
                             if (q >= P.minq_snp) {
-                                const int code = seq_code_at(R.seq, so + ri);
+                                const int code = seq_code_at(R.seq, ri);
                                 atomicAdd(&cnt[(C_TOT_F + rev) * TILE + x], 1);
-                                if (o_anch && p == o_last) atomicAdd(&cnt[(C_ANC_F + rev) * TILE + x], 1);
+                                if (x == o_tag) atomicAdd(&cnt[(C_ANC_F + rev) * TILE + x], 1);
                                 const int cls = base_class(code);
                                 if (rcls < 4) {
                                     if (cls < 4) {
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tile_count(TileArgs A) {
                         }
                     }
                 }
-                if (a_last > hi + 1) break;      // warp-uniform: later ops cannot touch the tile
+                if (a_last > hi_rel + 1) break;  // warp-uniform: later ops cannot touch the tile
             }
             }
         }
