@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
     extern __shared__ int32_t smem[];
     int32_t *cnt = smem;                                   // [NCNT][TILE]
     char *s_ref = reinterpret_cast<char *>(cnt + NCNT * TILE);   // [TILE]
+    uint8_t *s_rinfo = reinterpret_cast<uint8_t *>(s_ref + TILE);  // [TILE]
     __shared__ int s_red[2];
     __shared__ int s_list[LIST_CAP];
     __shared__ int s_nlist, s_next;
@@ -204,7 +205,14 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
     for (int i = tid; i < NCNT * TILE; i += TC_THREADS) cnt[i] = 0;
     for (int i = tid; i < TILE; i += TC_THREADS) {
         const int64_t x = x0 + i;
-        s_ref[i] = (i < npos && x < rg.ref_len) ? A.ref[rg.ref_off + x] : '\0';
+        const char c = (i < npos && x < rg.ref_len) ? A.ref[rg.ref_off + x] : '\0';
+        s_ref[i] = c;
+        // bits 0-3: NT16 code of the reference character, bit 4: not an (upper-case) NT16 character -> every read base
+        // mismatches it (raw char compare, region_summary.cpp:394), bits 5-7: column class (0-3 = A,C,G,T; 7 = invalid)
+        int code = 16;
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (c == nt16_char(k)) code = k;
+        s_rinfo[i] = (uint8_t) (code | (ref_class(c) << 5));
     }
     if (tid < 2) s_red[tid] = 0;
     if (tid == 0) { s_nlist = 0; s_next = 0; }
@@ -336,27 +344,28 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
                     const int o_tag = __shfl_sync(0xffffffffu, tag, l);
                     if (idx < total) {
                         const int x = o_bx + idx;
-                        const char rch = s_ref[x];
-                        const int rcls = ref_class(rch);
+                        const uint32_t rinfo = s_rinfo[x];
+                        const int rcls = (int) (rinfo >> 5);
                         if (o_tag == -1) {
                             if (rcls < 4) atomicAdd(&cnt[(C_S_F + rev) * TILE + x], 1);
                         } else {
                             const int64_t ri = so + (int64_t) (o_brd + idx);
                             const int q = __ldg(R.qual + ri);
+                            const int code = seq_code_at(R.seq, ri);
                             if (q >= P.minq_snp) {
-                                const int code = seq_code_at(R.seq, ri);
                                 atomicAdd(&cnt[(C_TOT_F + rev) * TILE + x], 1);
-                                if (x == o_tag) atomicAdd(&cnt[(C_ANC_F + rev) * TILE + x], 1);
                                 const int cls = base_class(code);
-                                if (rcls < 4) {
+                                // rare paths: anchor of an indel, column differing from the reference column, raw mismatch
+                                if (x == o_tag) atomicAdd(&cnt[(C_ANC_F + rev) * TILE + x], 1);
+                                if (rcls < 4 && cls != rcls) {
                                     if (cls < 4) {
-                                        if (cls != rcls) atomicAdd(&cnt[(C_A_F + 4 * rev + cls) * TILE + x], 1);
+                                        atomicAdd(&cnt[(C_A_F + 4 * rev + cls) * TILE + x], 1);
                                     } else {
                                         atomicAdd(&cnt[(C_NON_F + rev) * TILE + x], 1);
                                         atomicAdd(&cnt[((cls == 4 ? C_D_F : C_S_F) + rev) * TILE + x], 1);
                                     }
                                 }
-                                if (nt16_char(code) != rch) {
+                                if ((rinfo & 31u) != (uint32_t) code) {          // nt16_char(code) != reference character
                                     atomicAdd(&cnt[C_SNP * TILE + x], 1);
                                     if (rcls >= 4 || cls >= 4) {
                                         atomicAdd(&cnt[C_RARE * TILE + x], 1);
@@ -844,7 +853,7 @@ extern "C" int pb_variant_encoder_create(pb_variant_encoder_t **out, int device)
     e->device = device;
     for (auto &ev : e->evt) PB_CUDA(cudaEventCreate(&ev));
     PB_CUDA(cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int) (NCNT * TILE * sizeof(int32_t) + TILE)));
+                                 (int) (NCNT * TILE * sizeof(int32_t) + 2 * TILE)));
     *out = e;
     return PB_OK;
 }
@@ -978,7 +987,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
     TA.tile_nsites = e->tile_nsites.as<int32_t>(); TA.tile_nev = e->tile_nev.as<int32_t>();
     TA.rare = e->rare.as<RareEv>(); TA.rare_n = reinterpret_cast<unsigned long long *>(sc + 2); TA.rare_cap = e->rare_cap;
     TA.P = P;
-    const size_t tc_smem = NCNT * TILE * sizeof(int32_t) + TILE;
+    const size_t tc_smem = NCNT * TILE * sizeof(int32_t) + 2 * TILE;
     unsigned long long n_rare = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         k_tile_count<<<(unsigned) n_tiles, TC_THREADS, tc_smem, st>>>(TA);
