@@ -175,11 +175,15 @@ def run_ours(args):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     enc_ms, net_ms, count_ms = [], [], []
+    enc_parts = {}
     ev0.record()
     for _ in range(args.steps):
         n_cand = step_device()
         t = caller.timings()
         enc_ms.append(t["encode_ms"]); net_ms.append(t["network_ms"]); count_ms.append(t["enc_count"])
+        for k, v in t.items():
+            if k.startswith("enc_"):
+                enc_parts.setdefault(k, []).append(v)
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -254,7 +258,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "api": "pepper_b200.pipeline.VariantCaller.call -> pb_variant_call_host (pinned host buffers)"},
         "gpu_launches": int(gpu_launches),
-        "phase_ms": {"encoder": float(np.mean(enc_ms)), "network": float(np.mean(net_ms)), "encoder_count_kernel": float(np.mean(count_ms))},
+        "phase_ms": {"encoder": float(np.mean(enc_ms)), "network": float(np.mean(net_ms)), "encoder_count_kernel": float(np.mean(count_ms)),
+                     "encoder_phases": {k: float(np.mean(v)) for k, v in enc_parts.items()}},
         "roofline": roof_net,
         "roofline_encoder": roof_enc,
     }
@@ -389,7 +394,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--regions", type=int, default=int(os.environ.get("PB_BENCH_REGIONS", "64")),
+    ap.add_argument("--regions", type=int, default=int(os.environ.get("PB_BENCH_REGIONS", "645")),
                     help="100 kb regions per GPU per step (chr20 = 645)")
     ap.add_argument("--region-size", type=int, default=100000)
     ap.add_argument("--coverage", type=float, default=30.0)

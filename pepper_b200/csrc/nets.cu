@@ -358,7 +358,7 @@ extern "C" int64_t pb_variant_net_param_numel(int i) { return (i >= 0 && i < PB_
 
 
 constexpr int VT = 33, VH = 256;
-constexpr int64_t VARIANT_CHUNK = 8192;
+constexpr int64_t VARIANT_CHUNK = 9472;     // 74 row tiles: 74 x 8 x 2 CTAs = 4 full waves of 2 CTAs x 148 SMs per LSTM step
 
 extern "C" int pb_variant_net_create(pb_variant_net_t **out, int device, const float *const *P) {
     if (!out || !P) { set_error("null argument"); return PB_ERR_ARG; }

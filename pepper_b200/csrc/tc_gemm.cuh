@@ -25,7 +25,8 @@ constexpr int TILE_ELEMS = 128 * BK;                 // 4096 bf16
 constexpr int TILE_BYTES = TILE_ELEMS * 2;           // 8192
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
-constexpr int THREADS = 192;                         // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int THREADS = 320;                         // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue
+constexpr int EPI_COLS = BN / 2;                     // columns per epilogue warp (two warps share a TMEM lane quarter)
 constexpr int TMEM_COLS = 128;
 
 enum { EPI_BIAS = 0, EPI_SELU = 1, EPI_LSTM = 2, EPI_GRU = 3 };
@@ -135,6 +136,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo
 
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
+    static_assert(THREADS == 64 + 8 * 32, "warp roles");
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES), bar_acc = smem_u32(bars + 2 * STAGES);
@@ -200,21 +202,23 @@ __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
         }
     } else {
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;               // which half of the 128 accumulator columns
         const int row = mt * BM + q * 32 + lane;
         const bool valid = row < G.M;
         const int r128 = q * 32 + lane;
         // state that does not depend on the accumulator is fetched while the main loop runs:
         // LSTM cell state c / GRU previous hidden state of this row's 32 units
-        float st[BN / 4];
+        float st[EPI_COLS / 4];
+        const int ubase = nt * (BN / 4) + half * (EPI_COLS / 4);       // first hidden unit of this warp
         if (EPI == EPI_LSTM) {
 #pragma unroll
-            for (int u = 0; u < BN / 4; u++) st[u] = valid ? D.c[(int64_t) (nt * (BN / 4) + u) * G.c_ld + row] : 0.f;
+            for (int u = 0; u < EPI_COLS / 4; u++) st[u] = valid ? D.c[(int64_t) (ubase + u) * G.c_ld + row] : 0.f;
         } else if (EPI == EPI_GRU) {
 #pragma unroll
-            for (int u8 = 0; u8 < BN / 32; u8++) {
+            for (int u8 = 0; u8 < EPI_COLS / 32; u8++) {
                 uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
                 if (valid && D.hp_hi) {
-                    const int j0 = nt * (BN / 4) + u8 * 8;
+                    const int j0 = ubase + u8 * 8;
                     const int64_t o = (int64_t) mt * D.hp_mt_stride + (int64_t) (j0 >> 5) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
                     h = *reinterpret_cast<const uint4 *>(D.hp_hi + o);
                     l = *reinterpret_cast<const uint4 *>(D.hp_lo + o);
@@ -228,7 +232,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
         mbar_wait(bar_acc, 0);
         tc_fence_after();
 #pragma unroll
-        for (int cc = 0; cc < BN / 32; cc++) {
+        for (int cl = 0; cl < EPI_COLS / 32; cl++) {
+            const int cc = half * (EPI_COLS / 32) + cl;
             uint32_t acc[32];
             tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
             const int col0 = nt * BN + cc * 32;
@@ -267,13 +272,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
                     const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
                     if (EPI == EPI_LSTM) {
                         const float ig = sigm(v0), fg = sigm(v1), gg = tanh_fast(v2), og = sigm(v3);
-                        const float cn = fg * st[cc * 8 + u] + ig * gg;
-                        st[cc * 8 + u] = cn;
+                        const float cn = fg * st[cl * 8 + u] + ig * gg;
+                        st[cl * 8 + u] = cn;
                         hn[u] = og * tanh_fast(cn);
                     } else {
                         const float r = sigm(v0), z = sigm(v1);
                         const float n = tanh_fast(v2 + r * v3);
-                        hn[u] = (1.0f - z) * n + z * st[cc * 8 + u];
+                        hn[u] = (1.0f - z) * n + z * st[cl * 8 + u];
                     }
                 }
                 if (valid) {
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
         }
         if (EPI == EPI_LSTM && valid) {
 #pragma unroll
-            for (int u = 0; u < BN / 4; u++) D.c[(int64_t) (nt * (BN / 4) + u) * G.c_ld + row] = st[u];
+            for (int u = 0; u < EPI_COLS / 4; u++) D.c[(int64_t) (ubase + u) * G.c_ld + row] = st[u];
         }
     }
     tc_fence_before();
