@@ -201,7 +201,21 @@ class PolishCaller:
             k = int(n.value)
             return PolishCalls(bases[:k], phred[:k], position[:k], index[:k], ireg[:k], cid[:k])
 
+    def call_device(self, dreads: DeviceReads, out: dict, stream: int = 0) -> int:
+        """Everything in HBM.  `out`: torch CUDA tensors bases/phred uint8 [cap,1000], position int64 [cap,1000],
+        index int32 [cap,1000], image_region/chunk_id int32 [cap]."""
+        n = C.c_int64(0)
+        cap = int(out["bases"].shape[0])
+        rc = self.L.pb_polish_call_device(self.enc.h, self.net.h, C.byref(dreads.struct), dreads.d_regions, dreads.n_regions,
+                                          dreads.h_regions, cap, out["bases"].data_ptr(), out["phred"].data_ptr(),
+                                          out["position"].data_ptr(), out["index"].data_ptr(), out["image_region"].data_ptr(),
+                                          out["chunk_id"].data_ptr(), C.byref(n), C.c_void_p(stream))
+        _lib.check(rc, "pb_polish_call_device")
+        return int(n.value)
+
     def timings(self) -> dict:
         ms = (C.c_float * 2)()
         _lib.check(self.L.pb_polish_call_timings(self.enc.h, ms), "timings")
-        return dict(encode_ms=float(ms[0]), network_ms=float(ms[1]))
+        d = dict(encode_ms=float(ms[0]), network_ms=float(ms[1]))
+        d.update({"enc_" + k: v for k, v in self.enc.timings().items()})
+        return d

@@ -84,3 +84,23 @@ def test_chunking_matches_reference_rule(enc):
         last = mine[-1]
         pad = np.nonzero(pos[last] == -1)[0]
         assert (imgs[last][pad] == 0).all()
+
+
+def test_more_reads_than_one_list_round(oracle_built, enc):
+    rng = np.random.default_rng(98)
+    S = 100
+    reads = []
+    for k in range(2300):
+        a = int(rng.integers(0, 900)); n = int(rng.integers(80, 200))
+        seq = "".join("ACGTN"[i] for i in rng.integers(0, 5, n))
+        if rng.random() < 0.3:
+            p = n // 2
+            reads.append(dict(pos=S + a, seq=seq, qual=20, cigar=[(0, p), (1, 3), (0, n - p - 3)], reverse=bool(k % 2)))
+        elif rng.random() < 0.3:
+            p = n // 2
+            reads.append(dict(pos=S + a, seq=seq, qual=20, cigar=[(0, p), (2, 4), (0, n - p)], reverse=bool(k % 2)))
+        else:
+            reads.append(dict(pos=S + a, seq=seq, qual=20, cigar=[(0, n)], reverse=bool(k % 2), mapq=int(k % 50 != 0) * 60))
+    reads.sort(key=lambda r: r["pos"])
+    tab = np.array([[S, S + 1100, S, S + 1100, 0, 0, 0, len(reads)]], dtype=np.int64)
+    _compare(oracle_built, enc, synth.make_batch(reads), synth.RegionTable(tab, np.zeros(1, np.uint8)), "deep")

@@ -122,3 +122,38 @@ def test_properties_full_size(enc):
         code = {65: 1, 67: 2, 71: 3, 84: 4}.get(int(ref[regions.table[r, 4] + x]), 5)
         assert a.images[i, 16, 0] == code
     assert 500 < len(a) < 20000
+
+
+def test_more_reads_than_one_list_round(oracle_built, enc):
+    """> 1024 reads in one region: k_tile_count scans the region's reads in several rounds (LIST_CAP);
+    also a very deep pileup (coverage ~ 390) with mixed indels."""
+    rng = np.random.default_rng(99)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 1800))
+    S = 5000
+    reads = []
+    for k in range(2600):
+        a = int(rng.integers(0, 1500))
+        n = int(rng.integers(120, 300))
+        seg = list(ref[a:a + n])
+        cig = []
+        if rng.random() < 0.3 and n > 60:                    # one SNP
+            p = int(rng.integers(5, n - 5)); seg[p] = "ACGT"[(("ACGT".index(seg[p])) + 1) % 4]
+        if rng.random() < 0.25 and n > 80:                   # one deletion of 1-3
+            p = int(rng.integers(20, n - 30)); d = int(rng.integers(1, 4))
+            seq = "".join(seg[:p] + seg[p + d:])
+            cig = [(0, p), (2, d), (0, n - p - d)]
+        elif rng.random() < 0.25 and n > 80:                 # one insertion of 1-2
+            p = int(rng.integers(20, n - 30)); ins = "".join("ACGT"[i] for i in rng.integers(0, 4, int(rng.integers(1, 3))))
+            seq = "".join(seg[:p]) + ins + "".join(seg[p:])
+            cig = [(0, p), (1, len(ins)), (0, n - p)]
+        else:
+            seq = "".join(seg); cig = [(0, n)]
+        reads.append(dict(pos=S + a, seq=seq, qual=[int(q) for q in rng.integers(1, 40, len(seq))], cigar=cig,
+                          reverse=bool(rng.random() < 0.5), mapq=int(60 if rng.random() > 0.02 else 0)))
+    reads.sort(key=lambda r: r["pos"])
+    batch = synth.make_batch(reads)
+    tab = np.array([[S, S + 1799, S + 100, S + 1700, 0, 1800, 0, len(reads)]], dtype=np.int64)
+    regions = synth.RegionTable(tab, np.frombuffer(ref.encode(), dtype=np.uint8).copy())
+    got = _compare(oracle_built, enc, batch, regions, synth.ont_params(), "deep")
+    assert len(got) > 50
+    assert got.depths.max() == 125            # clamped depth
