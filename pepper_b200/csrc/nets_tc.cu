@@ -4,6 +4,7 @@
 #include "tc_gemm.cuh"
 #include <vector>
 #include <algorithm>
+#include <stdlib.h>
 
 using namespace pb;
 using tc::Args;
@@ -29,16 +30,17 @@ static inline float bf2f(uint16_t h) {
 }
 
 // row-major [rows][K] fp32 (rows % 128 == 0 after padding, K % 32 == 0 after padding) -> hi / lo tiles [rt][kt][4][128][8]
-static void tile_matrix(const float *src, int64_t rows, int64_t K, int64_t rows_p, int64_t Kp, std::vector<uint16_t> &hi, std::vector<uint16_t> &lo) {
-    const int64_t RT = rows_p / 128, KT = Kp / 32;
-    hi.assign((size_t) (RT * KT * TILE_ELEMS), 0);
-    lo.assign((size_t) (RT * KT * TILE_ELEMS), 0);
+static void tile_matrix(const float *src, int64_t rows, int64_t K, int64_t rows_p, int64_t Kp, std::vector<uint16_t> &hi, std::vector<uint16_t> &lo,
+                        int64_t TR = 128 /* rows per tile: 128 for A operands, 256 for the weights of the persistent kernel */) {
+    const int64_t RT = rows_p / TR, KT = Kp / 32;
+    hi.assign((size_t) (RT * KT * TR * 32), 0);
+    lo.assign((size_t) (RT * KT * TR * 32), 0);
     for (int64_t r = 0; r < rows; r++)
         for (int64_t k = 0; k < K; k++) {
             const float v = src[r * K + k];
             const uint16_t h = f2bf(v);
             const uint16_t l = f2bf(v - bf2f(h));
-            const int64_t o = ((r / 128) * KT + k / 32) * TILE_ELEMS + ((k % 32) / 8) * 1024 + (r % 128) * 8 + (k % 8);
+            const int64_t o = ((r / TR) * KT + k / 32) * (TR * 32) + ((k % 32) / 8) * (TR * 8) + (r % TR) * 8 + (k % 8);
             hi[(size_t) o] = h;
             lo[(size_t) o] = l;
         }
@@ -62,20 +64,42 @@ int tc_upload_rnn(TcRnn &T, const float *Wp /* [4H][Kp_src] */, int K0, int K0p_
         for (int k = 0; k < H; k++) W[(size_t) n * Kp + K0p + k] = Wp[(size_t) n * Kp_src + K0p_src + k];
     }
     std::vector<uint16_t> hi, lo;
-    tile_matrix(W.data(), 4 * H, Kp, 4 * H, Kp, hi, lo);
+    tile_matrix(W.data(), 4 * H, Kp, 4 * H, Kp, hi, lo, 256);
     T.nkt_x = K0p / 32; T.nkt_h = H / 32;
     return upload_tiles(T.w_hi, T.w_lo, hi, lo);
 }
 int tc_upload_lin(TcLin &T, const float *w, int N, int K) {
     std::vector<uint16_t> hi, lo;
-    const int Np = (N + 127) / 128 * 128, Kp = (K + 31) / 32 * 32;
-    tile_matrix(w, N, K, Np, Kp, hi, lo);
+    const int Np = (N + 255) / 256 * 256, Kp = (K + 31) / 32 * 32;
+    tile_matrix(w, N, K, Np, Kp, hi, lo, 256);
     T.nkt = Kp / 32;
     return upload_tiles(T.w_hi, T.w_lo, hi, lo);
 }
 
+static int g_num_sms = 0;
+
+// persistent 128x256-tile kernel (weights packed in 256-row tiles); `nt128` = number of 128-column tiles = N / 128
 template <int EPI>
-static int launch_tc(const Args &A, int mt, int nt, int ndir, cudaStream_t st) {
+static int launch_tc(const Args &A, int mt, int nt128, int ndir, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(tc::k_tc_gemm_p<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSMEM_BYTES));
+        attr_set = true;
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        PB_CUDA(cudaGetDevice(&dev));
+        PB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (nt128 % 2) { set_error("tcgen05 path needs N %% 256 == 0"); return PB_ERR_ARG; }
+    const int nt = nt128 / 2;
+    const int tiles = mt * nt * ndir;
+    tc::k_tc_gemm_p<EPI><<<(unsigned) std::min(tiles, g_num_sms), tc::THREADS, tc::PSMEM_BYTES, st>>>(A, mt, nt, ndir);
+    return PB_OK;
+}
+// one 128x128 tile per CTA, two CTAs per SM (first tcgen05 version; kept for N %% 256 != 0 and as a cross-check)
+template <int EPI>
+static int launch_tc128(const Args &A, int mt, int nt, int ndir, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(tc::k_tc_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -313,8 +337,9 @@ extern "C" int pb_test_tc_gemm(int M, int N, int K, const float *h_A, const floa
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { set_error("no CUDA device: libpepper_b200 has no CPU fallback"); return PB_ERR_CUDA; }
     const int64_t Mt = ceil_div(M, 128);
     std::vector<uint16_t> ahi, alo, whi, wlo;
+    const bool big = (N % 256) == 0;
     tile_matrix(h_A, M, K, Mt * 128, K, ahi, alo);
-    tile_matrix(h_W, N, K, N, K, whi, wlo);
+    tile_matrix(h_W, N, K, N, K, whi, wlo, big ? 256 : 128);
     DevBuf dahi, dalo, dwhi, dwlo, dbias, dout;
     PB_TRY(upload_tiles(dahi, dalo, ahi, alo));
     PB_TRY(upload_tiles(dwhi, dwlo, whi, wlo));
@@ -329,7 +354,8 @@ extern "C" int pb_test_tc_gemm(int M, int N, int K, const float *h_A, const floa
     D.bias = dbias.as<float>();
     D.y_f32 = dout.as<float>(); D.ldy = N;
     A.d[0] = D; A.d[1] = D;
-    PB_TRY(launch_tc<tc::EPI_BIAS>(A, (int) Mt, N / 128, 1, 0));
+    if (big) PB_TRY(launch_tc<tc::EPI_BIAS>(A, (int) Mt, N / 128, 1, 0));
+    else PB_TRY(launch_tc128<tc::EPI_BIAS>(A, (int) Mt, N / 128, 1, 0));
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaDeviceSynchronize());
     PB_CUDA(cudaMemcpy(h_out, dout.p, sizeof(float) * (size_t) M * N, cudaMemcpyDeviceToHost));

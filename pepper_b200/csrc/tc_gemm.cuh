@@ -307,6 +307,239 @@ __global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
     }
 }
 
+// ---------------------------------------------------------------- persistent variant
+// One CTA per SM loops over output tiles (static round-robin).  The accumulator is double buffered in TMEM (2 x 128
+// columns) and the shared-memory ring is shared by consecutive tiles, so the MMA warp starts tile i+1 while the eight
+// epilogue warps are still applying the cell of tile i: the tensor pipe no longer idles during prologue / epilogue.
+// Tiles are 128 x 256 here: one tcgen05.mma covers N = 256, which halves the number of MMA instructions the single
+// issuing thread has to retire per FLOP (with N = 128 one thread cannot keep the tensor pipe busy; measured 52 %).
+constexpr int PBN = 256;
+constexpr int PSTAGES = 4;
+constexpr int WTILE_ELEMS = PBN * BK;                 // 8192 bf16: weight tile image [kc][256 rows][8]
+constexpr int WTILE_BYTES = WTILE_ELEMS * 2;
+constexpr int PSTAGE_BYTES = 2 * TILE_BYTES + 2 * WTILE_BYTES;   // A_hi, A_lo, B_hi, B_lo = 48 KB
+constexpr int PSMEM_BYTES = PSTAGES * PSTAGE_BYTES + 256;
+constexpr int PTMEM_COLS = 2 * PBN;                   // double-buffered accumulator = all 512 TMEM columns
+constexpr int PEPI_COLS = PBN / 2;                    // columns per epilogue warp
+constexpr uint32_t IDESC256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (PBN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+__device__ __forceinline__ uint64_t smem_desc_lbo(uint32_t addr, uint32_t lbo) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((addr >> 4) & 0x3FFF);
+    d |= (uint64_t) ((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t) ((128u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t) 1 << 46;
+    return d;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1) k_tc_gemm_p(Args G, int n_mt, int n_nt /* 256-column tiles */, int n_dir) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PSTAGES * PSTAGE_BYTES);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + PSTAGES);
+    const uint32_t bar_accf = smem_u32(bars + 2 * PSTAGES), bar_acce = smem_u32(bars + 2 * PSTAGES + 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * PSTAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = n_mt * n_nt * n_dir;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PSTAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) PTMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (dir, mt, nt): nt fastest so that CTAs running together share the A row tile
+    auto decode = [&](int tile, int &dir, int &mt, int &nt) {
+        nt = tile % n_nt;
+        const int r = tile / n_nt;
+        mt = r % n_mt;
+        dir = r / n_mt;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;                                   // running k-tile counter across tiles
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int dir, mt, nt;
+                decode(tile, dir, mt, nt);
+                const Dir &D = G.d[dir];
+                const int nkt0 = D.seg[0].nkt, nkt = nkt0 + D.seg[1].nkt;
+                for (int kt = 0; kt < nkt; kt++, g++) {
+                    const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    const Seg &S = (kt < nkt0) ? D.seg[0] : D.seg[1];
+                    const int64_t off = (int64_t) mt * S.mt_stride + (int64_t) ((kt < nkt0) ? kt : kt - nkt0) * TILE_ELEMS;
+                    const uint32_t st = smem_base + s * PSTAGE_BYTES;
+                    mbar_expect_tx(bar_full + 8 * s, (S.lo ? 2u : 1u) * TILE_BYTES + 2u * WTILE_BYTES);
+                    bulk_g2s(st, S.hi + off, TILE_BYTES, bar_full + 8 * s);
+                    if (S.lo) bulk_g2s(st + TILE_BYTES, S.lo + off, TILE_BYTES, bar_full + 8 * s);
+                    const int64_t woff = ((int64_t) nt * D.w_nkt + kt) * WTILE_ELEMS;
+                    bulk_g2s(st + 2 * TILE_BYTES, D.w_hi + woff, WTILE_BYTES, bar_full + 8 * s);
+                    bulk_g2s(st + 2 * TILE_BYTES + WTILE_BYTES, D.w_lo + woff, WTILE_BYTES, bar_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+                int dir, mt, nt;
+                decode(tile, dir, mt, nt);
+                const Dir &D = G.d[dir];
+                const int nkt0 = D.seg[0].nkt, nkt = nkt0 + D.seg[1].nkt;
+                const uint32_t buf = it & 1u, use = it >> 1;
+                mbar_wait(bar_acce + 8 * buf, (use & 1u) ^ 1u);        // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * PBN;
+                for (int kt = 0; kt < nkt; kt++, g++) {
+                    const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const bool has_lo = ((kt < nkt0) ? D.seg[0].lo : D.seg[1].lo) != nullptr;
+                    const uint32_t st = smem_base + s * PSTAGE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ks++) {
+                        const uint64_t a_hi = smem_desc_lbo(st + ks * 4096, 2048), a_lo = smem_desc_lbo(st + TILE_BYTES + ks * 4096, 2048);
+                        const uint64_t b_hi = smem_desc_lbo(st + 2 * TILE_BYTES + ks * 8192, 4096);
+                        const uint64_t b_lo = smem_desc_lbo(st + 2 * TILE_BYTES + WTILE_BYTES + ks * 8192, 4096);
+                        tc_mma(tacc, a_hi, b_hi, IDESC256, (kt > 0 || ks > 0) ? 1u : 0u);
+                        tc_mma(tacc, a_hi, b_lo, IDESC256, 1u);
+                        if (has_lo) tc_mma(tacc, a_lo, b_hi, IDESC256, 1u);
+                    }
+                    tc_commit(bar_empty + 8 * s);
+                }
+                tc_commit(bar_accf + 8 * buf);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int r128 = q * 32 + lane;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            int dir, mt, nt;
+            decode(tile, dir, mt, nt);
+            const Dir &D = G.d[dir];
+            const uint32_t buf = it & 1u, use = it >> 1;
+            const int row = mt * BM + r128;
+            const bool valid = row < G.M;
+            float st[PEPI_COLS / 4];
+            const int ubase = nt * (PBN / 4) + half * (PEPI_COLS / 4);
+            if (EPI == EPI_LSTM) {
+#pragma unroll
+                for (int u = 0; u < PEPI_COLS / 4; u++) st[u] = valid ? D.c[(int64_t) (ubase + u) * G.c_ld + row] : 0.f;
+            } else if (EPI == EPI_GRU) {
+#pragma unroll
+                for (int u8 = 0; u8 < PEPI_COLS / 32; u8++) {
+                    uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+                    if (valid && D.hp_hi) {
+                        const int j0 = ubase + u8 * 8;
+                        const int64_t o = (int64_t) mt * D.hp_mt_stride + (int64_t) (j0 >> 5) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                        h = *reinterpret_cast<const uint4 *>(D.hp_hi + o);
+                        l = *reinterpret_cast<const uint4 *>(D.hp_lo + o);
+                    }
+                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                    for (int e = 0; e < 8; e++)
+                        st[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+                }
+            }
+            mbar_wait(bar_accf + 8 * buf, use & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int cl = 0; cl < PEPI_COLS / 32; cl++) {
+                const int cc = half * (PEPI_COLS / 32) + cl;
+                const int col0 = nt * PBN + cc * 32;
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + buf * PBN + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
+                if (cl == PEPI_COLS / 32 - 1) {
+                    // last read of this accumulator buffer by this warp: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+                }
+                if (EPI == EPI_BIAS || EPI == EPI_SELU) {
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; g8++) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float x = __uint_as_float(acc[g8 * 8 + i]) + __ldg(D.bias + col0 + g8 * 8 + i);
+                            v[i] = (EPI == EPI_SELU) ? selu(x) : x;
+                        }
+                        if (valid) {
+                            if (D.y_hi) {
+                                uint4 hi, lo;
+                                split8(v, hi, lo);
+                                const int64_t o = (int64_t) mt * D.y_mt_stride + (int64_t) (D.y_kt0 + col0 / 32) * TILE_ELEMS + g8 * 1024 + r128 * 8;
+                                *reinterpret_cast<uint4 *>(D.y_hi + o) = hi;
+                                *reinterpret_cast<uint4 *>(D.y_lo + o) = lo;
+                            }
+                            if (D.y_f32) {
+                                float4 *dst = reinterpret_cast<float4 *>(D.y_f32 + (int64_t) row * D.ldy + col0 + g8 * 8);
+                                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            }
+                        }
+                    }
+                } else {
+                    const int j0 = col0 >> 2;
+                    float hn[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const float4 bz = __ldg(reinterpret_cast<const float4 *>(D.bias + col0 + 4 * u));
+                        const float v0 = __uint_as_float(acc[4 * u + 0]) + bz.x, v1 = __uint_as_float(acc[4 * u + 1]) + bz.y;
+                        const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
+                        if (EPI == EPI_LSTM) {
+                            const float ig = sigm(v0), fg = sigm(v1), gg = tanh_fast(v2), og = sigm(v3);
+                            const float cn = fg * st[cl * 8 + u] + ig * gg;
+                            st[cl * 8 + u] = cn;
+                            hn[u] = og * tanh_fast(cn);
+                        } else {
+                            const float r = sigm(v0), z = sigm(v1);
+                            const float n = tanh_fast(v2 + r * v3);
+                            hn[u] = (1.0f - z) * n + z * st[cl * 8 + u];
+                        }
+                    }
+                    if (valid) {
+                        uint4 hi, lo;
+                        split8(hn, hi, lo);
+                        const int64_t o = (int64_t) mt * D.y_mt_stride + (int64_t) (D.y_kt0 + (j0 >> 5)) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                        *reinterpret_cast<uint4 *>(D.y_hi + o) = hi;
+                        *reinterpret_cast<uint4 *>(D.y_lo + o) = lo;
+                        if (D.y_f32) {
+                            float4 *dst = reinterpret_cast<float4 *>(D.y_f32 + (int64_t) row * D.ldy + j0);
+                            dst[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                            dst[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                        }
+                    }
+                }
+            }
+            if (EPI == EPI_LSTM && valid) {
+#pragma unroll
+                for (int u = 0; u < PEPI_COLS / 4; u++) D.c[(int64_t) (ubase + u) * G.c_ld + row] = st[u];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) PTMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- operand preparation kernels
 // int8 images [B][T][F] -> tiled operand [mt][T][1 k-tile] (hi only; |v| <= 128 is exact in bf16)
 __global__ void k_tc_pack_images(const int8_t *__restrict__ img, __nv_bfloat16 *__restrict__ op, int64_t B, int T, int F) {
