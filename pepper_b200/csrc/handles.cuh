@@ -43,6 +43,10 @@ struct pb_variant_encoder {
     cudaEvent_t pevt[3] = {nullptr, nullptr, nullptr};
     float pms[2] = {0, 0};
     int64_t launches = 0;
+    // pipelined host entry (pipeline.cu): double-buffered staging + copy stream
+    pb::DevBuf g_buf[2][10];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr};
 };
 
 struct pb_polish_encoder {

@@ -3,6 +3,8 @@
 // feeds the network directly.
 #include "handles.cuh"
 #include <algorithm>
+#include <vector>
+#include <stdint.h>
 
 using namespace pb;
 
@@ -56,14 +58,58 @@ extern "C" int pb_variant_call_device(pb_variant_encoder_t *enc, pb_variant_net_
     return PB_OK;
 }
 
-extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *net, const pb_reads_t *h_reads,
+// One group of regions [g0, g1) staged into buffer set `b` on the copy stream.  Read / reference arrays keep their
+// ABSOLUTE offsets: the device base pointers are shifted back by the slice start ("virtual base"), so seq_off /
+// cigar_off / ref_off need no rebasing; only the per-read arrays are re-indexed from the group's first read.
+struct GroupView { pb_reads_t d; const pb_region_t *d_regions; const char *d_ref; std::vector<pb_region_t> h_regions; };
+
+static int stage_group(pb_variant_encoder_t *e, int b, const pb_reads_t *h, const pb_region_t *h_regions, int64_t g0, int64_t g1,
+                       const char *h_ref, GroupView &V) {
+    cudaStream_t cs = e->copy_stream;
+    DevBuf *B = e->g_buf[b];
+    const int64_t r0 = h_regions[g0].read_begin, r1 = h_regions[g1 - 1].read_end;
+    const int64_t n = r1 - r0;
+    const int64_t nb0 = h->seq_off[r0], nb1 = h->seq_off[r1], c0 = h->cigar_off[r0], c1 = h->cigar_off[r1];
+    const int64_t sb0 = nb0 >> 1, sb1 = (nb1 + 1) >> 1;
+    PB_TRY(upload(B[0], h->pos + r0, sizeof(int64_t) * n, cs));
+    PB_TRY(upload(B[1], h->seq_off + r0, sizeof(int64_t) * (n + 1), cs));
+    PB_TRY(upload(B[2], h->cigar_off + r0, sizeof(int64_t) * (n + 1), cs));
+    PB_TRY(upload(B[3], h->flags + r0, n, cs));
+    PB_TRY(upload(B[4], h->mapq + r0, n, cs));
+    PB_TRY(upload(B[5], h->seq + sb0, (size_t) (sb1 - sb0), cs));
+    PB_TRY(upload(B[6], h->qual + nb0, (size_t) (nb1 - nb0), cs));
+    PB_TRY(upload(B[7], h->cigar + c0, sizeof(uint32_t) * (c1 - c0), cs));
+    V.h_regions.assign(h_regions + g0, h_regions + g1);
+    int64_t ref0 = INT64_MAX, ref1 = 0;
+    for (auto &rg : V.h_regions) {
+        rg.read_begin -= r0; rg.read_end -= r0;
+        ref0 = std::min(ref0, rg.ref_off); ref1 = std::max(ref1, rg.ref_off + rg.ref_len);
+    }
+    if (ref1 < ref0) { ref0 = 0; ref1 = 0; }
+    PB_TRY(upload(B[8], V.h_regions.data(), sizeof(pb_region_t) * V.h_regions.size(), cs));
+    PB_TRY(upload(B[9], h_ref + ref0, (size_t) (ref1 - ref0), cs));
+    PB_CUDA(cudaEventRecord(e->copied[b], cs));
+    V.d.n_reads = n;
+    V.d.pos = B[0].as<int64_t>(); V.d.seq_off = B[1].as<int64_t>(); V.d.cigar_off = B[2].as<int64_t>();
+    V.d.flags = B[3].as<uint8_t>(); V.d.mapq = B[4].as<uint8_t>();
+    V.d.seq = B[5].as<uint8_t>() - sb0; V.d.qual = B[6].as<uint8_t>() - nb0; V.d.cigar = B[7].as<uint32_t>() - c0;
+    V.d_regions = B[8].as<pb_region_t>();
+    V.d_ref = B[9].as<char>() - ref0;
+    return PB_OK;
+}
+
+__global__ void k_add_offset_i32(int32_t *p, int64_t n, int32_t off) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += off;
+}
+
+// single-shot host entry: everything copied up front (small batches, or regions whose read ranges are not ascending)
+static int variant_call_host_single(pb_variant_encoder_t *e, pb_variant_net_t *net, const pb_reads_t *h_reads,
                                     const pb_region_t *h_regions, int64_t n_regions, const char *h_ref, int64_t ref_bytes,
                                     const pb_variant_params_t *params, int64_t capacity, int8_t *h_images,
                                     int64_t *h_positions, uint8_t *h_depths, uint8_t *h_freqs, char *h_keys,
                                     int32_t *h_region_of, float *h_probs, int64_t *n_out, void *stream_) {
-    if (!e || !net || !h_reads || !h_regions || !params || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
     cudaStream_t st = (cudaStream_t) stream_;
-    PB_CUDA(cudaSetDevice(e->device));
     DevBuf *rb[8] = {&e->h_pos, &e->h_seq_off, &e->h_cigar_off, &e->h_flags, &e->h_mapq, &e->h_seq, &e->h_qual, &e->h_cigar};
     pb_reads_t d;
     PB_TRY(upload_reads(h_reads, rb, &d, st));
@@ -82,6 +128,95 @@ extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *n
                                   e->p_freqs.as<uint8_t>(), e->p_keys.as<char>(), e->p_region_of.as<int32_t>(), e->p_probs.as<float>(),
                                   n_out, stream_));
     const int64_t n = *n_out;
+    if (n > 0) {
+        if (h_images) PB_CUDA(cudaMemcpyAsync(h_images, e->p_images.p, (size_t) n * 33 * 26, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_positions, e->p_positions.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_depths, e->p_depths.p, n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_freqs, e->p_freqs.p, n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_keys, e->p_keys.p, (size_t) n * PB_ALLELE_STRIDE, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_region_of, e->p_region_of.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(h_probs, e->p_probs.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+    }
+    PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+// Host entry: regions are processed in groups; the H2D copy of group g+1 (copy stream, pinned source) overlaps the
+// encoder + network kernels of group g, so PCIe time hides behind compute for all but the first group.
+constexpr int64_t CALL_GROUP = 96;
+
+extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *net, const pb_reads_t *h_reads,
+                                    const pb_region_t *h_regions, int64_t n_regions, const char *h_ref, int64_t ref_bytes,
+                                    const pb_variant_params_t *params, int64_t capacity, int8_t *h_images,
+                                    int64_t *h_positions, uint8_t *h_depths, uint8_t *h_freqs, char *h_keys,
+                                    int32_t *h_region_of, float *h_probs, int64_t *n_out, void *stream_) {
+    if (!e || !net || !h_reads || !h_regions || !params || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
+    (void) ref_bytes;
+    cudaStream_t st = (cudaStream_t) stream_;
+    PB_CUDA(cudaSetDevice(e->device));
+    *n_out = 0;
+    if (n_regions <= 0) return PB_OK;
+    bool ascending = true;
+    for (int64_t r = 0; r < n_regions; r++) {
+        if (h_regions[r].read_begin < 0 || h_regions[r].read_end > h_reads->n_reads || h_regions[r].read_begin > h_regions[r].read_end) {
+            set_error("region %lld: read range out of bounds", (long long) r);
+            return PB_ERR_ARG;
+        }
+        if (r > 0 && h_regions[r].read_begin < h_regions[r - 1].read_end) ascending = false;
+    }
+    if (n_regions <= CALL_GROUP || !ascending)
+        return variant_call_host_single(e, net, h_reads, h_regions, n_regions, h_ref, ref_bytes, params, capacity, h_images, h_positions,
+                                        h_depths, h_freqs, h_keys, h_region_of, h_probs, n_out, stream_);
+    if (!e->copy_stream) {
+        PB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) PB_CUDA(cudaEventCreateWithFlags(&e->copied[b], cudaEventDisableTiming));
+    }
+    PB_TRY(ensure_events(e->pevt, 3));
+    const int64_t cap = std::max<int64_t>(capacity, 1);
+    PB_TRY(e->p_images.reserve((size_t) cap * 33 * 26));
+    PB_TRY(e->p_positions.reserve(sizeof(int64_t) * cap));
+    PB_TRY(e->p_depths.reserve(cap));
+    PB_TRY(e->p_freqs.reserve(cap));
+    PB_TRY(e->p_keys.reserve((size_t) cap * PB_ALLELE_STRIDE));
+    PB_TRY(e->p_region_of.reserve(sizeof(int32_t) * cap));
+    PB_TRY(e->p_probs.reserve(sizeof(float) * 3 * cap));
+
+    const int64_t n_groups = ceil_div(n_regions, CALL_GROUP);
+    GroupView V[2];
+    PB_TRY(stage_group(e, 0, h_reads, h_regions, 0, std::min(n_regions, CALL_GROUP), h_ref, V[0]));
+    int64_t done = 0;
+    float enc_ms = 0.f, net_ms = 0.f;
+    int rc = PB_OK;
+    for (int64_t g = 0; g < n_groups && rc == PB_OK; g++) {
+        const int b = (int) (g & 1);
+        if (g + 1 < n_groups)
+            PB_TRY(stage_group(e, b ^ 1, h_reads, h_regions, (g + 1) * CALL_GROUP, std::min(n_regions, (g + 2) * CALL_GROUP), h_ref, V[b ^ 1]));
+        PB_CUDA(cudaStreamWaitEvent(st, e->copied[b], 0));
+        int64_t n_g = 0;
+        const int64_t room = std::max<int64_t>(capacity - done, 0);
+        rc = pb_variant_call_device(e, net, &V[b].d, V[b].d_regions, (int64_t) V[b].h_regions.size(), V[b].h_regions.data(), V[b].d_ref, 0,
+                                    params, room, e->p_images.as<int8_t>() + done * 33 * 26, e->p_positions.as<int64_t>() + done,
+                                    e->p_depths.as<uint8_t>() + done, e->p_freqs.as<uint8_t>() + done,
+                                    e->p_keys.as<char>() + done * PB_ALLELE_STRIDE, e->p_region_of.as<int32_t>() + done,
+                                    e->p_probs.as<float>() + done * 3, &n_g, stream_);
+        if (rc == PB_ERR_CAPACITY) {
+            // the caller retries with the returned size: extrapolate from the regions seen so far (retried again if short)
+            const int64_t seen = std::min(n_regions, (g + 1) * CALL_GROUP);
+            const int64_t need = (int64_t) ((double) (done + n_g) * (double) n_regions / (double) seen * 1.25) + 4096;
+            cudaStreamSynchronize(e->copy_stream);
+            *n_out = need;
+            set_error("candidate capacity %lld too small (estimated need %lld)", (long long) capacity, (long long) need);
+            return PB_ERR_CAPACITY;
+        }
+        if (rc != PB_OK) return rc;
+        if (n_g > 0 && g > 0)
+            k_add_offset_i32<<<(unsigned) ceil_div(n_g, 256), 256, 0, st>>>(e->p_region_of.as<int32_t>() + done, n_g, (int32_t) (g * CALL_GROUP));
+        enc_ms += e->pms[0]; net_ms += e->pms[1];
+        done += n_g;
+    }
+    e->pms[0] = enc_ms; e->pms[1] = net_ms;
+    *n_out = done;
+    const int64_t n = done;
     if (n > 0) {
         if (h_images) PB_CUDA(cudaMemcpyAsync(h_images, e->p_images.p, (size_t) n * 33 * 26, cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaMemcpyAsync(h_positions, e->p_positions.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));

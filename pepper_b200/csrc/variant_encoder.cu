@@ -871,6 +871,8 @@ extern "C" int pb_variant_encoder_destroy(pb_variant_encoder_t *e) {
     for (auto *b : bufs) b->release();
     for (auto &ev : e->evt) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->pevt) if (ev) cudaEventDestroy(ev);
+    for (int b = 0; b < 2; b++) { for (auto &gb : e->g_buf[b]) gb.release(); if (e->copied[b]) cudaEventDestroy(e->copied[b]); }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
     return PB_OK;
 }

@@ -53,3 +53,25 @@ def test_polish_call_matches_separate_stages(oracle_built):
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_variant_call_pipelined_groups_match_single_shot(oracle_built):
+    """> 96 regions: the host entry stages region groups on a copy stream while the previous group computes; the result
+    must equal the encoder + network run in one shot (and the oracle's candidate list)."""
+    from oracle import nets
+    from pepper_b200.pipeline import VariantCaller
+    state = nets.make_variant_weights(1)
+    reads, regions = synth.make_variant_workload(6, 1500, 25, synth.ONT, seed=33)
+    reads, regions = synth.tile_workload(reads, regions, 40)             # 240 regions -> 3 groups
+    caller = VariantCaller(state)
+    calls = caller.call(reads, regions, synth.ont_params(), want_images=True)
+    enc = caller.enc.encode(reads, regions, synth.ont_params())
+    assert calls.keys == enc.keys and np.array_equal(calls.positions, enc.positions)
+    assert np.array_equal(calls.region_of, enc.region_of) and np.array_equal(calls.images, enc.images)
+    assert np.array_equal(calls.probs, caller.net.predict(enc.images))
+    small = caller.call(reads, regions, synth.ont_params(), capacity=7)   # capacity retry across groups
+    assert np.array_equal(small.probs, calls.probs)
+    one = synth.RegionTable(regions.table[:6].copy(), regions.ref)
+    want = oracle_built.variant_encode(reads, one, synth.ont_params(), "port")
+    assert calls.keys[:len(want["keys"])] == want["keys"]
+    caller.close()

@@ -134,20 +134,24 @@ def test_more_reads_than_one_list_round(oracle_built, enc):
     for k in range(2600):
         a = int(rng.integers(0, 1500))
         n = int(rng.integers(120, 300))
-        seg = list(ref[a:a + n])
-        cig = []
-        if rng.random() < 0.3 and n > 60:                    # one SNP
-            p = int(rng.integers(5, n - 5)); seg[p] = "ACGT"[(("ACGT".index(seg[p])) + 1) % 4]
-        if rng.random() < 0.25 and n > 80:                   # one deletion of 1-3
-            p = int(rng.integers(20, n - 30)); d = int(rng.integers(1, 4))
-            seq = "".join(seg[:p] + seg[p + d:])
-            cig = [(0, p), (2, d), (0, n - p - d)]
-        elif rng.random() < 0.25 and n > 80:                 # one insertion of 1-2
-            p = int(rng.integers(20, n - 30)); ins = "".join("ACGT"[i] for i in rng.integers(0, 4, int(rng.integers(1, 3))))
-            seq = "".join(seg[:p]) + ins + "".join(seg[p:])
-            cig = [(0, p), (1, len(ins)), (0, n - p)]
-        else:
-            seq = "".join(seg); cig = [(0, n)]
+        # recurrent variant sites so that the site thresholds are reached: SNPs at x % 50 == 7 (40 % of the reads),
+        # a 2-base deletion after x % 120 == 60 (35 %), an insertion after x % 170 == 85 (35 %)
+        seq, cig, run = [], [], 0
+        x = a
+        while x < a + n:
+            base = ref[x]
+            if x % 50 == 7 and rng.random() < 0.4:
+                base = "ACGT"[("ACGT".index(base) + 1 + int(rng.integers(0, 2))) % 4]
+            seq.append(base); run += 1
+            if x % 120 == 60 and x + 3 < a + n and rng.random() < 0.35:
+                cig += [(0, run), (2, 2)]; run = 0; x += 2
+            elif x % 170 == 85 and x + 1 < a + n and rng.random() < 0.35:
+                ins = ["AC", "A", "ACG"][int(rng.integers(0, 3))]
+                cig += [(0, run), (1, len(ins))]; run = 0; seq.extend(ins)
+            x += 1
+        if run:
+            cig.append((0, run))
+        seq = "".join(seq)
         reads.append(dict(pos=S + a, seq=seq, qual=[int(q) for q in rng.integers(1, 40, len(seq))], cigar=cig,
                           reverse=bool(rng.random() < 0.5), mapq=int(60 if rng.random() > 0.02 else 0)))
     reads.sort(key=lambda r: r["pos"])
@@ -155,5 +159,5 @@ def test_more_reads_than_one_list_round(oracle_built, enc):
     tab = np.array([[S, S + 1799, S + 100, S + 1700, 0, 1800, 0, len(reads)]], dtype=np.int64)
     regions = synth.RegionTable(tab, np.frombuffer(ref.encode(), dtype=np.uint8).copy())
     got = _compare(oracle_built, enc, batch, regions, synth.ont_params(), "deep")
-    assert len(got) > 50
+    assert len(got) > 40 and {k[0] for k in got.keys} == {"1", "2", "3"}
     assert got.depths.max() == 125            # clamped depth
