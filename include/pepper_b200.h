@@ -302,6 +302,28 @@ int pb_polish_call_device(pb_polish_encoder_t *enc, pb_polish_net_t *net,
 int pb_variant_call_timings(pb_variant_encoder_t *enc, float *ms2);
 int pb_polish_call_timings(pb_polish_encoder_t *enc, float *ms2);
 
+/* ------------------------------------------------------------------------
+ * Polish stitch.  Replaces small_chunk_stitch +
+ * create_consensus_sequence (pepper/modules/python/Stitch.py:36-128) for one
+ * contig: drops the padding columns (-1,-1), the first 200 positions of every
+ * region that does not start at 0, the 50-column chunk overlap (the chunk whose
+ * id sorts later AS A STRING wins, Stitch.py:50), label 0, and concatenates
+ * A/C/G/T in (position, index) order.  Images must be ordered by region (regions
+ * sorted by start, tiled with the reference's 2 x 100 overlap) then chunk id —
+ * the order pb_polish_call_* produces.
+ *   out  char [capacity] (not NUL terminated); n_out = consensus length
+ * ---------------------------------------------------------------------- */
+int pb_polish_stitch_device(const uint8_t *d_bases, const int64_t *d_position,
+                            const int32_t *d_index, const int32_t *d_image_region,
+                            const int32_t *d_chunk_id, const int64_t *d_region_starts,
+                            int64_t n_images, char *d_out, int64_t capacity,
+                            int64_t *n_out, void *stream);
+int pb_polish_stitch_host(const uint8_t *h_bases, const int64_t *h_position,
+                          const int32_t *h_index, const int32_t *h_image_region,
+                          const int32_t *h_chunk_id, const int64_t *h_region_starts,
+                          int64_t n_regions, int64_t n_images, char *h_out,
+                          int64_t capacity, int64_t *n_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

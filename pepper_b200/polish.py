@@ -174,3 +174,25 @@ class PolishNet:
         n = C.c_int64(0)
         _lib.check(self.L.pb_polish_net_launches(self.h, C.byref(n)), "launches")
         return int(n.value)
+
+
+def stitch(bases, position, index, image_region, chunk_id, region_starts, stream: int = 0) -> str:
+    """Consensus sequence of one contig from the per-image predictions (== pepper Stitch.py:36-128), on the GPU.
+    Images ordered by region then chunk id; regions sorted by start (the order PolishCaller.call returns)."""
+    _lib.require_gpu()
+    L = _lib.lib()
+    vp = C.c_void_p
+    L.pb_polish_stitch_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int64), vp]
+    b = np.ascontiguousarray(bases, dtype=np.uint8)
+    p = np.ascontiguousarray(position, dtype=np.int64)
+    i = np.ascontiguousarray(index, dtype=np.int32)
+    r = np.ascontiguousarray(image_region, dtype=np.int32)
+    c = np.ascontiguousarray(chunk_id, dtype=np.int32)
+    s = np.ascontiguousarray(region_starts, dtype=np.int64)
+    n_img = b.shape[0]
+    cap = max(1, n_img * POLISH_SEQ_LEN)
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_int64(0)
+    _lib.check(L.pb_polish_stitch_host(b.ctypes.data, p.ctypes.data, i.ctypes.data, r.ctypes.data, c.ctypes.data, s.ctypes.data,
+                                       s.shape[0], n_img, out.ctypes.data, cap, C.byref(n), C.c_void_p(stream)), "pb_polish_stitch_host")
+    return bytes(out[:int(n.value)]).decode()
