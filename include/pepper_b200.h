@@ -324,6 +324,37 @@ int pb_polish_stitch_host(const uint8_t *h_bases, const int64_t *h_position,
                           int64_t n_regions, int64_t n_images, char *h_out,
                           int64_t capacity, int64_t *n_out, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Candidate selection.  Replaces the per-candidate logic of
+ * small_chunk_stitch, pepper_variant/modules/python/CandidateFinder.py:356-530:
+ * homopolymer context of the +-10 bp reference window (:393-406), genotype =
+ * argmax of the prediction (:411), Margin list = SNP alleles with a non-ref
+ * genotype (:427-449), DeepVariant list by the p-value / frequency thresholds
+ * per allele type in and outside repeats (:460-519).  One allele per record
+ * (what the encoder emits).
+ *   flags  uint8 [n]: bit0 Margin record, bit1 DeepVariant record, bit2 in repeat,
+ *                     bit3 delete ref/alt swap (:497-505), bit4 reference base valid
+ *   genotype uint8 [n]: 0 hom-ref, 1 het, 2 hom-alt
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    double snp_p_value, insert_p_value, delete_p_value;
+    double snp_p_value_in_lc, insert_p_value_in_lc, delete_p_value_in_lc;
+    double report_snp_above_freq, report_indel_above_freq;
+} pb_candidate_options_t;
+int pb_variant_find_candidates_device(const int64_t *d_positions, const int32_t *d_region_of,
+                                      const uint8_t *d_depths, const uint8_t *d_freqs,
+                                      const char *d_keys, const float *d_probs, int64_t n,
+                                      const pb_region_t *d_regions, const char *d_ref,
+                                      const pb_candidate_options_t *opt,
+                                      uint8_t *d_flags, uint8_t *d_genotype, void *stream);
+int pb_variant_find_candidates_host(const int64_t *h_positions, const int32_t *h_region_of,
+                                    const uint8_t *h_depths, const uint8_t *h_freqs,
+                                    const char *h_keys, const float *h_probs, int64_t n,
+                                    const pb_region_t *h_regions, int64_t n_regions,
+                                    const char *h_ref, int64_t ref_bytes,
+                                    const pb_candidate_options_t *opt,
+                                    uint8_t *h_flags, uint8_t *h_genotype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
