@@ -16,7 +16,7 @@ struct TcVariant {
 };
 struct TcPolish {
     TcRnn enc[2], dec[2];
-    DevBuf img_op, yenc_hi, yenc_lo, ydec_hi, ydec_lo, zero;
+    DevBuf img_op, yenc_hi, yenc_lo, ydec_hi, ydec_lo, zero, flags;
 };
 int tc_upload_rnn(TcRnn &T, const float *Wp, int K0, int K0p_src, int H, int Kp_src);
 int tc_upload_lin(TcLin &T, const float *w, int N, int K);

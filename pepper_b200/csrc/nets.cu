@@ -582,7 +582,7 @@ extern "C" int pb_polish_net_destroy(pb_polish_net_t *N) {
     if (N->tc) {
         TcPolish &T = *N->tc;
         for (int d = 0; d < 2; d++) { T.enc[d].w_hi.release(); T.enc[d].w_lo.release(); T.dec[d].w_hi.release(); T.dec[d].w_lo.release(); }
-        DevBuf *tb[] = {&T.img_op, &T.yenc_hi, &T.yenc_lo, &T.ydec_hi, &T.ydec_lo, &T.zero};
+        DevBuf *tb[] = {&T.img_op, &T.yenc_hi, &T.yenc_lo, &T.ydec_hi, &T.ydec_lo, &T.zero, &T.flags};
         for (auto *b : tb) b->release();
         delete N->tc;
     }
@@ -635,8 +635,15 @@ extern "C" int pb_polish_net_forward_device(pb_polish_net_t *N, const uint8_t *d
     cudaStream_t st = (cudaStream_t) stream_;
     PB_CUDA(cudaSetDevice(N->device));
     N->launches = 0;
-    for (int64_t b0 = 0; b0 < n; b0 += POLISH_CHUNK) {
-        const int64_t B = std::min(POLISH_CHUNK, n - b0);
+    // tcgen05 mode: a window layer is one cooperative launch of 4 CTAs per 128-image row tile, all resident
+    int64_t chunk = POLISH_CHUNK;
+    if (N->mode == 1) {
+        int sms = 0;
+        PB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, N->device));
+        chunk = std::max<int64_t>(1, sms / 4) * 128;
+    }
+    for (int64_t b0 = 0; b0 < n; b0 += chunk) {
+        const int64_t B = std::min(chunk, n - b0);
         if (B > N->chunk) {
             for (int i = 0; i < 2; i++) PB_TRY(N->h[i].reserve(sizeof(float) * 2 * B * PH));
             PB_TRY(N->yenc.reserve(sizeof(float) * B * PWIN * 256));

@@ -255,41 +255,37 @@ __global__ void k_tc_unpack_seq(const bf16 *__restrict__ y_hi, const bf16 *__res
     dst[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-// one bidirectional GRU layer over the 100 steps of a window.
-//   x operand: [mt][100][xkt] tiles (hi, lo or hi only); h0 operand: tiles (mt, 100 steps, 8) of another sequence operand
-//   (its fwd state at time 99 / bwd state at time 0) or the zero operand.
+// one bidirectional GRU layer over the 100 steps of a window: ONE cooperative launch of k_gru_window.
+//   x operand: [mt][100][xkt] tiles (hi, lo or hi only); h0: the fwd state at time 99 / bwd state at time 0 of another
+//   sequence operand (h0_is_seq) or the zero operand.
 static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi, const bf16 *x_lo, int xkt, const bf16 *h0_hi,
                         const bf16 *h0_lo, bool h0_is_seq, bf16 *y_hi, bf16 *y_lo, int64_t B, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(tc::k_gru_window, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSMEM_BYTES));
+        attr_set = true;
+    }
+    TcPolish &T = *N->tc;
     const int64_t Mt = ceil_div(B, 128);
     const int64_t ystride = (int64_t) PWIN * 8 * TILE_ELEMS;
-    for (int t = 0; t < PWIN; t++) {
-        Args A;
-        A.M = (int) B; A.N = 4 * PH; A.c_ld = 0;
-        for (int d = 0; d < 2; d++) {
-            const int tt = d == 0 ? t : PWIN - 1 - t;
-            const int tp = d == 0 ? tt - 1 : tt + 1;
-            Dir D = empty_dir();
-            D.seg[0].hi = x_hi + (int64_t) tt * xkt * TILE_ELEMS; D.seg[0].lo = x_lo ? x_lo + (int64_t) tt * xkt * TILE_ELEMS : nullptr;
-            D.seg[0].mt_stride = (int64_t) PWIN * xkt * TILE_ELEMS; D.seg[0].nkt = xkt;
-            const bf16 *hh, *hl; int64_t hs;
-            if (t > 0) {
-                hh = y_hi + ((int64_t) tp * 8 + d * 4) * TILE_ELEMS; hl = y_lo + ((int64_t) tp * 8 + d * 4) * TILE_ELEMS; hs = ystride;
-            } else if (h0_is_seq) {
-                const int t0 = d == 0 ? PWIN - 1 : 0;
-                hh = h0_hi + ((int64_t) t0 * 8 + d * 4) * TILE_ELEMS; hl = h0_lo + ((int64_t) t0 * 8 + d * 4) * TILE_ELEMS; hs = ystride;
-            } else {
-                hh = h0_hi; hl = h0_lo; hs = 0;          // zero operand (4 tiles, shared by every row tile)
-            }
-            D.seg[1].hi = hh; D.seg[1].lo = hl; D.seg[1].mt_stride = hs; D.seg[1].nkt = 4;
-            D.hp_hi = hh; D.hp_lo = hl; D.hp_mt_stride = hs;
-            D.w_hi = W[d].w_hi.as<bf16>(); D.w_lo = W[d].w_lo.as<bf16>(); D.w_nkt = W[d].nkt_x + W[d].nkt_h;
-            D.bias = Wb[d].bias.as<float>();
-            D.y_hi = y_hi; D.y_lo = y_lo; D.y_mt_stride = ystride; D.y_kt0 = tt * 8 + d * 4;
-            A.d[d] = D;
-        }
-        PB_TRY(launch_tc<tc::EPI_GRU>(A, (int) Mt, 4 * PH / 128, 2, st));
-        N->launches++;
+    PB_TRY(T.flags.reserve(sizeof(int) * 2 * Mt));
+    PB_CUDA(cudaMemsetAsync(T.flags.p, 0, sizeof(int) * 2 * Mt, st));
+    tc::GruWin G;
+    G.x_hi = x_hi; G.x_lo = x_lo; G.x_kt = xkt;
+    for (int d = 0; d < 2; d++) {
+        const int t0 = d == 0 ? PWIN - 1 : 0;
+        G.h0_hi[d] = h0_is_seq ? h0_hi + ((int64_t) t0 * 8 + d * 4) * TILE_ELEMS : h0_hi;
+        G.h0_lo[d] = h0_is_seq ? h0_lo + ((int64_t) t0 * 8 + d * 4) * TILE_ELEMS : h0_lo;
+        G.w_hi[d] = W[d].w_hi.as<bf16>(); G.w_lo[d] = W[d].w_lo.as<bf16>();
+        G.bias[d] = Wb[d].bias.as<float>();
     }
+    G.h0_mt_stride = h0_is_seq ? ystride : 0;
+    G.y_hi = y_hi; G.y_lo = y_lo; G.flags = T.flags.as<int>();
+    G.M = (int) B; G.n_mt = (int) Mt; G.T = PWIN;
+    if (W[0].nkt_x != xkt || W[0].nkt_h != 4) { set_error("gru_layer_tc: weight / operand k-tile mismatch"); return PB_ERR_STATE; }
+    void *args[] = {&G};
+    PB_CUDA(cudaLaunchCooperativeKernel((void *) tc::k_gru_window, dim3((unsigned) (4 * Mt)), dim3(tc::THREADS), args, tc::PSMEM_BYTES, st));
+    N->launches++;
     return PB_OK;
 }
 
