@@ -261,8 +261,12 @@ __global__ void k_tc_unpack_seq(const bf16 *__restrict__ y_hi, const bf16 *__res
 static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi, const bf16 *x_lo, int xkt, const bf16 *h0_hi,
                         const bf16 *h0_lo, bool h0_is_seq, bf16 *y_hi, bf16 *y_lo, int64_t B, cudaStream_t st) {
     static bool attr_set = false;
+    static int use_cluster = 1;       // PB_GRU_CLUSTER=0 selects the HBM-flag kernel (cooperative launch, <= 37 row tiles)
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(tc::k_gru_window, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(tc::k_gru_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CSMEM_BYTES));
+        const char *e = getenv("PB_GRU_CLUSTER");
+        use_cluster = (e && e[0] == '0') ? 0 : 1;
         attr_set = true;
     }
     TcPolish &T = *N->tc;
@@ -283,8 +287,13 @@ static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi
     G.y_hi = y_hi; G.y_lo = y_lo; G.flags = T.flags.as<int>();
     G.M = (int) B; G.n_mt = (int) Mt; G.T = PWIN;
     if (W[0].nkt_x != xkt || W[0].nkt_h != 4) { set_error("gru_layer_tc: weight / operand k-tile mismatch"); return PB_ERR_STATE; }
-    void *args[] = {&G};
-    PB_CUDA(cudaLaunchCooperativeKernel((void *) tc::k_gru_window, dim3((unsigned) (4 * Mt)), dim3(tc::THREADS), args, tc::PSMEM_BYTES, st));
+    if (use_cluster) {
+        tc::k_gru_cluster<<<(unsigned) (4 * Mt), tc::THREADS, tc::CSMEM_BYTES, st>>>(G);      // clusters of 2 CTAs (__cluster_dims__)
+        PB_CUDA(cudaGetLastError());
+    } else {
+        void *args[] = {&G};
+        PB_CUDA(cudaLaunchCooperativeKernel((void *) tc::k_gru_window, dim3((unsigned) (4 * Mt)), dim3(tc::THREADS), args, tc::PSMEM_BYTES, st));
+    }
     N->launches++;
     return PB_OK;
 }

@@ -732,6 +732,211 @@ __global__ void __launch_bounds__(THREADS, 1) k_gru_window(GruWin G) {
     }
 }
 
+// ---------------------------------------------------------------- cluster-resident GRU window kernel (polish)
+// Same work split as k_gru_window, but the two CTAs that own the two halves of a (direction, row tile) form a thread-block
+// CLUSTER and exchange h_t through distributed shared memory instead of HBM: the epilogue writes its 64 units of h_t (bf16
+// hi/lo operand tiles) into the local H buffer, one thread pushes them to the sibling's H buffer with
+// cp.async.bulk.shared::cluster (completing on the sibling's mbarrier), and the MMA warp of each CTA feeds the h part of
+// the next step straight from its H buffer.  The per-step critical path loses the store -> fence -> flag -> poll -> L2
+// round trip; there is no cross-cluster dependency, so any batch size runs (no cooperative launch).
+constexpr int CSTAGES = 2;
+constexpr int HBUF_BYTES = 4 * 2 * TILE_BYTES;                  // 4 k-tiles x (hi, lo) = 64 KB
+constexpr int CSMEM_BYTES = 2 * HBUF_BYTES + CSTAGES * PSTAGE_BYTES + 256;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gru_cluster(GruWin G) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *ring = smem + 2 * HBUF_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + CSTAGES * PSTAGE_BYTES);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + CSTAGES);
+    const uint32_t bar_accf = smem_u32(bars + 2 * CSTAGES), bar_acce = smem_u32(bars + 2 * CSTAGES + 2);
+    const uint32_t bar_h = smem_u32(bars + 2 * CSTAGES + 4);               // h_ready[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * CSTAGES + 6);
+    const uint32_t hbuf = smem_u32(smem), ring_base = smem_u32(ring);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x & 1, pair = blockIdx.x >> 1;                // nt == rank in the cluster
+    const int mt = pair % G.n_mt, dir = pair / G.n_mt;
+    const int nkt = G.x_kt + 4;
+    const int64_t seq_stride = (int64_t) G.T * 8 * TILE_ELEMS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CSTAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 8); mbar_init(bar_h + 8 * b, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) PTMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // the sibling's barriers exist before anything is sent to them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // initial state -> H[1] (the "t-1" buffer of step 0)
+            mbar_expect_tx(bar_h + 8, 8u * TILE_BYTES);
+            for (int kk = 0; kk < 4; kk++) {
+                const int64_t off = (int64_t) mt * G.h0_mt_stride + (int64_t) kk * TILE_ELEMS;
+                bulk_g2s(hbuf + HBUF_BYTES + kk * 2 * TILE_BYTES, G.h0_hi[dir] + off, TILE_BYTES, bar_h + 8);
+                bulk_g2s(hbuf + HBUF_BYTES + kk * 2 * TILE_BYTES + TILE_BYTES, G.h0_lo[dir] + off, TILE_BYTES, bar_h + 8);
+            }
+            uint32_t g = 0;
+            for (int t = 0; t < G.T; t++) {
+                const int tt = dir == 0 ? t : G.T - 1 - t;
+                for (int kt = 0; kt < nkt; kt++, g++) {
+                    const uint32_t s = g % CSTAGES, ph = (g / CSTAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    const uint32_t st = ring_base + s * PSTAGE_BYTES;
+                    const int64_t woff = ((int64_t) nt * nkt + kt) * WTILE_ELEMS;
+                    if (kt < G.x_kt) {
+                        const int64_t off = ((int64_t) (mt * G.T + tt) * G.x_kt + kt) * TILE_ELEMS;
+                        mbar_expect_tx(bar_full + 8 * s, (G.x_lo ? 2u : 1u) * TILE_BYTES + 2u * WTILE_BYTES);
+                        bulk_g2s(st, G.x_hi + off, TILE_BYTES, bar_full + 8 * s);
+                        if (G.x_lo) bulk_g2s(st + TILE_BYTES, G.x_lo + off, TILE_BYTES, bar_full + 8 * s);
+                    } else {
+                        mbar_expect_tx(bar_full + 8 * s, 2u * WTILE_BYTES);      // A comes from the resident H buffer
+                    }
+                    bulk_g2s(st + 2 * TILE_BYTES, G.w_hi[dir] + woff, WTILE_BYTES, bar_full + 8 * s);
+                    bulk_g2s(st + 2 * TILE_BYTES + WTILE_BYTES, G.w_lo[dir] + woff, WTILE_BYTES, bar_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = 0; t < G.T; t++) {
+                const uint32_t buf = (uint32_t) t & 1u, use = (uint32_t) t >> 1;
+                mbar_wait(bar_acce + 8 * buf, (use & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * PBN;
+                const uint32_t hsrc = hbuf + (((uint32_t) (t + 1)) & 1u) * HBUF_BYTES;     // H[(t-1)&1]
+                for (int kt = 0; kt < nkt; kt++, g++) {
+                    const uint32_t s = g % CSTAGES, ph = (g / CSTAGES) & 1u;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    const bool xpart = kt < G.x_kt;
+                    if (kt == G.x_kt) mbar_wait(bar_h + 8 * (((uint32_t) (t + 1)) & 1u), ((uint32_t) t >> 1) & 1u);   // h_{t-1} complete
+                    tc_fence_after();
+                    const bool has_lo = !xpart || (G.x_lo != nullptr);
+                    const uint32_t st = ring_base + s * PSTAGE_BYTES;
+                    const uint32_t a_base = xpart ? st : hsrc + (uint32_t) (kt - G.x_kt) * 2 * TILE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ks++) {
+                        const uint64_t a_hi = smem_desc_lbo(a_base + ks * 4096, 2048), a_lo = smem_desc_lbo(a_base + TILE_BYTES + ks * 4096, 2048);
+                        const uint64_t b_hi = smem_desc_lbo(st + 2 * TILE_BYTES + ks * 8192, 4096);
+                        const uint64_t b_lo = smem_desc_lbo(st + 2 * TILE_BYTES + WTILE_BYTES + ks * 8192, 4096);
+                        tc_mma(tacc, a_hi, b_hi, IDESC256, (kt > 0 || ks > 0) ? 1u : 0u);
+                        tc_mma(tacc, a_hi, b_lo, IDESC256, 1u);
+                        if (has_lo) tc_mma(tacc, a_lo, b_hi, IDESC256, 1u);
+                    }
+                    tc_commit(bar_empty + 8 * s);
+                }
+                tc_commit(bar_accf + 8 * buf);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int r128 = q * 32 + lane;
+        const int row = mt * BM + r128;
+        const bool valid = row < G.M;
+        const int ubase = nt * (PBN / 4) + half * (PEPI_COLS / 4);
+        const float *bias = G.bias[dir];
+        float hp[PEPI_COLS / 4];
+#pragma unroll
+        for (int u8 = 0; u8 < PEPI_COLS / 32; u8++) {
+            uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+            if (valid) {
+                const int j0 = ubase + u8 * 8;
+                const int64_t o = (int64_t) mt * G.h0_mt_stride + (int64_t) (j0 >> 5) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                h = *reinterpret_cast<const uint4 *>(G.h0_hi[dir] + o);
+                l = *reinterpret_cast<const uint4 *>(G.h0_lo[dir] + o);
+            }
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                hp[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+        }
+        const uint32_t peer = (uint32_t) (nt ^ 1);
+        for (int t = 0; t < G.T; t++) {
+            const int tt = dir == 0 ? t : G.T - 1 - t;
+            const uint32_t buf = (uint32_t) t & 1u, use = (uint32_t) t >> 1;
+            uint8_t *hdst = smem + buf * HBUF_BYTES;                                   // H[t&1]
+            mbar_wait(bar_accf + 8 * buf, use & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int cl = 0; cl < PEPI_COLS / 32; cl++) {
+                const int cc = half * (PEPI_COLS / 32) + cl;
+                const int col0 = nt * PBN + cc * 32;
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + buf * PBN + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
+                if (cl == PEPI_COLS / 32 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+                }
+                const int j0 = col0 >> 2;
+                float hn[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias + col0 + 4 * u));
+                    const float v0 = __uint_as_float(acc[4 * u + 0]) + bz.x, v1 = __uint_as_float(acc[4 * u + 1]) + bz.y;
+                    const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
+                    const float r = sigm(v0), z = sigm(v1);
+                    const float n = tanh_fast(v2 + r * v3);
+                    hn[u] = (1.0f - z) * n + z * hp[cl * 8 + u];
+                    hp[cl * 8 + u] = hn[u];
+                }
+                uint4 hi, lo;
+                split8(hn, hi, lo);
+                // local H buffer (rows beyond M carry zeros-derived values; harmless, never stored to HBM)
+                const uint32_t so = (uint32_t) (j0 >> 5) * 2 * TILE_BYTES + (uint32_t) (((j0 & 31) >> 3) * 1024 + r128 * 8) * 2;
+                *reinterpret_cast<uint4 *>(hdst + so) = hi;
+                *reinterpret_cast<uint4 *>(hdst + so + TILE_BYTES) = lo;
+                if (valid) {
+                    const int64_t o = (int64_t) mt * seq_stride + ((int64_t) tt * 8 + dir * 4 + (j0 >> 5)) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                    *reinterpret_cast<uint4 *>(G.y_hi + o) = hi;
+                    *reinterpret_cast<uint4 *>(G.y_lo + o) = lo;
+                }
+            }
+            if (t + 1 < G.T) {
+                // my two k-tiles of h_t are in the local H buffer: make them visible to the async proxy, then one thread
+                // announces them locally and pushes them into the sibling's H buffer (completing on ITS barrier)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (threadIdx.x == 64) {
+                    mbar_expect_tx(bar_h + 8 * buf, 4u * TILE_BYTES);                // the sibling's two k-tiles (hi, lo) will land here
+                    const uint32_t rbar = mapa_u32(bar_h + 8 * buf, peer);
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; k2++) {
+                        const uint32_t off = (uint32_t) buf * HBUF_BYTES + (uint32_t) (2 * nt + k2) * 2 * TILE_BYTES;
+                        const uint32_t rdst = mapa_u32(hbuf + off, peer);
+                        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(rdst), "r"(hbuf + off), "r"(2u * TILE_BYTES), "r"(rbar) : "memory");
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // nobody exits while the sibling may still write into its shared memory
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) PTMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- operand preparation kernels
 // int8 images [B][T][F] -> tiled operand [mt][T][1 k-tile] (hi only; |v| <= 128 is exact in bf16)
 __global__ void k_tc_pack_images(const int8_t *__restrict__ img, __nv_bfloat16 *__restrict__ op, int64_t B, int T, int F) {
