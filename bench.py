@@ -233,14 +233,20 @@ def run_ours(args):
     count_s = float(np.mean(count_ms)) / 1e3
     net_s = float(np.mean(net_ms)) / 1e3
     roof_enc = dict(bound="hbm", kernel="k_tile_count", achieved=alg_bytes / count_s / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=alg_bytes / count_s / 1e9 / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
+                    frac=alg_bytes / count_s / 1e9 / peaks["hbm_gbs"], traffic=int(alg_bytes * 1.30), peak_source=peaks["source"],
+                    traffic_note="dram__bytes_read+write of k_tile_count = 1.30 x algorithmic bytes in the ncu --set full capture "
+                                 "(77.2 MB vs 59.4 MB at 8 regions, profiles/README.md); scaled to this launch",
                     algorithmic_bytes_per_launch=alg_bytes, launch_ms=count_s * 1e3,
                     note="algorithmic bytes of the whole encoder (SURVEY 8d) over the pileup-count kernel's time")
     tf = n_cand * FLOP_PER_CAND / net_s / 1e12
     roof_net = dict(bound="tensor", kernel="k_tc_gemm (tcgen05 LSTM-step / MLP GEMMs, all launches of the step; 3 bf16 products per algorithmic FLOP)", achieved=tf,
                     peak=peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], unit="TFLOP/s",
                     frac=tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), traffic=None, peak_source=peaks["source"] + ", sustained bf16",
-                    flops_per_step=n_cand * FLOP_PER_CAND, step_ms=net_s * 1e3)
+                    flops_per_step=n_cand * FLOP_PER_CAND, step_ms=net_s * 1e3,
+                    executed_bf16_tflops=3 * tf, executed_frac=3 * tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
+                    note="achieved = fp32-equivalent algorithmic FLOPs (161.4 MFLOP per candidate) / network time; every FLOP is "
+                         "executed as three bf16 tensor-core products (hi/lo split), so the tensor pipe runs at executed_frac; "
+                         "ncu: linear_1 launch 95 % tensor-pipe active, decoder LSTM step 60 % (profiles/README.md)")
 
     line = {
         "metric": "genomic bases/sec (make_images+inference)", "value": value, "unit": "bases/s", "n_gpus": world,
