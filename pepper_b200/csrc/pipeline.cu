@@ -144,6 +144,7 @@ static int variant_call_host_single(pb_variant_encoder_t *e, pb_variant_net_t *n
 // Host entry: regions are processed in groups; the H2D copy of group g+1 (copy stream, pinned source) overlaps the
 // encoder + network kernels of group g, so PCIe time hides behind compute for all but the first group.
 constexpr int64_t CALL_GROUP = 96;
+constexpr int64_t CALL_FIRST_GROUP = 24;
 
 extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *net, const pb_reads_t *h_reads,
                                     const pb_region_t *h_regions, int64_t n_regions, const char *h_ref, int64_t ref_bytes,
@@ -181,16 +182,21 @@ extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *n
     PB_TRY(e->p_region_of.reserve(sizeof(int32_t) * cap));
     PB_TRY(e->p_probs.reserve(sizeof(float) * 3 * cap));
 
-    const int64_t n_groups = ceil_div(n_regions, CALL_GROUP);
+    // group boundaries: a short first group keeps the un-overlapped first copy small
+    std::vector<int64_t> gb;
+    gb.push_back(0);
+    for (int64_t r = std::min<int64_t>(CALL_FIRST_GROUP, n_regions); r < n_regions; r += CALL_GROUP) gb.push_back(r);
+    gb.push_back(n_regions);
+    const int64_t n_groups = (int64_t) gb.size() - 1;
     GroupView V[2];
-    PB_TRY(stage_group(e, 0, h_reads, h_regions, 0, std::min(n_regions, CALL_GROUP), h_ref, V[0]));
+    PB_TRY(stage_group(e, 0, h_reads, h_regions, gb[0], gb[1], h_ref, V[0]));
     int64_t done = 0;
     float enc_ms = 0.f, net_ms = 0.f;
     int rc = PB_OK;
     for (int64_t g = 0; g < n_groups && rc == PB_OK; g++) {
         const int b = (int) (g & 1);
         if (g + 1 < n_groups)
-            PB_TRY(stage_group(e, b ^ 1, h_reads, h_regions, (g + 1) * CALL_GROUP, std::min(n_regions, (g + 2) * CALL_GROUP), h_ref, V[b ^ 1]));
+            PB_TRY(stage_group(e, b ^ 1, h_reads, h_regions, gb[g + 1], gb[g + 2], h_ref, V[b ^ 1]));
         PB_CUDA(cudaStreamWaitEvent(st, e->copied[b], 0));
         int64_t n_g = 0;
         const int64_t room = std::max<int64_t>(capacity - done, 0);
@@ -201,7 +207,7 @@ extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *n
                                     e->p_probs.as<float>() + done * 3, &n_g, stream_);
         if (rc == PB_ERR_CAPACITY) {
             // the caller retries with the returned size: extrapolate from the regions seen so far (retried again if short)
-            const int64_t seen = std::min(n_regions, (g + 1) * CALL_GROUP);
+            const int64_t seen = gb[g + 1];
             const int64_t need = (int64_t) ((double) (done + n_g) * (double) n_regions / (double) seen * 1.25) + 4096;
             cudaStreamSynchronize(e->copy_stream);
             *n_out = need;
@@ -210,7 +216,7 @@ extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *n
         }
         if (rc != PB_OK) return rc;
         if (n_g > 0 && g > 0)
-            k_add_offset_i32<<<(unsigned) ceil_div(n_g, 256), 256, 0, st>>>(e->p_region_of.as<int32_t>() + done, n_g, (int32_t) (g * CALL_GROUP));
+            k_add_offset_i32<<<(unsigned) ceil_div(n_g, 256), 256, 0, st>>>(e->p_region_of.as<int32_t>() + done, n_g, (int32_t) gb[g]);
         enc_ms += e->pms[0]; net_ms += e->pms[1];
         done += n_g;
     }

@@ -110,12 +110,15 @@ class VariantCaller:
         self.net.close()
 
     def call(self, reads: ReadBatch, regions: RegionTable, params: dict, capacity: int | None = None,
-             want_images: bool = False, stream: int = 0) -> VariantCalls:
+             want_images: bool = False, stream: int = 0, reuse_buffers: bool = False) -> VariantCalls:
         hr = HostReads(reads)
-        return self.call_prepared(hr, regions, params, capacity, want_images, stream)
+        return self.call_prepared(hr, regions, params, capacity, want_images, stream, reuse_buffers)
 
     def call_prepared(self, hr: HostReads, regions: RegionTable, params: dict, capacity: int | None = None,
-                      want_images: bool = False, stream: int = 0) -> VariantCalls:
+                      want_images: bool = False, stream: int = 0, reuse_buffers: bool = False) -> VariantCalls:
+        """`reuse_buffers=True`: results land in page-locked buffers owned by the caller object and the returned arrays are
+        views of them (valid until the next call) — the streaming mode a pipeline worker uses; default: fresh arrays."""
+        self._reuse = reuse_buffers
         regs, keep = regions_array(regions)
         ref = np.ascontiguousarray(regions.ref, dtype=np.uint8)
         p = variant_params(**params)
@@ -123,13 +126,13 @@ class VariantCaller:
             span = int((regions.col("cand_end") - regions.col("cand_start") + 1).sum())
             capacity = max(1024, span // 16)
         while True:
-            img = np.empty((capacity, WINDOW, FEATURES), dtype=np.int8) if want_images else None
-            pos = np.empty(capacity, dtype=np.int64)
-            dep = np.empty(capacity, dtype=np.uint8)
-            frq = np.empty(capacity, dtype=np.uint8)
-            keys = np.empty((capacity, ALLELE_STRIDE), dtype=np.uint8)
-            rof = np.empty(capacity, dtype=np.int32)
-            probs = np.empty((capacity, 3), dtype=np.float32)
+            img = self._out("images", (capacity, WINDOW, FEATURES), np.int8) if want_images else None
+            pos = self._out("positions", (capacity,), np.int64)
+            dep = self._out("depths", (capacity,), np.uint8)
+            frq = self._out("freqs", (capacity,), np.uint8)
+            keys = self._out("keys", (capacity, ALLELE_STRIDE), np.uint8)
+            rof = self._out("region_of", (capacity,), np.int32)
+            probs = self._out("probs", (capacity, 3), np.float32)
             n = C.c_int64(0)
             rc = self.L.pb_variant_call_host(self.enc.h, self.net.h, C.byref(hr.struct), regs, regions.n_regions,
                                              ref.ctypes.data, ref.shape[0], C.byref(p), capacity,
@@ -142,6 +145,20 @@ class VariantCaller:
             _lib.check(rc, "pb_variant_call_host")
             k = int(n.value)
             return VariantCalls(pos[:k], dep[:k], frq[:k], keys[:k], rof[:k], probs[:k], img[:k] if want_images else None)
+
+    def _out(self, name: str, shape, dtype):
+        """Page-locked result buffers, reused across calls (the returned arrays are views: copy them to keep them past
+        the next call)."""
+        if not getattr(self, "_reuse", False):
+            return np.empty(shape, dtype=dtype)
+        import torch
+        cache = self.__dict__.setdefault("_pinned", {})
+        need = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        t = cache.get(name)
+        if t is None or t.numel() < need:
+            t = torch.empty(max(need, 1), dtype=torch.uint8).pin_memory()
+            cache[name] = t
+        return t.numpy()[:need].view(dtype).reshape(shape)
 
     def call_device(self, dreads: DeviceReads, params: dict, out: dict, stream: int = 0) -> int:
         """Everything in HBM.  `out` holds torch CUDA tensors: images int8 [cap,33,26], positions int64 [cap],
