@@ -91,5 +91,5 @@ namespace pb {
 int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, float *d_probs, float *d_hidden_dbg, cudaStream_t st,
                        void (*out_kernel)(const float *, const float *, const float *, float *, int64_t, cudaStream_t));
 int polish_forward_tc(pb_polish_net *N, const uint8_t *d_images, int64_t B, int64_t n_total, int64_t b0, float *d_hidden_dbg,
-                      float *ydec_f32, void (*dense_kernel)(pb_polish_net *, const float *, int64_t, int, cudaStream_t), cudaStream_t st);
+                      cudaStream_t st);
 }  // namespace pb

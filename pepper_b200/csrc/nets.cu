@@ -595,9 +595,6 @@ extern "C" int pb_polish_net_set_mode(pb_polish_net_t *N, int mode) {
     N->mode = mode;
     return PB_OK;
 }
-static void launch_polish_dense(pb_polish_net *N, const float *ydec, int64_t B, int win_start, cudaStream_t st) {
-    k_polish_dense_acc<<<(unsigned) ceil_div(B * PWIN, 8), 256, 0, st>>>(ydec, N->dW.as<float>(), N->dB.as<float>(), N->acc.as<float>(), B, win_start);
-}
 extern "C" int pb_polish_net_launches(pb_polish_net_t *N, int64_t *n) {
     if (!N || !n) return PB_ERR_ARG;
     *n = N->launches;
@@ -645,17 +642,19 @@ extern "C" int pb_polish_net_forward_device(pb_polish_net_t *N, const uint8_t *d
     for (int64_t b0 = 0; b0 < n; b0 += chunk) {
         const int64_t B = std::min(chunk, n - b0);
         if (B > N->chunk) {
-            for (int i = 0; i < 2; i++) PB_TRY(N->h[i].reserve(sizeof(float) * 2 * B * PH));
-            PB_TRY(N->yenc.reserve(sizeof(float) * B * PWIN * 256));
-            PB_TRY(N->ydec.reserve(sizeof(float) * B * PWIN * 256));
+            if (N->mode == 0) {
+                for (int i = 0; i < 2; i++) PB_TRY(N->h[i].reserve(sizeof(float) * 2 * B * PH));
+                PB_TRY(N->yenc.reserve(sizeof(float) * B * PWIN * 256));
+                PB_TRY(N->ydec.reserve(sizeof(float) * B * PWIN * 256));
+            }
             PB_TRY(N->acc.reserve(sizeof(float) * B * PSEQ * 5));
             N->chunk = B;
         }
         const uint8_t *img = d_images + b0 * PSEQ * 10;
-        PB_CUDA(cudaMemsetAsync(N->h[0].p, 0, sizeof(float) * 2 * B * PH, st));       // hidden = zeros (cpu.py:53)
+        if (N->mode == 0) PB_CUDA(cudaMemsetAsync(N->h[0].p, 0, sizeof(float) * 2 * B * PH, st));       // hidden = zeros (cpu.py:53)
         PB_CUDA(cudaMemsetAsync(N->acc.p, 0, sizeof(float) * B * PSEQ * 5, st));
         if (N->mode == 1) {
-            PB_TRY(polish_forward_tc(N, img, B, n, b0, d_hidden_dbg, N->ydec.as<float>(), launch_polish_dense, st));
+            PB_TRY(polish_forward_tc(N, img, B, n, b0, d_hidden_dbg, st));
         } else
         for (int w = 0; w < PNWIN; w++) {
             const int i = w * PJUMP;

@@ -234,25 +234,47 @@ __global__ void k_tc_unpack_hidden(const bf16 *__restrict__ y_hi, const bf16 *__
     const int64_t o = (((b >> 7) * PWIN + tt) * 8 + d * 4 + (j >> 5)) * TILE_ELEMS + ((j & 31) >> 3) * 1024 + (b & 127) * 8 + (j & 7);
     out[i] = __bfloat162float(y_hi[o]) + __bfloat162float(y_lo[o]);
 }
-// fp32 [B][100][256] decoder output out of its sequence operand (input of the dense+softmax kernel)
-__global__ void k_tc_unpack_seq(const bf16 *__restrict__ y_hi, const bf16 *__restrict__ y_lo, float *__restrict__ out, int64_t B) {
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;      // (b, t, f/8)
-    if (i >= B * PWIN * 32) return;
-    const int f8 = (int) (i & 31);
-    const int t = (int) ((i >> 5) % PWIN);
-    const int64_t b = i / (32 * PWIN);
-    const int64_t o = (((b >> 7) * PWIN + t) * 8 + (f8 >> 2)) * TILE_ELEMS + (f8 & 3) * 1024 + (b & 127) * 8;
-    const uint4 h = *reinterpret_cast<const uint4 *>(y_hi + o), l = *reinterpret_cast<const uint4 *>(y_lo + o);
-    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-    float v[8];
+// dense1 (256 -> 5) + softmax + window accumulate straight from the decoder's tiled output operand
+// (predict_distributed_cpu.py:62-81): one thread per (image row, time step); lanes = consecutive rows of a row tile, so
+// every 16-byte operand load is coalesced; no fp32 copy of the decoder output is ever written.
+__global__ void __launch_bounds__(128) k_polish_dense_tiles(const bf16 *__restrict__ y_hi, const bf16 *__restrict__ y_lo,
+                                                            const float *__restrict__ W /* [5][256] */, const float *__restrict__ bias,
+                                                            float *__restrict__ acc /* [B][1000][5] */, int64_t B, int win_start) {
+    __shared__ float sW[5 * 256];
+    for (int i = threadIdx.x; i < 5 * 256; i += 128) sW[i] = W[i];
+    __syncthreads();
+    const int64_t mt = blockIdx.x / PWIN;
+    const int t = (int) (blockIdx.x % PWIN);
+    const int r128 = threadIdx.x;
+    const int64_t row = mt * 128 + r128;
+    if (row >= B) return;
+    float s[5] = {bias[0], bias[1], bias[2], bias[3], bias[4]};
+    const int64_t tile0 = (mt * PWIN + t) * 8;
+#pragma unroll 2
+    for (int kt = 0; kt < 8; kt++) {
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const uint16_t hb = (uint16_t) (hw[e >> 1] >> (16 * (e & 1))), lb = (uint16_t) (lw[e >> 1] >> (16 * (e & 1)));
-        v[e] = __uint_as_float((uint32_t) hb << 16) + __uint_as_float((uint32_t) lb << 16);
+        for (int kc = 0; kc < 4; kc++) {
+            const int64_t o = (tile0 + kt) * TILE_ELEMS + kc * 1024 + r128 * 8;
+            const uint4 h = *reinterpret_cast<const uint4 *>(y_hi + o), l = *reinterpret_cast<const uint4 *>(y_lo + o);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const float v = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+                const int f = kt * 32 + kc * 8 + e;
+#pragma unroll
+                for (int c = 0; c < 5; c++) s[c] = fmaf(v, sW[c * 256 + f], s[c]);
+            }
+        }
     }
-    float4 *dst = reinterpret_cast<float4 *>(out + (b * PWIN + t) * 256 + f8 * 8);
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    float m = s[0];
+#pragma unroll
+    for (int c = 1; c < 5; c++) m = fmaxf(m, s[c]);
+    float e[5], sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 5; c++) { e[c] = expf(s[c] - m); sum += e[c]; }
+    float *dst = acc + (row * 1000 + win_start + t) * 5;
+#pragma unroll
+    for (int c = 0; c < 5; c++) dst[c] += e[c] / sum;
 }
 
 // one bidirectional GRU layer over the 100 steps of a window: ONE cooperative launch of k_gru_window.
@@ -299,7 +321,7 @@ static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi
 }
 
 int polish_forward_tc(pb_polish_net *N, const uint8_t *d_images, int64_t B, int64_t n_total, int64_t b0, float *d_hidden_dbg,
-                      float *ydec_f32, void (*dense_kernel)(pb_polish_net *, const float *, int64_t, int, cudaStream_t), cudaStream_t st) {
+                      cudaStream_t st) {
     TcPolish &T = *N->tc;
     const int64_t Mt = ceil_div(B, 128);
     const int64_t seq = Mt * PWIN * 8 * TILE_ELEMS;
@@ -323,9 +345,8 @@ int polish_forward_tc(pb_polish_net *N, const uint8_t *d_images, int64_t B, int6
                                                                                     d_hidden_dbg + ((int64_t) w * n_total + b0) * 2 * PH, B);
             N->launches++;
         }
-        k_tc_unpack_seq<<<(unsigned) ceil_div(B * PWIN * 32, 256), 256, 0, st>>>(T.ydec_hi.as<bf16>(), T.ydec_lo.as<bf16>(), ydec_f32, B);
-        N->launches++;
-        dense_kernel(N, ydec_f32, B, i, st);
+        k_polish_dense_tiles<<<(unsigned) (Mt * PWIN), 128, 0, st>>>(T.ydec_hi.as<bf16>(), T.ydec_lo.as<bf16>(), N->dW.as<float>(), N->dB.as<float>(),
+                                                                    N->acc.as<float>(), B, i);
         N->launches++;
     }
     PB_CUDA(cudaGetLastError());

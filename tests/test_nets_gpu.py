@@ -107,4 +107,28 @@ def test_polish_net_vs_oracle(n, seed, mode):
     _check_bases(bases, wb, wa, phred, wp, acc)
     b2, p2 = net.predict(x)
     assert np.array_equal(b2, bases) and np.array_equal(p2, phred)
-    assert net.launches() == (19 * 201 + 1 if mode == 0 else 19 * 5 + 1)     # tcgen05: one launch per window layer
+    assert net.launches() == (19 * 201 + 1 if mode == 0 else 19 * 4 + 1)     # tcgen05: pack, encoder window, decoder window, dense+softmax
+
+
+def test_variant_net_chunk_invariance():
+    """Full-size property: a candidate's probabilities do not depend on what else is in the batch or on where the
+    9,472-candidate chunk boundaries fall (20,000 candidates = 3 chunks vs the same rows predicted in small batches)."""
+    from pepper_b200 import weights
+    from pepper_b200.variant import VariantNet
+    net = VariantNet(weights.random_variant_state(3))
+    x = _variant_images(20000, 9)
+    full = net.predict(x)
+    assert np.isfinite(full).all() and np.allclose(full.sum(1), 1.0, atol=1e-5)
+    for lo, hi in ((0, 100), (9400, 9600), (18900, 20000)):
+        assert np.array_equal(net.predict(x[lo:hi]), full[lo:hi])
+    assert np.array_equal(net.predict(x), full)                      # idempotent
+
+
+def test_polish_net_batch_invariance():
+    from pepper_b200 import weights
+    from pepper_b200.polish import PolishNet
+    net = PolishNet(weights.random_polish_state(4))
+    x = _polish_images(300, 8)
+    b, p = net.predict(x)
+    b2, p2 = net.predict(x[120:140])
+    assert np.array_equal(b2, b[120:140]) and np.array_equal(p2, p[120:140])
