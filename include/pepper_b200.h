@@ -94,6 +94,62 @@ int  pb_version(void);
 int  pb_device_count(void);
 
 /* ------------------------------------------------------------------------
+ * Region read fetch + trim.  Replaces the per-record body of
+ *   BAM_handler::get_reads(chromosome, start, stop, include_supplementary,
+ *                          min_mapq, min_baseq)
+ * (pepper/modules/src/dataio/bam_handler.cpp:115-451; the pepper_variant copy
+ * pepper_variant/modules/cpp/bam_handler.cpp is identical) for a BATCH of
+ * region queries against one coordinate-sorted contig held in device memory:
+ *   - which records a query returns: htslib 1.9 iterator overlap rule
+ *     (pos < stop && pos + max(reference length of the CIGAR, n_cigar ? 0 : 1) > start)
+ *   - flag / MAPQ filters                                   bam_handler.cpp:139-150
+ *   - the CIGAR-walk trim to [start, stop] (inclusive stop, anchor on the first
+ *     match base, I/S/D/N only after the anchor)             bam_handler.cpp:176-303
+ *   - reads left without bases are dropped                  bam_handler.cpp:432
+ * The trimmed reads come out as a pb_reads_t in HBM that feeds the encoders
+ * directly.  Record fields the encoders never read (query_name, bad_indicies,
+ * hp_tag; min_baseq only feeds bad_indicies) are not materialised.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    int64_t         n_records;
+    const int64_t  *pos;        /* [n]   bam1_core_t.pos, non-decreasing               */
+    const int64_t  *seq_off;    /* [n+1] base (nibble) offsets into seq / byte offsets into qual */
+    const int64_t  *cigar_off;  /* [n+1]                                               */
+    const uint16_t *flag;       /* [n]   bam1_core_t.flag (SAM FLAG bits)              */
+    const uint8_t  *mapq;       /* [n]   bam1_core_t.qual                              */
+    const uint8_t  *seq;        /* 4-bit codes, bam_get_seq                            */
+    const uint8_t  *qual;       /* bam_get_qual                                        */
+    const uint32_t *cigar;      /* len<<4|op, bam_get_cigar                            */
+} pb_records_t;
+
+typedef struct { int64_t start, stop; } pb_interval_t;          /* get_reads(chrom, start, stop) */
+typedef struct { int32_t include_supplementary, min_mapq, min_baseq, reserved; } pb_get_reads_options_t;
+
+typedef struct pb_read_trimmer pb_read_trimmer_t;
+int pb_read_trimmer_create(pb_read_trimmer_t **out, int device);
+int pb_read_trimmer_destroy(pb_read_trimmer_t *t);
+
+/* Phase 1: evaluate every query.  h_reads_per_interval[i] = len(get_reads(...)) of query i. */
+int pb_get_reads_plan_device(pb_read_trimmer_t *t, const pb_records_t *d_records /* struct on host, pointers on device */,
+                             const pb_interval_t *h_intervals, int64_t n_intervals,
+                             const pb_get_reads_options_t *opt, int64_t *h_reads_per_interval, void *stream);
+/* Phase 2: write the trimmed reads of the planned queries.  h_select (optional) lists, per query, indices into that
+ * query's result in get_reads order - the reference's reservoir sample (AlignmentSummarizer.py:113-125) - NULL = all.
+ * d_reads_out is a view of buffers owned by the trimmer (valid until its next plan/destroy); reads of query i are
+ * [h_read_begin[i], h_read_end[i]).                                                                              */
+int pb_get_reads_emit_device(pb_read_trimmer_t *t, const int64_t *h_select_off /* [n+1] or NULL */,
+                             const int32_t *h_select, pb_reads_t *d_reads_out,
+                             int64_t *h_read_begin, int64_t *h_read_end, void *stream);
+/* sizes[3] = n_reads, n_bases, n_cigar of the last emit; fetch copies it to host arrays sized accordingly */
+int pb_get_reads_sizes(pb_read_trimmer_t *t, int64_t *sizes);
+int pb_get_reads_fetch(pb_read_trimmer_t *t, int64_t *pos, int64_t *seq_off, int64_t *cigar_off, uint8_t *flags,
+                       uint8_t *mapq, uint8_t *seq, uint8_t *qual, uint32_t *cigar, void *stream);
+/* Host-buffer convenience: upload the records, plan.  (emit/fetch as above) */
+int pb_get_reads_plan_host(pb_read_trimmer_t *t, const pb_records_t *h_records,
+                           const pb_interval_t *h_intervals, int64_t n_intervals,
+                           const pb_get_reads_options_t *opt, int64_t *h_reads_per_interval, void *stream);
+
+/* ------------------------------------------------------------------------
  * Variant encoder.  Replaces
  *   RegionalSummaryGenerator(contig, region_start, region_end, ref_seq)
  *     .generate_max_insert_summary(reads)

@@ -12,9 +12,9 @@ import os
 import subprocess
 import numpy as np
 
-from pepper_b200.abi import (HostReads, PbReads, PbRegion, PbVariantParams, regions_array, variant_params,
-                             WINDOW, FEATURES, ALLELE_STRIDE, POLISH_FEATURES)
-from pepper_b200.synth import ReadBatch, RegionTable
+from pepper_b200.abi import (HostReads, HostRecords, PbReads, PbRecords, PbRegion, PbVariantParams, regions_array,
+                             variant_params, WINDOW, FEATURES, ALLELE_STRIDE, POLISH_FEATURES)
+from pepper_b200.synth import ReadBatch, RecordBatch, RegionTable, NT16, CODE_OF, pack_codes
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -34,11 +34,12 @@ _libs: dict[str, C.CDLL] = {}
 
 
 def lib(kind: str) -> C.CDLL:
-    """kind in {'port', 'ref_variant', 'ref_polish'}"""
+    """kind in {'port', 'ref_variant', 'ref_polish', 'ref_getreads'}"""
     if kind not in _libs:
         path = {"port": os.path.join(HERE, "liboracle_port.so"),
                 "ref_variant": os.path.join(HERE, "_ref", "libref_variant.so"),
-                "ref_polish": os.path.join(HERE, "_ref", "libref_polish.so")}[kind]
+                "ref_polish": os.path.join(HERE, "_ref", "libref_polish.so"),
+                "ref_getreads": os.path.join(HERE, "_ref", "libref_getreads.so")}[kind]
         L = _load(path)
         if kind in ("port", "ref_variant"):
             pre = "port" if kind == "port" else "ref"
@@ -57,6 +58,16 @@ def lib(kind: str) -> C.CDLL:
             g.restype = None
             g.argtypes = [C.c_void_p] * 3
         if kind == "port":
+            L.port_get_reads.restype = C.c_int64
+            L.port_get_reads.argtypes = [C.POINTER(PbRecords), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11
+        if kind == "ref_getreads":
+            L.ref_getreads_load.restype = None
+            L.ref_getreads_load.argtypes = [C.POINTER(PbRecords)]
+            L.ref_getreads_query.restype = None
+            L.ref_getreads_query.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            L.ref_getreads_fetch.restype = None
+            L.ref_getreads_fetch.argtypes = [C.c_void_p] * 11
+        if kind == "port":
             L.port_variant_debug.restype = None
             L.port_variant_debug.argtypes = [C.c_void_p] * 5
         _libs[kind] = L
@@ -66,6 +77,56 @@ def lib(kind: str) -> C.CDLL:
 def have_ref() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libref_variant.so")) and \
         os.path.exists(os.path.join(HERE, "_ref", "libref_polish.so"))
+
+
+def have_ref_getreads() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_getreads.so"))
+
+
+_loaded_records = [None]
+
+
+def get_reads(records: RecordBatch, start: int, stop: int, include_supplementary: bool = False, min_mapq: int = 0,
+              min_baseq: int = 0, impl: str = "port"):
+    """BAM_handler.get_reads for one query.  Returns (ReadBatch, pos_end int64 [n], n_bad int64 [n]).
+    impl='port': oracle/port_getreads.c;  impl='ref': the unmodified reference function (oracle/_ref/libref_getreads.so)."""
+    hr = HostRecords(records)
+    nb, nc, n = int(records.seq_off[-1]), int(records.cigar_off[-1]), records.n_records
+    sizes = np.zeros(3, dtype=np.int64)
+    if impl == "port":
+        L = lib("port")
+        pos, pos_end, n_bad = (np.zeros(n + 1, dtype=np.int64) for _ in range(3))
+        seq_off, cigar_off = np.zeros(n + 2, dtype=np.int64), np.zeros(n + 2, dtype=np.int64)
+        flags, mapq = np.zeros(n + 1, dtype=np.uint8), np.zeros(n + 1, dtype=np.uint8)
+        seq, qual, cigar = np.zeros(nb // 2 + 2, dtype=np.uint8), np.zeros(nb + 1, dtype=np.uint8), np.zeros(nc + 1, dtype=np.uint32)
+        L.port_get_reads(C.byref(hr.struct), start, stop, int(include_supplementary), min_mapq, min_baseq,
+                         pos.ctypes.data, pos_end.ctypes.data, seq_off.ctypes.data, cigar_off.ctypes.data, flags.ctypes.data,
+                         mapq.ctypes.data, seq.ctypes.data, qual.ctypes.data, cigar.ctypes.data, n_bad.ctypes.data, sizes.ctypes.data)
+        m, mb, mc = (int(x) for x in sizes)
+        return (ReadBatch(pos[:m].copy(), seq_off[:m + 1].copy(), cigar_off[:m + 1].copy(), flags[:m].copy(), mapq[:m].copy(),
+                          seq[:(mb + 1) // 2].copy(), qual[:mb].copy(), cigar[:mc].copy()), pos_end[:m].copy(), n_bad[:m].copy())
+    L = lib("ref_getreads")
+    if _loaded_records[0] is not records:
+        L.ref_getreads_load(C.byref(hr.struct))
+        _loaded_records[0] = records
+    L.ref_getreads_query(start, stop, int(include_supplementary), min_mapq, min_baseq, sizes.ctypes.data)
+    m, mb, mc = (int(x) for x in sizes)
+    pos, pos_end, n_bad = (np.zeros(m + 1, dtype=np.int64) for _ in range(3))
+    seq_off, cigar_off = np.zeros(m + 1, dtype=np.int64), np.zeros(m + 1, dtype=np.int64)
+    flags, mapq = np.zeros(m + 1, dtype=np.uint8), np.zeros(m + 1, dtype=np.uint8)
+    ascii_ = np.zeros(mb + 1, dtype=np.uint8)
+    qual = np.zeros(mb + 1, dtype=np.uint8)
+    op, ln = np.zeros(mc + 1, dtype=np.int32), np.zeros(mc + 1, dtype=np.int32)
+    L.ref_getreads_fetch(pos.ctypes.data, pos_end.ctypes.data, seq_off.ctypes.data, cigar_off.ctypes.data, flags.ctypes.data,
+                         mapq.ctypes.data, ascii_.ctypes.data, qual.ctypes.data, op.ctypes.data, ln.ctypes.data, n_bad.ctypes.data)
+    lut = np.full(256, 255, dtype=np.uint8)
+    for ch, code in CODE_OF.items():
+        lut[ord(ch)] = code
+    codes = lut[ascii_[:mb]]
+    assert (codes != 255).all()
+    cigar = ((ln[:mc].astype(np.uint32) << 4) | op[:mc].astype(np.uint32)).astype(np.uint32)
+    return (ReadBatch(pos[:m].copy(), seq_off.copy(), cigar_off.copy(), flags[:m].copy(), mapq[:m].copy(), pack_codes(codes),
+                      qual[:mb].copy(), cigar), pos_end[:m].copy(), n_bad[:m].copy())
 
 
 def variant_encode(reads: ReadBatch, regions: RegionTable, params: dict, impl: str = "port",

@@ -1,3 +1,3 @@
+// TEST INFRASTRUCTURE ONLY (oracle): see sam.h (in-memory stand-in for the htslib calls BAM_handler makes).
 #pragma once
-#include <cstdint>
-struct htsFile; struct hts_idx_t; struct bam_hdr_t;
+#include "sam.h"

@@ -4,7 +4,7 @@ from __future__ import annotations
 import ctypes as C
 import numpy as np
 
-from .synth import ReadBatch, RegionTable
+from .synth import ReadBatch, RecordBatch, RegionTable
 
 WINDOW = 33
 FEATURES = 26
@@ -24,6 +24,22 @@ class PbReads(C.Structure):
                 ("pos", C.c_void_p), ("seq_off", C.c_void_p), ("cigar_off", C.c_void_p),
                 ("flags", C.c_void_p), ("mapq", C.c_void_p),
                 ("seq", C.c_void_p), ("qual", C.c_void_p), ("cigar", C.c_void_p)]
+
+
+class PbRecords(C.Structure):
+    _fields_ = [("n_records", C.c_int64),
+                ("pos", C.c_void_p), ("seq_off", C.c_void_p), ("cigar_off", C.c_void_p),
+                ("flag", C.c_void_p), ("mapq", C.c_void_p),
+                ("seq", C.c_void_p), ("qual", C.c_void_p), ("cigar", C.c_void_p)]
+
+
+class PbInterval(C.Structure):
+    _fields_ = [("start", C.c_int64), ("stop", C.c_int64)]
+
+
+class PbGetReadsOptions(C.Structure):
+    _fields_ = [("include_supplementary", C.c_int32), ("min_mapq", C.c_int32), ("min_baseq", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class PbRegion(C.Structure):
@@ -73,6 +89,30 @@ class HostReads:
         self.struct = PbReads(b.n_reads, self.pos.ctypes.data, self.seq_off.ctypes.data,
                               self.cigar_off.ctypes.data, self.flags.ctypes.data, self.mapq.ctypes.data,
                               self.seq.ctypes.data, self.qual.ctypes.data, self.cigar.ctypes.data)
+
+
+class HostRecords:
+    """Keeps the numpy arrays alive and exposes a pb_records_t pointing at them."""
+
+    def __init__(self, b: RecordBatch):
+        self.pos = _c(b.pos, np.int64)
+        self.seq_off = _c(b.seq_off, np.int64)
+        self.cigar_off = _c(b.cigar_off, np.int64)
+        self.flag = _c(b.flag, np.uint16)
+        self.mapq = _c(b.mapq, np.uint8)
+        self.seq = _c(np.concatenate([b.seq, np.zeros(1, np.uint8)]), np.uint8)
+        self.qual = _c(np.concatenate([b.qual, np.zeros(1, np.uint8)]), np.uint8)
+        self.cigar = _c(np.concatenate([b.cigar, np.zeros(1, np.uint32)]), np.uint32)
+        self.nbytes = sum(getattr(self, n).nbytes for n in ("pos", "seq_off", "cigar_off", "flag", "mapq", "seq", "qual", "cigar"))
+        self.struct = PbRecords(b.n_records, self.pos.ctypes.data, self.seq_off.ctypes.data, self.cigar_off.ctypes.data,
+                                self.flag.ctypes.data, self.mapq.ctypes.data, self.seq.ctypes.data, self.qual.ctypes.data,
+                                self.cigar.ctypes.data)
+
+
+def intervals_array(intervals):
+    """ctypes array of pb_interval_t from [(start, stop), ...]"""
+    t = _c(np.asarray(intervals, dtype=np.int64).reshape(-1, 2), np.int64)
+    return (PbInterval * t.shape[0]).from_buffer(t), t
 
 
 def regions_array(tab: RegionTable):

@@ -236,3 +236,26 @@ class PolishCaller:
         d = dict(encode_ms=float(ms[0]), network_ms=float(ms[1]))
         d.update({"enc_" + k: v for k, v in self.enc.timings().items()})
         return d
+
+
+class FetchedReads:
+    """Output of a batched ReadTrimmer.get_reads (reads in HBM, one query per region) + the region table: the object
+    VariantCaller.call_device / PolishCaller.call_device take in place of DeviceReads.  read_begin / read_end of the
+    table come from the trimmer."""
+
+    def __init__(self, trimmed, regions: RegionTable, device: int = 0):
+        import torch
+        dev = torch.device("cuda", device)
+        assert trimmed.read_begin.shape[0] == regions.n_regions
+        tab = np.ascontiguousarray(regions.table, dtype=np.int64).copy()
+        tab[:, 6] = trimmed.read_begin
+        tab[:, 7] = trimmed.read_end
+        self.table = tab
+        self._trimmed = trimmed
+        self.struct = trimmed.struct
+        self.h_regions = (PbRegion * tab.shape[0]).from_buffer(tab)
+        self._keep = [torch.from_numpy(tab).to(dev), torch.from_numpy(np.ascontiguousarray(regions.ref, dtype=np.uint8)).to(dev)]
+        self.d_regions = self._keep[0].data_ptr()
+        self.d_ref = self._keep[1].data_ptr()
+        self.ref_bytes = int(self._keep[1].numel())
+        self.n_regions = regions.n_regions

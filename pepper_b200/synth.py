@@ -389,6 +389,24 @@ def region_batch(reads: ReadBatch, regions: RegionTable, r: int):
     return sub, RegionTable(row[None, :], ref)
 
 
+def take_reads(reads: ReadBatch, indices) -> ReadBatch:
+    """Gather reads in the given order (down-sampled / permuted read lists)."""
+    idx = np.asarray(indices, dtype=np.int64)
+    codes = reads.codes()
+    lens = reads.seq_off[idx + 1] - reads.seq_off[idx]
+    clens = reads.cigar_off[idx + 1] - reads.cigar_off[idx]
+    seq_off = np.zeros(idx.shape[0] + 1, dtype=np.int64)
+    cig_off = np.zeros(idx.shape[0] + 1, dtype=np.int64)
+    np.cumsum(lens, out=seq_off[1:])
+    np.cumsum(clens, out=cig_off[1:])
+    pick = [np.arange(reads.seq_off[i], reads.seq_off[i + 1]) for i in idx]
+    cpick = [np.arange(reads.cigar_off[i], reads.cigar_off[i + 1]) for i in idx]
+    bi = np.concatenate(pick).astype(np.int64) if pick else np.zeros(0, dtype=np.int64)
+    ci = np.concatenate(cpick).astype(np.int64) if cpick else np.zeros(0, dtype=np.int64)
+    return ReadBatch(reads.pos[idx].copy(), seq_off, cig_off, reads.flags[idx].copy(), reads.mapq[idx].copy(),
+                     pack_codes(codes[bi]), reads.qual[bi].copy(), reads.cigar[ci].copy())
+
+
 def ont_params() -> dict:
     """--ont_r9_guppy5_sup image-generation thresholds, SetParameters.py:16-37."""
     return dict(min_snp_baseq=1, min_indel_baseq=1, snp_freq_threshold=0.10, insert_freq_threshold=0.15,
@@ -401,3 +419,74 @@ def hifi_params() -> dict:
     return dict(min_snp_baseq=10, min_indel_baseq=10, snp_freq_threshold=0.10, insert_freq_threshold=0.12,
                 delete_freq_threshold=0.10, min_coverage_threshold=2, snp_candidate_freq_threshold=0.10,
                 indel_candidate_freq_threshold=0.10, candidate_support_threshold=2, skip_indels=0)
+
+
+# ------------------------------------------------------------------ raw alignment records (input of get_reads, row a2)
+FLAG_REVERSE, FLAG_UNMAP, FLAG_SECONDARY, FLAG_QCFAIL, FLAG_DUP, FLAG_SUPP = 16, 4, 256, 512, 1024, 2048
+
+
+@dataclass
+class RecordBatch:
+    """SoA batch of alignment records as htslib hands them to BAM_handler::get_reads == pb_records_t
+    (coordinate-sorted, one contig; BAM-native packing)."""
+    pos: np.ndarray          # int64 [n]
+    seq_off: np.ndarray      # int64 [n+1]
+    cigar_off: np.ndarray    # int64 [n+1]
+    flag: np.ndarray         # uint16 [n]   SAM FLAG
+    mapq: np.ndarray         # uint8 [n]
+    seq: np.ndarray          # uint8 packed
+    qual: np.ndarray         # uint8 [nbases]
+    cigar: np.ndarray        # uint32 [nops]
+
+    @property
+    def n_records(self) -> int:
+        return int(self.pos.shape[0])
+
+    @property
+    def n_bases(self) -> int:
+        return int(self.seq_off[-1])
+
+
+def make_records(records: list[dict]) -> RecordBatch:
+    """Explicit records for the hand-written KATs: pos, seq, qual, cigar [(op,len)...], flag, mapq."""
+    b = make_batch([dict(r, reverse=False) for r in records])
+    flag = np.array([r.get("flag", 0) for r in records], dtype=np.uint16)
+    return RecordBatch(b.pos, b.seq_off, b.cigar_off, flag, b.mapq, b.seq, b.qual, b.cigar)
+
+
+def simulate_contig_records(contig_len: int, coverage: float, platform: Platform, seed: int, contig_start: int = 0,
+                            p_clip_head: float = 0.3, p_hard: float = 0.05, p_filtered: float = 0.06):
+    """Whole-contig alignment records: the read model of simulate_region_reads over the full contig, then decorated the
+    way an aligner's output is — leading soft / hard clips, trailing hard clips, SAM FLAG bits (reverse, secondary,
+    supplementary, duplicate, QC-fail, unmapped).  Returns (RecordBatch, genome uint8 ASCII)."""
+    genome = make_reference(contig_len, seed)
+    b = simulate_region_reads(genome, contig_start, coverage, platform, seed * 7919 + 13)
+    rng = np.random.default_rng(seed + 991)
+    codes = b.codes()
+    pos, flag, code_l, qual_l, cig_l = [], [], [], [], []
+    seq_off, cig_off = [0], [0]
+    for r in range(b.n_reads):
+        c = codes[b.seq_off[r]:b.seq_off[r + 1]]
+        q = b.qual[b.seq_off[r]:b.seq_off[r + 1]]
+        cg = b.cigar[b.cigar_off[r]:b.cigar_off[r + 1]]
+        head = []
+        if rng.random() < p_clip_head:
+            sl = int(rng.integers(1, 40))
+            c = np.concatenate([ACGT_CODES[rng.integers(0, 4, sl)], c])
+            q = np.concatenate([rng.integers(2, 40, sl).astype(np.uint8), q])
+            head.append((sl << 4) | OP_S)
+        if rng.random() < p_hard:
+            head.insert(0, (int(rng.integers(1, 500)) << 4) | OP_H)
+        tail = [(int(rng.integers(1, 500)) << 4) | OP_H] if rng.random() < p_hard else []
+        cg = np.concatenate([np.array(head, dtype=np.uint32), cg, np.array(tail, dtype=np.uint32)]).astype(np.uint32)
+        f = FLAG_REVERSE if b.flags[r] & 1 else 0
+        if rng.random() < p_filtered:
+            f |= int(rng.choice([FLAG_UNMAP, FLAG_SECONDARY, FLAG_QCFAIL, FLAG_DUP, FLAG_SUPP]))
+        pos.append(int(b.pos[r])); flag.append(f); code_l.append(c); qual_l.append(q); cig_l.append(cg)
+        seq_off.append(seq_off[-1] + c.shape[0]); cig_off.append(cig_off[-1] + cg.shape[0])
+    allc = np.concatenate(code_l) if code_l else np.zeros(0, dtype=np.uint8)
+    rec = RecordBatch(np.array(pos, dtype=np.int64), np.array(seq_off, dtype=np.int64), np.array(cig_off, dtype=np.int64),
+                      np.array(flag, dtype=np.uint16), b.mapq.copy(), pack_codes(allc),
+                      np.concatenate(qual_l) if qual_l else np.zeros(0, dtype=np.uint8),
+                      np.concatenate(cig_l) if cig_l else np.zeros(0, dtype=np.uint32))
+    return rec, genome

@@ -184,3 +184,54 @@ def polish_kats():
     reads.append(dict(pos=S + 250, seq=ref[250:300] + "TT", qual=30, cigar=[(OP_M, 50), (OP_I, 2)]))
     out.append(("insert_after_delete", make_batch(reads), reg(len(reads))))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# get_reads KATs (row a2): records + queries that walk every branch of bam_handler.cpp:176-303
+def getreads_kats():
+    """[(name, RecordBatch, [(start, stop, include_supplementary, min_mapq, min_baseq), ...])]"""
+    from pepper_b200.synth import make_records, OP_M, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X
+    A = "ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"
+
+    def seq(n, off=0):
+        return (A * (n // len(A) + 2))[off:off + n]
+    recs = [
+        # 0: plain match spanning the query on both sides
+        dict(pos=100, seq=seq(200), cigar=[(OP_M, 200)]),
+        # 1: leading hard + soft clip, insertion exactly at `start` (dropped: no anchor yet), match, deletion, match
+        dict(pos=150, seq=seq(10 + 5 + 40 + 30), cigar=[(OP_H, 7), (OP_S, 10), (OP_I, 5), (OP_M, 40), (OP_D, 6), (OP_M, 30)], flag=16),
+        # 2: starts in a deletion relative to start: M ends before start, D spans start, then M
+        dict(pos=120, seq=seq(20 + 50, 3), cigar=[(OP_M, 20), (OP_D, 40), (OP_M, 50)]),
+        # 3: insertion and soft clip right at stop / stop+1, = and X ops, trailing hard clip
+        dict(pos=180, seq=seq(20 + 4 + 20 + 6 + 9, 1), qual=[5, 40] * 29 + [7], cigar=[(OP_EQ, 20), (OP_I, 4), (OP_X, 20), (OP_I, 6), (OP_S, 9), (OP_H, 3)]),
+        # 4: ref skip (N) crossing stop, pad (P) and zero-length ops in the middle
+        dict(pos=185, seq=seq(10 + 3 + 10, 2), cigar=[(OP_M, 10), (OP_P, 4), (OP_I, 3), (OP_M, 0), (OP_N, 50), (OP_M, 10)]),
+        # 5..9: filtered by flag
+        dict(pos=190, seq=seq(30), cigar=[(OP_M, 30)], flag=256),
+        dict(pos=191, seq=seq(30), cigar=[(OP_M, 30)], flag=512),
+        dict(pos=192, seq=seq(30), cigar=[(OP_M, 30)], flag=1024),
+        dict(pos=193, seq=seq(30), cigar=[(OP_M, 30)], flag=4),
+        dict(pos=194, seq=seq(30), cigar=[(OP_M, 30)], flag=2048 | 16),
+        # 10: low MAPQ
+        dict(pos=195, seq=seq(30), cigar=[(OP_M, 30)], mapq=3),
+        # 11: non-ACGT bases and low qualities (bad_indicies rule)
+        dict(pos=196, seq="ACGNNRYACGTACGTAAAAA", qual=[1, 2, 3, 40, 40, 40, 40, 9, 10, 11] * 2, cigar=[(OP_M, 20)]),
+        # 12: overlaps the query only with a deletion -> visited by the iterator, keeps no base, dropped (:432)
+        dict(pos=140, seq=seq(5 + 5), cigar=[(OP_M, 5), (OP_D, 200), (OP_M, 5)]),
+        # 13: record without CIGAR (iterator gives it length 1)
+        dict(pos=210, seq=seq(12), cigar=[]),
+        # 14: single base at exactly stop (inclusive stop)
+        dict(pos=260, seq=seq(40), cigar=[(OP_M, 40)]),
+        # 15: starts exactly at stop+... beyond the query
+        dict(pos=261, seq=seq(40), cigar=[(OP_S, 5), (OP_M, 35)]),
+        # 16: insertion first, then match (I before any anchor inside the region)
+        dict(pos=205, seq=seq(8 + 30), cigar=[(OP_I, 8), (OP_M, 30)]),
+        # 17: match ending exactly at stop followed by insertion at stop+1 (cut) and deletion
+        dict(pos=231, seq=seq(30 + 5 + 10), cigar=[(OP_M, 30), (OP_I, 5), (OP_D, 3), (OP_M, 10)]),
+    ]
+    recs.sort(key=lambda r: r["pos"])
+    batch = make_records(recs)
+    queries = [(160, 260, False, 0, 0), (160, 260, True, 0, 10), (160, 260, False, 20, 0), (100, 101, False, 0, 0),
+               (0, 100, False, 0, 0), (299, 400, False, 0, 0), (260, 261, True, 0, 0), (205, 206, False, 0, 7),
+               (150, 340, True, 0, 0), (199, 200, False, 0, 0), (139, 145, False, 0, 0), (330, 1000, True, 0, 0)]
+    return [("branches", batch, queries)]
