@@ -150,6 +150,37 @@ int pb_get_reads_plan_host(pb_read_trimmer_t *t, const pb_records_t *h_records,
                            const pb_get_reads_options_t *opt, int64_t *h_reads_per_interval, void *stream);
 
 /* ------------------------------------------------------------------------
+ * File readers under BAM_handler / FASTA_handler.  Host code
+ * written from the SAM/BAM/BAI and faidx specifications (the reference gets
+ * these from htslib 1.9: sam_open / sam_index_load / sam_hdr_read /
+ * sam_itr_queryi / sam_itr_next, bam_handler.cpp:6-28,127-135; fai_load /
+ * faidx_fetch_seq, fasta_handler.cpp:7-50).
+ * ---------------------------------------------------------------------- */
+typedef struct pb_bam pb_bam_t;
+/* BAM_handler(path): opens path and path + ".bai" (or name.bai); n_threads <= 0 = all cores (BGZF inflate pool) */
+int pb_bam_open(pb_bam_t **out, const char *path, int n_threads);
+int pb_bam_close(pb_bam_t *b);
+int pb_bam_n_contigs(pb_bam_t *b);                              /* get_chromosome_sequence_names (bam_handler.cpp:103) */
+const char *pb_bam_contig_name(pb_bam_t *b, int tid);
+int64_t pb_bam_contig_length(pb_bam_t *b, int tid);            /* ..._with_length (:88)                              */
+int pb_bam_contig_id(pb_bam_t *b, const char *name);           /* bam_name2id                                         */
+const char *pb_bam_header_text(pb_bam_t *b, int64_t *len);     /* get_sample_names parses @RG SM from it (:30-56)     */
+/* every record sam_itr_queryi(idx, tid, beg, end) / sam_itr_next would return, in file order, as a pb_records_t in
+ * reader-owned host memory (page-locked when a GPU is present; valid until the next fetch / close)                   */
+int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_records_t *h_view);
+int pb_bam_io_stats(pb_bam_t *b, int64_t *compressed_bytes, int64_t *inflated_bytes);
+
+typedef struct pb_fasta pb_fasta_t;
+int pb_fasta_open(pb_fasta_t **out, const char *path);          /* FASTA_handler(path): path + ".fai" must exist       */
+int pb_fasta_close(pb_fasta_t *f);
+int pb_fasta_n_contigs(pb_fasta_t *f);                          /* get_chromosome_names (fasta_handler.cpp:19)         */
+const char *pb_fasta_contig_name(pb_fasta_t *f, int i);
+int64_t pb_fasta_contig_length(pb_fasta_t *f, const char *name);/* get_chromosome_sequence_length (:52)                */
+/* get_reference_sequence(region, start, stop) (:31-50) = faidx_fetch_seq(.., start, stop - 1, &len); *len = -2 when the
+ * contig is absent; PB_ERR_CAPACITY (with *len set) when cap is too small                                            */
+int pb_fasta_fetch(pb_fasta_t *f, const char *name, int64_t start, int64_t stop, char *out, int64_t cap, int64_t *len);
+
+/* ------------------------------------------------------------------------
  * Variant encoder.  Replaces
  *   RegionalSummaryGenerator(contig, region_start, region_end, ref_seq)
  *     .generate_max_insert_summary(reads)

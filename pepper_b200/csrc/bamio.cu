@@ -1,0 +1,555 @@
+// Host-side BAM / BGZF / BAI and FASTA / FAI readers: the file I/O under BAM_handler / FASTA_handler
+// (pepper/modules/src/dataio/bam_handler.cpp:6-28,115-135, fasta_handler.cpp:7-55), which the reference gets from
+// htslib 1.9 (sam_open / sam_index_load / sam_hdr_read / sam_itr_queryi / sam_itr_next, fai_load / faidx_fetch_seq).
+// Written from the format specification (SAMv1 4.1 BGZF, 4.2 BAM, 5.2 BAI; faidx 5-column index), not from htslib.
+//
+// pb_bam_fetch hands back every record the htslib iterator would return for (tid, beg, end) - file order, overlap rule
+// pos < end && pos + max(rlen, n_cigar ? 0 : 1) > beg - as a pb_records_t in (page-locked when a GPU is present) host
+// memory, ready for pb_get_reads_plan_host / one cudaMemcpy.  BGZF blocks of a fetch are inflated by a thread pool and
+// the records are scattered into the SoA arrays in parallel; the trim itself runs on the GPU (get_reads.cu).
+// This file contains no device code; it is host plumbing, not a compute fallback.
+#include "common.cuh"
+#include <zlib.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace pb;
+
+namespace {
+
+struct MappedFile {
+    const uint8_t *p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    bool open(const char *path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { ::close(fd); fd = -1; return false; }
+        n = (size_t) st.st_size;
+        if (n == 0) { p = nullptr; return true; }
+        void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { ::close(fd); fd = -1; return false; }
+        p = (const uint8_t *) m;
+        return true;
+    }
+    void close() {
+        if (p) munmap((void *) p, n);
+        if (fd >= 0) ::close(fd);
+        p = nullptr; fd = -1; n = 0;
+    }
+};
+
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline int32_t rdi32(const uint8_t *p) { int32_t v; memcpy(&v, p, 4); return v; }
+inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+// size of the BGZF block at `off` (0 when it is not a valid block header); payload offset returned through *data_off
+size_t bgzf_block_size(const uint8_t *f, size_t n, size_t off, size_t *data_off) {
+    if (off + 18 > n) return 0;
+    const uint8_t *h = f + off;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+    const size_t xlen = rd16(h + 10);
+    if (off + 12 + xlen > n) return 0;
+    size_t x = 0, bsize = 0;
+    while (x + 4 <= xlen) {
+        const uint8_t *e = h + 12 + x;
+        const size_t slen = rd16(e + 2);
+        if (e[0] == 'B' && e[1] == 'C' && slen == 2) bsize = (size_t) rd16(e + 4) + 1;
+        x += 4 + slen;
+    }
+    if (!bsize || off + bsize > n) return 0;
+    *data_off = 12 + xlen;
+    return bsize;
+}
+
+bool inflate_block(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_len) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = (Bytef *) src; zs.avail_in = (uInt) src_len;
+    zs.next_out = dst; zs.avail_out = (uInt) dst_len;
+    const int rc = inflate(&zs, Z_FINISH);
+    const bool ok = (rc == Z_STREAM_END) && zs.total_out == dst_len;
+    inflateEnd(&zs);
+    return ok;
+}
+
+struct Block { size_t coff, data_off, bsize; uint32_t isize; size_t uoff; };
+
+template <typename F> void parallel_for(int n_threads, size_t n, F f) {
+    if (n_threads <= 1 || n < 2) { for (size_t i = 0; i < n; i++) f(i); return; }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    const int T = (int) std::min<size_t>((size_t) n_threads, n);
+    for (int t = 0; t < T; t++) th.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); });
+    for (auto &x : th) x.join();
+}
+
+struct HostBuf {                 // grow-only; page-locked when a CUDA device is present (faster H2D), plain otherwise
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    bool reserve(size_t bytes, bool want_pinned) {
+        if (bytes <= cap) return true;
+        release();
+        const size_t want = bytes + bytes / 8 + 256;
+        if (want_pinned && cudaMallocHost(&p, want) == cudaSuccess) pinned = true;
+        else { cudaGetLastError(); p = malloc(want); pinned = false; }
+        if (!p) return false;
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+        p = nullptr; cap = 0;
+    }
+    template <typename T> T *as() { return (T *) p; }
+};
+
+struct Chunk { uint64_t beg, end; };
+struct RefIndex { std::map<uint32_t, std::vector<Chunk>> bins; std::vector<uint64_t> linear; };
+
+// bins overlapping [beg, end) (SAMv1 5.3 reg2bins)
+void reg2bins(int64_t beg, int64_t end, std::vector<uint32_t> &out) {
+    --end;
+    out.push_back(0);
+    for (int64_t k = 1 + (beg >> 26); k <= 1 + (end >> 26); ++k) out.push_back((uint32_t) k);
+    for (int64_t k = 9 + (beg >> 23); k <= 9 + (end >> 23); ++k) out.push_back((uint32_t) k);
+    for (int64_t k = 73 + (beg >> 20); k <= 73 + (end >> 20); ++k) out.push_back((uint32_t) k);
+    for (int64_t k = 585 + (beg >> 17); k <= 585 + (end >> 17); ++k) out.push_back((uint32_t) k);
+    for (int64_t k = 4681 + (beg >> 14); k <= 4681 + (end >> 14); ++k) out.push_back((uint32_t) k);
+}
+
+struct RecRef { size_t off; uint32_t l_seq, n_cigar; const uint8_t *cigar; };   // off: start of the record body in the inflated buffer
+
+}  // namespace
+
+struct pb_bam {
+    MappedFile f;
+    int n_threads = 1;
+    bool pinned = false;
+    std::string text;
+    std::vector<std::string> names;
+    std::vector<int64_t> lens;
+    std::vector<RefIndex> index;
+    size_t first_record_voff_block = 0;
+    // fetch scratch / outputs
+    std::vector<uint8_t> ubuf;
+    HostBuf o_pos, o_seq_off, o_cigar_off, o_flag, o_mapq, o_seq, o_qual, o_cigar;
+    int64_t n_compressed = 0, n_inflated = 0;
+};
+
+struct pb_fasta {
+    MappedFile f;
+    struct Entry { std::string name; int64_t len, off, linebases, linewidth; };
+    std::vector<Entry> entries;
+    std::map<std::string, int> by_name;
+};
+
+namespace {
+
+// inflate the blocks covering compressed offsets [c0, c1_block] (c1_block = offset of the LAST block needed)
+int inflate_range(pb_bam *b, size_t c0, size_t c1_block, std::vector<Block> &blocks, std::vector<uint8_t> &out) {
+    blocks.clear();
+    size_t off = c0, utotal = 0;
+    while (off <= c1_block && off < b->f.n) {
+        size_t data_off;
+        const size_t bs = bgzf_block_size(b->f.p, b->f.n, off, &data_off);
+        if (!bs) { set_error("corrupt BGZF block at offset %zu", off); return PB_ERR_ARG; }
+        const uint32_t isize = rd32(b->f.p + off + bs - 4);
+        blocks.push_back({off, data_off, bs, isize, utotal});
+        utotal += isize;
+        off += bs;
+    }
+    out.resize(utotal + 8);
+    std::atomic<int> bad(0);
+    parallel_for(b->n_threads, blocks.size(), [&](size_t i) {
+        const Block &k = blocks[i];
+        if (k.isize && !inflate_block(b->f.p + k.coff + k.data_off, k.bsize - k.data_off - 8, out.data() + k.uoff, k.isize)) bad = 1;
+    });
+    if (bad) { set_error("BGZF inflate failed"); return PB_ERR_ARG; }
+    for (auto &k : blocks) { b->n_compressed += (int64_t) k.bsize; b->n_inflated += k.isize; }
+    return PB_OK;
+}
+
+size_t upos_of(const std::vector<Block> &blocks, uint64_t voff, size_t utotal) {
+    const size_t coff = (size_t) (voff >> 16);
+    auto it = std::lower_bound(blocks.begin(), blocks.end(), coff, [](const Block &k, size_t c) { return k.coff < c; });
+    if (it == blocks.end() || it->coff != coff) return utotal;         // past the last needed block
+    return it->uoff + (size_t) (voff & 0xffff);
+}
+
+int load_header(pb_bam *b) {
+    // the header sits at the start of the file; inflate blocks until it is complete
+    std::vector<Block> blocks;
+    std::vector<uint8_t> u;
+    size_t want_blocks = 1;
+    for (;;) {
+        size_t off = 0, last = 0, cnt = 0;
+        while (off < b->f.n && cnt < want_blocks) { size_t d; const size_t bs = bgzf_block_size(b->f.p, b->f.n, off, &d); if (!bs) break; last = off; off += bs; cnt++; }
+        if (!cnt) { set_error("not a BGZF file"); return PB_ERR_ARG; }
+        PB_TRY(inflate_range(b, 0, last, blocks, u));
+        const size_t n = u.size() - 8;
+        bool complete = false;
+        if (n >= 12 && !memcmp(u.data(), "BAM\1", 4)) {
+            const size_t l_text = rd32(u.data() + 4);
+            size_t p = 8 + l_text;
+            if (p + 4 <= n) {
+                const uint32_t n_ref = rd32(u.data() + p);
+                p += 4;
+                complete = true;
+                b->names.clear(); b->lens.clear();
+                for (uint32_t i = 0; i < n_ref; i++) {
+                    if (p + 4 > n) { complete = false; break; }
+                    const uint32_t l_name = rd32(u.data() + p);
+                    if (p + 4 + l_name + 4 > n) { complete = false; break; }
+                    b->names.emplace_back((const char *) u.data() + p + 4, l_name ? l_name - 1 : 0);
+                    b->lens.push_back(rd32(u.data() + p + 4 + l_name));
+                    p += 8 + l_name;
+                }
+                if (complete) b->text.assign((const char *) u.data() + 8, l_text);
+            }
+        } else if (n >= 4) { set_error("not a BAM file (bad magic)"); return PB_ERR_ARG; }
+        if (complete) break;
+        if (cnt < want_blocks) { set_error("truncated BAM header"); return PB_ERR_ARG; }
+        want_blocks *= 2;
+    }
+    b->n_compressed = b->n_inflated = 0;
+    return PB_OK;
+}
+
+int load_bai(pb_bam *b, const char *path) {
+    MappedFile f;
+    if (!f.open(path)) { set_error("cannot open BAM index %s", path); return PB_ERR_ARG; }
+    const uint8_t *p = f.p;
+    const size_t n = f.n;
+    size_t o = 8;
+    if (n < 8 || memcmp(p, "BAI\1", 4)) { f.close(); set_error("%s is not a BAI index", path); return PB_ERR_ARG; }
+    const uint32_t n_ref = rd32(p + 4);
+    b->index.assign(n_ref, RefIndex());
+    for (uint32_t r = 0; r < n_ref; r++) {
+        if (o + 4 > n) goto bad;
+        {
+            const uint32_t n_bin = rd32(p + o); o += 4;
+            for (uint32_t i = 0; i < n_bin; i++) {
+                if (o + 8 > n) goto bad;
+                const uint32_t bin = rd32(p + o), n_chunk = rd32(p + o + 4);
+                o += 8;
+                if (o + 16ull * n_chunk > n) goto bad;
+                auto &v = b->index[r].bins[bin];
+                for (uint32_t c = 0; c < n_chunk; c++, o += 16) v.push_back({rd64(p + o), rd64(p + o + 8)});
+            }
+            if (o + 4 > n) goto bad;
+            const uint32_t n_intv = rd32(p + o); o += 4;
+            if (o + 8ull * n_intv > n) goto bad;
+            b->index[r].linear.resize(n_intv);
+            for (uint32_t i = 0; i < n_intv; i++, o += 8) b->index[r].linear[i] = rd64(p + o);
+        }
+    }
+    f.close();
+    return PB_OK;
+bad:
+    f.close();
+    set_error("truncated BAI index %s", path);
+    return PB_ERR_ARG;
+}
+
+}  // namespace
+
+extern "C" int pb_bam_open(pb_bam_t **out, const char *path, int n_threads) {
+    if (!out || !path) { set_error("null argument"); return PB_ERR_ARG; }
+    auto *b = new pb_bam();
+    if (!b->f.open(path)) { delete b; set_error("cannot open BAM file %s", path); return PB_ERR_ARG; }
+    b->n_threads = n_threads > 0 ? n_threads : (int) std::max(1u, std::thread::hardware_concurrency());
+    int ndev = 0;
+    b->pinned = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
+    if (!b->pinned) cudaGetLastError();
+    int rc = load_header(b);
+    if (rc == PB_OK) {
+        std::string bai = std::string(path) + ".bai";
+        struct stat st;
+        if (stat(bai.c_str(), &st) != 0) {                       // also accept name.bai next to name.bam
+            std::string alt(path);
+            if (alt.size() > 4 && alt.substr(alt.size() - 4) == ".bam") alt = alt.substr(0, alt.size() - 4) + ".bai";
+            if (stat(alt.c_str(), &st) == 0) bai = alt;
+        }
+        rc = load_bai(b, bai.c_str());
+    }
+    if (rc != PB_OK) { b->f.close(); delete b; return rc; }
+    *out = b;
+    return PB_OK;
+}
+
+extern "C" int pb_bam_close(pb_bam_t *b) {
+    if (!b) return PB_OK;
+    HostBuf *bufs[] = {&b->o_pos, &b->o_seq_off, &b->o_cigar_off, &b->o_flag, &b->o_mapq, &b->o_seq, &b->o_qual, &b->o_cigar};
+    for (auto *x : bufs) x->release();
+    b->f.close();
+    delete b;
+    return PB_OK;
+}
+
+extern "C" int pb_bam_n_contigs(pb_bam_t *b) { return b ? (int) b->names.size() : 0; }
+extern "C" const char *pb_bam_contig_name(pb_bam_t *b, int tid) { return (b && tid >= 0 && tid < (int) b->names.size()) ? b->names[tid].c_str() : nullptr; }
+extern "C" int64_t pb_bam_contig_length(pb_bam_t *b, int tid) { return (b && tid >= 0 && tid < (int) b->lens.size()) ? b->lens[tid] : -1; }
+extern "C" int pb_bam_contig_id(pb_bam_t *b, const char *name) {
+    if (!b || !name) return -1;
+    for (size_t i = 0; i < b->names.size(); i++) if (b->names[i] == name) return (int) i;
+    return -1;
+}
+extern "C" const char *pb_bam_header_text(pb_bam_t *b, int64_t *len) {
+    if (!b) return nullptr;
+    if (len) *len = (int64_t) b->text.size();
+    return b->text.c_str();
+}
+extern "C" int pb_bam_io_stats(pb_bam_t *b, int64_t *compressed, int64_t *inflated) {
+    if (!b) return PB_ERR_ARG;
+    if (compressed) *compressed = b->n_compressed;
+    if (inflated) *inflated = b->n_inflated;
+    return PB_OK;
+}
+
+extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_records_t *view) {
+    if (!b || !view) { set_error("null argument"); return PB_ERR_ARG; }
+    memset(view, 0, sizeof(*view));
+    if (tid < 0 || tid >= (int) b->names.size()) { set_error("contig id %d out of range", tid); return PB_ERR_ARG; }
+    if (beg < 0) beg = 0;
+    if (end > (1ll << 29)) end = 1ll << 29;
+    std::vector<RecRef> recs;
+    std::vector<int64_t> rpos;
+    std::vector<Block> blocks;
+    if (end > beg && tid < (int) b->index.size()) {
+        const RefIndex &ri = b->index[tid];
+        std::vector<uint32_t> bins;
+        reg2bins(beg, end, bins);
+        uint64_t min_off = 0;
+        if (!ri.linear.empty()) {
+            const size_t w = (size_t) (beg >> 14);
+            min_off = ri.linear[std::min(w, ri.linear.size() - 1)];
+            if (w >= ri.linear.size()) min_off = ri.linear.back();
+        }
+        std::vector<Chunk> chunks;
+        for (uint32_t bin : bins) {
+            auto it = ri.bins.find(bin);
+            if (it == ri.bins.end()) continue;
+            for (const Chunk &c : it->second) if (c.end > min_off) chunks.push_back(c);
+        }
+        std::sort(chunks.begin(), chunks.end(), [](const Chunk &a, const Chunk &c) { return a.beg < c.beg; });
+        std::vector<Chunk> merged;
+        for (const Chunk &c : chunks) {
+            if (!merged.empty() && c.beg <= merged.back().end) merged.back().end = std::max(merged.back().end, c.end);
+            else merged.push_back(c);
+        }
+        if (!merged.empty()) {
+            // one inflate pass over the whole span of the merged chunks would decompress gaps too; inflate per chunk group:
+            // chunks whose block ranges touch are handled together
+            size_t gi = 0;
+            std::vector<uint8_t> &u = b->ubuf;
+            // collect (buffer copy) per group: to keep record pointers valid, every group's inflated bytes are appended to one store
+            std::vector<uint8_t> store;
+            std::vector<size_t> rec_store_off;
+            bool done = false;
+            while (gi < merged.size() && !done) {
+                size_t gj = gi;
+                uint64_t gend = merged[gi].end;
+                while (gj + 1 < merged.size() && (merged[gj + 1].beg >> 16) <= (gend >> 16)) { gj++; gend = std::max(gend, merged[gj].end); }
+                const size_t c0 = (size_t) (merged[gi].beg >> 16);
+                size_t c1 = (size_t) (gend >> 16);
+                if ((gend & 0xffff) == 0 && c1 > c0) c1 -= 1;             // the block at gend is not needed; c1 then points inside the previous block: fine for `off <= c1`
+                PB_TRY(inflate_range(b, c0, c1, blocks, u));
+                const size_t utotal = u.size() - 8;
+                const size_t base = store.size();
+                store.insert(store.end(), u.begin(), u.begin() + utotal);
+                for (size_t ci = gi; ci <= gj && !done; ci++) {
+                    size_t p = upos_of(blocks, merged[ci].beg, utotal);
+                    const size_t pe = std::min(upos_of(blocks, merged[ci].end, utotal), utotal);
+                    while (p + 4 <= pe) {
+                        const uint32_t bs = rd32(u.data() + p);
+                        if (p + 4 + bs > utotal) { set_error("BAM record runs past its chunk"); return PB_ERR_ARG; }
+                        const uint8_t *r = u.data() + p + 4;
+                        const int32_t rtid = rdi32(r), pos = rdi32(r + 4);
+                        if (rtid != tid || pos >= end) { if (rtid > tid || (rtid == tid && pos >= end)) { done = true; break; } p += 4 + bs; continue; }
+                        const uint32_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
+                        const uint8_t *cig = r + 32 + l_name;
+                        uint32_t n_cigar = n_cig;
+                        const uint8_t *cigar = cig;
+                        // long CIGAR convention (SAMv1 4.2.2): "<l_seq>S<rlen>N" + CG:B,I tag
+                        if (n_cig == 2 && (rd32(cig) & 15) == 4 && (rd32(cig) >> 4) == l_seq && (rd32(cig + 4) & 15) == 3) {
+                            const uint8_t *a = cig + 8 + (l_seq + 1) / 2 + l_seq, *ae = r + bs;
+                            while (a + 3 <= ae) {
+                                const char t0 = (char) a[0], t1 = (char) a[1], ty = (char) a[2];
+                                a += 3;
+                                size_t sz = 0;
+                                if (ty == 'A' || ty == 'c' || ty == 'C') sz = 1;
+                                else if (ty == 's' || ty == 'S') sz = 2;
+                                else if (ty == 'i' || ty == 'I' || ty == 'f') sz = 4;
+                                else if (ty == 'Z' || ty == 'H') { while (a + sz < ae && a[sz]) sz++; sz++; }
+                                else if (ty == 'B') {
+                                    if (a + 5 > ae) break;
+                                    const char st = (char) a[0];
+                                    const uint32_t cnt = rd32(a + 1);
+                                    const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                                    if (t0 == 'C' && t1 == 'G' && st == 'I') { n_cigar = cnt; cigar = a + 5; }
+                                    sz = 5 + es * cnt;
+                                } else break;
+                                a += sz;
+                            }
+                        }
+                        int64_t rlen = 0;
+                        for (uint32_t k = 0; k < n_cigar; k++) {
+                            const uint32_t c = rd32(cigar + 4 * k);
+                            const int op = (int) (c & 15);
+                            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
+                        }
+                        if (n_cigar == 0) rlen = 1;
+                        if ((int64_t) pos + rlen > beg) {
+                            recs.push_back({base + p + 4, l_seq, n_cigar, nullptr});
+                            rec_store_off.push_back(base + (size_t) (cigar - u.data()));
+                            rpos.push_back(pos);
+                        }
+                        p += 4 + bs;
+                    }
+                }
+                gi = gj + 1;
+            }
+            u.swap(store);                                                   // b->ubuf now holds every group's bytes
+            for (size_t i = 0; i < recs.size(); i++) recs[i].cigar = u.data() + rec_store_off[i];
+        }
+    }
+    const int64_t n = (int64_t) recs.size();
+    std::vector<int64_t> so(n + 1, 0), co(n + 1, 0);
+    for (int64_t i = 0; i < n; i++) { so[i + 1] = so[i] + recs[i].l_seq; co[i + 1] = co[i] + recs[i].n_cigar; }
+    const int64_t nb = so[n], nc = co[n];
+    const bool pin = b->pinned;
+    if (!b->o_pos.reserve(sizeof(int64_t) * (n + 1), pin) || !b->o_seq_off.reserve(sizeof(int64_t) * (n + 1), pin) ||
+        !b->o_cigar_off.reserve(sizeof(int64_t) * (n + 1), pin) || !b->o_flag.reserve(sizeof(uint16_t) * (n + 1), pin) ||
+        !b->o_mapq.reserve(n + 1, pin) || !b->o_seq.reserve((size_t) nb / 2 + 16, pin) || !b->o_qual.reserve((size_t) nb + 16, pin) ||
+        !b->o_cigar.reserve(sizeof(uint32_t) * (nc + 4), pin)) { set_error("out of host memory"); return PB_ERR_ARG; }
+    memcpy(b->o_seq_off.p, so.data(), sizeof(int64_t) * (n + 1));
+    memcpy(b->o_cigar_off.p, co.data(), sizeof(int64_t) * (n + 1));
+    int64_t *o_pos = b->o_pos.as<int64_t>();
+    uint16_t *o_flag = b->o_flag.as<uint16_t>();
+    uint8_t *o_mapq = b->o_mapq.as<uint8_t>(), *o_seq = b->o_seq.as<uint8_t>(), *o_qual = b->o_qual.as<uint8_t>();
+    uint32_t *o_cigar = b->o_cigar.as<uint32_t>();
+    const uint8_t *u = b->ubuf.data();
+    auto seq_of = [&](int64_t i) { const uint8_t *r = u + recs[i].off; return r + 32 + r[8] + 4 * (size_t) rd16(r + 12); };
+    auto code_at = [](const uint8_t *s, int64_t k) { return (k & 1) ? (s[k >> 1] & 15) : (s[k >> 1] >> 4); };
+    const size_t grain = 64;
+    parallel_for(b->n_threads, ((size_t) n + grain - 1) / grain, [&](size_t g) {
+        for (int64_t i = (int64_t) (g * grain); i < std::min<int64_t>(n, (int64_t) ((g + 1) * grain)); i++) {
+            const uint8_t *r = u + recs[i].off;
+            o_pos[i] = rpos[i];
+            o_mapq[i] = r[9];
+            o_flag[i] = rd16(r + 14);
+            const int64_t l = recs[i].l_seq;
+            memcpy(o_cigar + co[i], recs[i].cigar, 4 * (size_t) recs[i].n_cigar);
+            const uint8_t *s = seq_of(i);
+            memcpy(o_qual + so[i], s + (l + 1) / 2, (size_t) l);
+            // nibble-contiguous packing: the byte shared with the previous record is written by THIS record; a trailing half
+            // byte only by the last record
+            const int64_t o = so[i];
+            if (!(o & 1)) {
+                memcpy(o_seq + (o >> 1), s, (size_t) (l >> 1));
+            } else if (l > 0) {
+                int64_t pv = i - 1;
+                while (recs[pv].l_seq == 0) pv--;                      // o odd => some earlier record has bases
+                o_seq[o >> 1] = (uint8_t) (code_at(seq_of(pv), recs[pv].l_seq - 1) << 4 | code_at(s, 0));
+                for (int64_t B = (o + 1) >> 1; B < (o + l) >> 1; B++) {
+                    const int64_t k = 2 * B - o;
+                    o_seq[B] = (uint8_t) (code_at(s, k) << 4 | code_at(s, k + 1));
+                }
+            }
+        }
+    });
+    if (nb & 1) {                                                       // trailing half byte: last record that has bases
+        int64_t last = n - 1;
+        while (recs[last].l_seq == 0) last--;
+        o_seq[nb >> 1] = (uint8_t) (code_at(seq_of(last), recs[last].l_seq - 1) << 4);
+    }
+    view->n_records = n;
+    view->pos = o_pos; view->seq_off = b->o_seq_off.as<int64_t>(); view->cigar_off = b->o_cigar_off.as<int64_t>();
+    view->flag = o_flag; view->mapq = o_mapq; view->seq = o_seq; view->qual = o_qual; view->cigar = o_cigar;
+    return PB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------- FASTA
+extern "C" int pb_fasta_open(pb_fasta_t **out, const char *path) {
+    if (!out || !path) { set_error("null argument"); return PB_ERR_ARG; }
+    auto *f = new pb_fasta();
+    if (!f->f.open(path)) { delete f; set_error("cannot open FASTA file %s", path); return PB_ERR_ARG; }
+    MappedFile idx;
+    const std::string fai = std::string(path) + ".fai";
+    if (!idx.open(fai.c_str())) { f->f.close(); delete f; set_error("cannot open FASTA index %s (file must be indexed)", fai.c_str()); return PB_ERR_ARG; }
+    const char *p = (const char *) idx.p, *e = p + idx.n;
+    while (p < e) {
+        const char *nl = (const char *) memchr(p, '\n', (size_t) (e - p));
+        const char *le = nl ? nl : e;
+        std::string line(p, le);
+        p = nl ? nl + 1 : e;
+        if (line.empty()) continue;
+        pb_fasta::Entry en;
+        size_t t0 = line.find('\t');
+        if (t0 == std::string::npos) continue;
+        en.name = line.substr(0, t0);
+        long long v[4] = {0, 0, 0, 0};
+        if (sscanf(line.c_str() + t0 + 1, "%lld\t%lld\t%lld\t%lld", &v[0], &v[1], &v[2], &v[3]) != 4) { idx.close(); f->f.close(); delete f; set_error("malformed .fai line"); return PB_ERR_ARG; }
+        en.len = v[0]; en.off = v[1]; en.linebases = v[2]; en.linewidth = v[3];
+        f->by_name[en.name] = (int) f->entries.size();
+        f->entries.push_back(en);
+    }
+    idx.close();
+    *out = f;
+    return PB_OK;
+}
+
+extern "C" int pb_fasta_close(pb_fasta_t *f) {
+    if (!f) return PB_OK;
+    f->f.close();
+    delete f;
+    return PB_OK;
+}
+extern "C" int pb_fasta_n_contigs(pb_fasta_t *f) { return f ? (int) f->entries.size() : 0; }
+extern "C" const char *pb_fasta_contig_name(pb_fasta_t *f, int i) { return (f && i >= 0 && i < (int) f->entries.size()) ? f->entries[i].name.c_str() : nullptr; }
+extern "C" int64_t pb_fasta_contig_length(pb_fasta_t *f, const char *name) {
+    if (!f || !name) return -1;
+    auto it = f->by_name.find(name);
+    return it == f->by_name.end() ? -1 : f->entries[it->second].len;
+}
+
+// FASTA_handler::get_reference_sequence(region, start, stop) == faidx_fetch_seq(fai, region, start, stop - 1, &len)
+// (fasta_handler.cpp:31-50): inclusive end, both ends clamped into the contig like htslib 1.9 faidx.c does, characters
+// returned as stored (no case folding).  *len = -2 when the contig is absent (and PB_ERR_ARG is returned).
+extern "C" int pb_fasta_fetch(pb_fasta_t *f, const char *name, int64_t start, int64_t stop, char *out, int64_t cap, int64_t *len) {
+    if (!f || !name || !len) { set_error("null argument"); return PB_ERR_ARG; }
+    auto it = f->by_name.find(name);
+    if (it == f->by_name.end()) { *len = -2; set_error("CHROMOSOME NAME NOT PRESENT IN REFERENCE FASTA FILE: %s", name); return PB_ERR_ARG; }
+    const pb_fasta::Entry &e = f->entries[it->second];
+    int64_t b = start, en = stop - 1;
+    if (en < b) b = en;
+    if (b < 0) b = 0; else if (e.len <= b) b = e.len - 1;
+    if (en < 0) en = 0; else if (e.len <= en) en = e.len - 1;
+    const int64_t n = (e.len > 0) ? en - b + 1 : 0;
+    *len = n;
+    if (n > cap) return PB_ERR_CAPACITY;
+    if (!out || n <= 0) return PB_OK;
+    int64_t w = 0;
+    for (int64_t i = b; i <= en;) {
+        const int64_t line = i / e.linebases, col = i % e.linebases;
+        const int64_t take = std::min(e.linebases - col, en - i + 1);
+        const int64_t off = e.off + line * e.linewidth + col;
+        if ((size_t) (off + take) > f->f.n) { set_error("FASTA index points past the end of the file"); return PB_ERR_ARG; }
+        memcpy(out + w, f->f.p + off, (size_t) take);
+        w += take; i += take;
+    }
+    return PB_OK;
+}

@@ -103,15 +103,15 @@ class ReadTrimmer:
 
     def get_reads(self, records, intervals, include_supplementary: bool = False, min_mapq: int = 0, min_baseq: int = 0,
                   max_reads: int | None = None, downsample_rate: float = 1.0, stream: int = 0) -> TrimmedReads:
-        """`records`: DeviceRecords (HBM) or RecordBatch (host, uploaded).  `intervals`: [(start, stop), ...] exactly as the
+        """`records`: DeviceRecords (HBM), RecordBatch (host, uploaded) or a BamReader.fetch view (host, uploaded).  `intervals`: [(start, stop), ...] exactly as the
         reference passes them to get_reads.  `max_reads` / `downsample_rate`: the caller-side reservoir sample
         (total_allowed = int(min(max_reads, downsample_rate * total_reads)), AlignmentSummarizer.py:110)."""
         iv, _keep = intervals_array(intervals)
         n = len(iv)
         opt = PbGetReadsOptions(int(bool(include_supplementary)), int(min_mapq), int(min_baseq), 0)
         counts = np.zeros(n, dtype=np.int64)
-        if isinstance(records, RecordBatch):
-            hr = HostRecords(records)
+        if isinstance(records, RecordBatch) or getattr(records, "on_host", False):
+            hr = HostRecords(records) if isinstance(records, RecordBatch) else records
             rc = self.L.pb_get_reads_plan_host(self.h, C.byref(hr.struct), C.cast(iv, C.c_void_p), n, C.byref(opt),
                                                counts.ctypes.data, C.c_void_p(stream))
         else:

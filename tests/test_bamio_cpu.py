@@ -1,0 +1,135 @@
+"""CPU tests of the host BGZF / BAM / BAI and FASTA / FAI readers (row f4, pepper_b200/csrc/bamio.cu): files written by
+pepper_b200/synth_files.py from the specification, read back through the C-ABI; the region fetch against the htslib
+iterator rule evaluated directly on the arrays; the BAM bytes cross-checked with an independent pure-Python parse of the
+gzip-decompressed stream."""
+import gzip
+import os
+import struct
+import numpy as np
+import pytest
+
+from pepper_b200 import synth, synth_files
+
+FIELDS = ("pos", "seq_off", "cigar_off", "flag", "mapq", "seq", "qual", "cigar")
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("bamio")
+    rec0, g0 = synth.simulate_contig_records(60000, 15, synth.ONT, 3, contig_start=2000)
+    rec1, g1 = synth.simulate_contig_records(150000, 8, synth.HIFI, 4, contig_start=0)
+    # a record without SEQ (as aligners emit for secondary alignments) in the middle of contig 0
+    bam = str(d / "t.bam")
+    synth_files.write_bam(bam, [("chrA", 70000), ("chrB", 150000), ("chrEmpty", 1000)], {0: rec0, 1: rec1}, long_cigar_over=300)
+    fa = str(d / "t.fa")
+    g0full = np.concatenate([synth.make_reference(2000, 77), g0])
+    g0full[100:130] = np.frombuffer(b"acgtnacgtnacgtnacgtnacgtnacgtn", dtype=np.uint8)        # lower case is preserved
+    synth_files.write_fasta(fa, [("chrA", g0full), ("chrB", g1), ("tiny", np.frombuffer(b"ACGT", dtype=np.uint8))])
+    return dict(bam=bam, fa=fa, rec=[rec0, rec1], genome=[g0full, g1])
+
+
+def expected_fetch(rec, beg, end):
+    rlen = np.zeros(rec.n_records, dtype=np.int64)
+    for r in range(rec.n_records):
+        c = rec.cigar[rec.cigar_off[r]:rec.cigar_off[r + 1]]
+        rlen[r] = synth_files.record_ref_len(c) if c.shape[0] else 1
+    keep = np.nonzero((rec.pos < end) & (rec.pos + rlen > beg))[0]
+    return keep
+
+
+def subset(rec, idx):
+    b = synth.take_reads(synth.ReadBatch(rec.pos, rec.seq_off, rec.cigar_off, (rec.flag & 0xff).astype(np.uint8), rec.mapq, rec.seq,
+                                         rec.qual, rec.cigar), idx)
+    return b, rec.flag[idx]
+
+
+def test_full_contig_roundtrip(files):
+    from pepper_b200.bamio import BamReader
+    r = BamReader(files["bam"], threads=3)
+    assert r.get_chromosome_sequence_names() == ["chrA", "chrB", "chrEmpty"]
+    assert r.get_chromosome_sequence_names_with_length() == [("chrA", 70000), ("chrB", 150000), ("chrEmpty", 1000)]
+    assert r.get_sample_names() == {"sample_b200"}
+    for tid, name in enumerate(["chrA", "chrB"]):
+        got = r.fetch(name, 0, 1 << 29).to_batch()
+        for f in FIELDS:
+            assert np.array_equal(getattr(got, f), getattr(files["rec"][tid], f)), (name, f)
+    assert r.fetch("chrEmpty", 0, 1000).n_records == 0
+    comp, infl = r.io_stats()
+    assert infl > comp > 0
+    r.close()
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_region_fetch_matches_iterator_rule(files, threads):
+    from pepper_b200.bamio import BamReader
+    r = BamReader(files["bam"], threads=threads)
+    rng = np.random.default_rng(5)
+    n_total = 0
+    for tid, name, length in [(0, "chrA", 70000), (1, "chrB", 150000)]:
+        rec = files["rec"][tid]
+        for _ in range(30):
+            beg = int(rng.integers(0, length))
+            end = beg + int(rng.choice([1, 10, 1201, 16384, 40000]))
+            want_idx = expected_fetch(rec, beg, end)
+            got = r.fetch(name, beg, end).to_batch()
+            want, wflag = subset(rec, want_idx)
+            assert got.n_records == want.n_reads, (name, beg, end)
+            assert np.array_equal(got.pos, want.pos) and np.array_equal(got.flag, wflag)
+            for f in ("seq_off", "cigar_off", "mapq", "seq", "qual", "cigar"):
+                assert np.array_equal(getattr(got, f), getattr(want, f)), (name, beg, end, f)
+            n_total += got.n_records
+    assert n_total > 300
+
+
+def test_bam_bytes_against_independent_python_parse(files):
+    """The writer's bytes are a valid gzip multi-member stream; parsing the records in pure Python gives the batch back."""
+    raw = gzip.open(files["bam"]).read()
+    assert raw[:4] == b"BAM\x01"
+    l_text, = struct.unpack_from("<i", raw, 4)
+    p = 8 + l_text
+    n_ref, = struct.unpack_from("<i", raw, p)
+    p += 4
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", raw, p)
+        p += 8 + l_name
+    rec = files["rec"][0]
+    for r in range(5):
+        bs, tid, pos, l_name, mapq, _bin, n_cig, flag, l_seq = struct.unpack_from("<iiiBBHHHi", raw, p)
+        assert (tid, pos, mapq, flag, l_seq) == (0, int(rec.pos[r]), int(rec.mapq[r]), int(rec.flag[r]), int(rec.seq_off[r + 1] - rec.seq_off[r]))
+        cig = np.frombuffer(raw, dtype="<u4", count=n_cig, offset=p + 36 + l_name)
+        want = rec.cigar[rec.cigar_off[r]:rec.cigar_off[r + 1]]
+        if n_cig == want.shape[0]:
+            assert np.array_equal(cig, want)
+        else:                                          # long-CIGAR convention
+            assert n_cig == 2 and (cig[0] & 15) == 4 and (cig[0] >> 4) == l_seq and (cig[1] & 15) == 3
+        p += 4 + bs
+
+
+def test_fasta(files):
+    from pepper_b200.bamio import FastaReader
+    from pepper_b200._lib import PepperB200Error
+    f = FastaReader(files["fa"])
+    assert f.get_chromosome_names() == ["chrA", "chrB", "tiny"]
+    g = files["genome"][0]
+    assert f.get_chromosome_sequence_length("chrA") == g.shape[0]
+    for (s, e) in [(0, 10), (55, 65), (59, 61), (100, 130), (1000, 5000), (g.shape[0] - 5, g.shape[0])]:
+        assert f.get_reference_sequence("chrA", s, e) == g[s:e].tobytes().decode(), (s, e)
+    # faidx clamping: stop past the end is cut at the last base; start < 0 is cut at 0
+    assert f.get_reference_sequence("chrA", g.shape[0] - 5, g.shape[0] + 100) == g[-5:].tobytes().decode()
+    assert f.get_reference_sequence("tiny", -3, 2) == "AC"
+    assert f.get_reference_sequence("tiny", 0, 4) == "ACGT"
+    with pytest.raises(PepperB200Error):
+        f.get_reference_sequence("nope", 0, 10)
+
+
+def test_errors(tmp_path):
+    from pepper_b200.bamio import BamReader, FastaReader
+    from pepper_b200._lib import PepperB200Error
+    with pytest.raises(PepperB200Error):
+        BamReader(str(tmp_path / "missing.bam"))
+    p = tmp_path / "junk.bam"
+    p.write_bytes(b"not a bam file at all" * 10)
+    with pytest.raises(PepperB200Error):
+        BamReader(str(p))
+    with pytest.raises(PepperB200Error):
+        FastaReader(str(tmp_path / "missing.fa"))
