@@ -150,6 +150,36 @@ int pb_get_reads_plan_host(pb_read_trimmer_t *t, const pb_records_t *h_records,
                            const pb_get_reads_options_t *opt, int64_t *h_reads_per_interval, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Read -> reference realignment.  Replaces
+ *   ReadAligner(ref_start, ref_end, ref_seq).align_reads_to_reference(reads)
+ * (pepper/modules/src/local_reassembly/simple_aligner.cpp:66-106 on top of the
+ * vendored SSW library ssw.c / ssw_cpp.cpp; pybind_api.h ReadAligner) for every
+ * region of a batch: region i is [ref_start, ...] with its reference string
+ * ref[ref_off : ref_off + ref_len] (= get_reference_sequence(chrom,
+ * region_start, region_end + ALIGNMENT_SAFE_BASES), AlignmentSummarizer.py:
+ * 164-170) and its reads [read_begin, read_end).  Each read is aligned against
+ * the reference suffix that starts at its own position; with sw_score > 1 it
+ * takes the SSW CIGAR ('=' / 'X' -> M tuples, S, I, D) and
+ * pos = pos + ref_begin, otherwise it is returned unchanged.  Sequences and
+ * qualities are never modified: the output pb_reads_t aliases the input's
+ * seq_off / flags / mapq / seq / qual and owns new pos / cigar_off / cigar
+ * (valid until the realigner's next call).  The reference implementation drops
+ * reads that start before the region start; here that is PB_ERR_ARG (fetch the
+ * reads with get_reads(start = region start), as the reference's caller does).
+ * ---------------------------------------------------------------------- */
+typedef struct pb_realigner pb_realigner_t;
+int pb_realigner_create(pb_realigner_t **out, int device);
+int pb_realigner_destroy(pb_realigner_t *t);
+int pb_realign_device(pb_realigner_t *t, const pb_reads_t *d_reads,
+                      const pb_region_t *d_regions, const pb_region_t *h_regions, int64_t n_regions,
+                      const char *d_ref, int64_t ref_bytes, pb_reads_t *d_out, void *stream);
+/* host buffers in, new pos [n] / cigar_off [n+1] / cigar out; PB_ERR_CAPACITY (with *n_cigar set) if cigar_capacity is short */
+int pb_realign_host(pb_realigner_t *t, const pb_reads_t *h_reads, const pb_region_t *h_regions, int64_t n_regions,
+                    const char *h_ref, int64_t ref_bytes, int64_t *h_pos, int64_t *h_cigar_off, uint32_t *h_cigar,
+                    int64_t cigar_capacity, int64_t *n_cigar, void *stream);
+int pb_realign_stats(pb_realigner_t *t, int64_t *n_aligned, int64_t *n_realigned, float *ms_sw, float *ms_cigar);
+
+/* ------------------------------------------------------------------------
  * File readers under BAM_handler / FASTA_handler.  Host code
  * written from the SAM/BAM/BAI and faidx specifications (the reference gets
  * these from htslib 1.9: sam_open / sam_index_load / sam_hdr_read /

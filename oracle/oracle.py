@@ -34,12 +34,13 @@ _libs: dict[str, C.CDLL] = {}
 
 
 def lib(kind: str) -> C.CDLL:
-    """kind in {'port', 'ref_variant', 'ref_polish', 'ref_getreads'}"""
+    """kind in {'port', 'ref_variant', 'ref_polish', 'ref_getreads', 'ref_realign'}"""
     if kind not in _libs:
         path = {"port": os.path.join(HERE, "liboracle_port.so"),
                 "ref_variant": os.path.join(HERE, "_ref", "libref_variant.so"),
                 "ref_polish": os.path.join(HERE, "_ref", "libref_polish.so"),
-                "ref_getreads": os.path.join(HERE, "_ref", "libref_getreads.so")}[kind]
+                "ref_getreads": os.path.join(HERE, "_ref", "libref_getreads.so"),
+                "ref_realign": os.path.join(HERE, "_ref", "libref_realign.so")}[kind]
         L = _load(path)
         if kind in ("port", "ref_variant"):
             pre = "port" if kind == "port" else "ref"
@@ -60,6 +61,18 @@ def lib(kind: str) -> C.CDLL:
         if kind == "port":
             L.port_get_reads.restype = C.c_int64
             L.port_get_reads.argtypes = [C.POINTER(PbRecords), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11
+        if kind == "port":
+            L.port_ssw_align.restype = C.c_int
+            L.port_ssw_align.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+            L.port_realign.restype = C.c_int64
+            L.port_realign.argtypes = [C.POINTER(PbReads), C.c_int64, C.c_int64, C.c_int64, C.c_char_p, C.c_int64] + [C.c_void_p] * 6
+        if kind == "ref_realign":
+            L.ref_realign_run.restype = None
+            L.ref_realign_run.argtypes = [C.POINTER(PbReads), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p]
+            L.ref_realign_fetch.restype = None
+            L.ref_realign_fetch.argtypes = [C.c_void_p] * 5
+            L.ref_ssw_align.restype = None
+            L.ref_ssw_align.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_char_p, C.c_int32]
         if kind == "ref_getreads":
             L.ref_getreads_load.restype = None
             L.ref_getreads_load.argtypes = [C.POINTER(PbRecords)]
@@ -198,3 +211,52 @@ def images_to_int8(images_i32: np.ndarray) -> np.ndarray:
     """DataStore.write_summary stores int8 (pepper_variant DataStore.py:68): values wrap mod 256."""
     return images_i32.astype(np.int64).astype(np.uint8).view(np.int8) if images_i32.size else \
         np.zeros(images_i32.shape, dtype=np.int8)
+
+
+def have_ref_realign() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_realign.so"))
+
+
+_OPCH = "MIDNSHP=X"
+
+
+def ssw_align(query: str, ref: str, impl: str = "port"):
+    """LibSSWPairwiseAligner.set_reference(ref); .align(query) (simple_aligner.cpp:12-29).
+    Returns (score, ref_begin, ref_end, query_begin, query_end, mismatches, cigar_string)."""
+    out = np.zeros(6, dtype=np.int32)
+    if impl == "port":
+        cap = 2 * len(query) + len(ref) + 16
+        cig = np.zeros(cap, dtype=np.uint32)
+        n = lib("port").port_ssw_align(query.encode(), len(query), ref.encode(), len(ref), out.ctypes.data, cig.ctypes.data, cap)
+        s = "".join(f"{int(c >> 4)}{_OPCH[int(c & 15)]}" for c in cig[:n])
+        return tuple(int(x) for x in out) + (s,)
+    buf = C.create_string_buffer(4 * (len(query) + len(ref)) + 64)
+    lib("ref_realign").ref_ssw_align(query.encode(), ref.encode(), len(ref), out.ctypes.data, buf, len(buf))
+    return tuple(int(x) for x in out) + (buf.value.decode(),)
+
+
+def realign(reads: ReadBatch, rb: int, re_: int, region_start: int, region_end: int, ref_seq: str, impl: str = "port"):
+    """ReadAligner(region_start, region_end, ref_seq).align_reads_to_reference(reads[rb:re]).
+    Returns (pos, pos_end, cigar_off, cigar uint32) of the output reads (sequence / qualities are unchanged)."""
+    hr = HostReads(reads)
+    if impl == "port":
+        n_in = re_ - rb
+        nb = int(reads.seq_off[re_] - reads.seq_off[rb])
+        cap = 2 * nb + (len(ref_seq) + 16) * n_in + int(reads.cigar_off[-1]) + 64
+        pos, pos_end, kept = (np.zeros(n_in + 1, dtype=np.int64) for _ in range(3))
+        cigar_off = np.zeros(n_in + 2, dtype=np.int64)
+        cigar = np.zeros(cap, dtype=np.uint32)
+        score = np.zeros(n_in + 1, dtype=np.int32)
+        n = lib("port").port_realign(C.byref(hr.struct), rb, re_, region_start, ref_seq.encode(), len(ref_seq), pos.ctypes.data,
+                                     pos_end.ctypes.data, cigar_off.ctypes.data, cigar.ctypes.data, kept.ctypes.data, score.ctypes.data)
+        n = int(n)
+        return pos[:n].copy(), pos_end[:n].copy(), cigar_off[:n + 1].copy(), cigar[:int(cigar_off[n])].copy()
+    L = lib("ref_realign")
+    sizes = np.zeros(2, dtype=np.int64)
+    L.ref_realign_run(C.byref(hr.struct), rb, re_, region_start, region_end, ref_seq.encode(), len(ref_seq), sizes.ctypes.data)
+    n, nc = int(sizes[0]), int(sizes[1])
+    pos, pos_end = np.zeros(n + 1, dtype=np.int64), np.zeros(n + 1, dtype=np.int64)
+    cigar_off = np.zeros(n + 1, dtype=np.int64)
+    op, ln = np.zeros(nc + 1, dtype=np.int32), np.zeros(nc + 1, dtype=np.int32)
+    L.ref_realign_fetch(pos.ctypes.data, pos_end.ctypes.data, cigar_off.ctypes.data, op.ctypes.data, ln.ctypes.data)
+    return pos[:n].copy(), pos_end[:n].copy(), cigar_off.copy(), ((ln[:nc].astype(np.uint32) << 4) | op[:nc].astype(np.uint32))

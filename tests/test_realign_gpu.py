@@ -1,0 +1,90 @@
+"""GPU parity for row f1: the realignment kernels (pepper_b200/csrc/realign.cu, through the C-ABI) against the plain-C
+restatement of ReadAligner::align_reads_to_reference / SSW (oracle/port_realign.c), bit-exact positions and CIGARs."""
+import numpy as np
+import pytest
+
+from pepper_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_realign(oracle, reads, regions):
+    pos, cig, off = [], [], [0]
+    for r in range(regions.n_regions):
+        row = regions.table[r]
+        ref = regions.ref[int(row[4]):int(row[4] + row[5])].tobytes().decode()
+        p, pe, co, c = oracle.realign(reads, int(row[6]), int(row[7]), int(row[0]), int(row[1]) + 20, ref, impl="port")
+        assert p.shape[0] == int(row[7] - row[6])          # nothing dropped: reads start inside their region
+        pos.append(p)
+        cig.append(c)
+        off.extend((co[1:] + off[-1]).tolist())
+        off[-1] = off[-1]
+    return np.concatenate(pos), np.array(off, dtype=np.int64), np.concatenate(cig)
+
+
+def workload(n_regions, coverage, platform, seed):
+    from pepper_b200.realign import realign_regions
+    reads, regions = synth.make_polish_workload(n_regions, coverage, platform, seed=seed)
+    genome = synth.make_reference(n_regions * 1000 + 1, seed)
+    return reads, realign_regions(regions, genome)
+
+
+@pytest.mark.parametrize("platform,seed", [(synth.ONT, 5), (synth.HIFI, 6)])
+def test_realign_matches_oracle(oracle_built, platform, seed):
+    from pepper_b200.realign import Realigner
+    reads, regions = workload(4, 25, platform, seed)
+    want_pos, want_off, want_cig = oracle_realign(oracle_built, reads, regions)
+    ra = Realigner(0)
+    got = ra.realign(reads, regions)
+    st = ra.stats()
+    assert st["realigned"] > 0.9 * reads.n_reads
+    assert np.array_equal(got.pos, want_pos)
+    assert np.array_equal(got.cigar_off, want_off)
+    assert np.array_equal(got.cigar, want_cig)
+    assert not np.array_equal(got.cigar_off, reads.cigar_off)          # the CIGARs really changed
+    ra.close()
+
+
+def test_realign_edge_reads(oracle_built):
+    """Short reads (byte mode, score < 255), reads the aligner rejects (score <= 1), N bases, long indels, band growth."""
+    from pepper_b200.realign import Realigner
+    rng = np.random.default_rng(3)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 1400))
+    recs = []
+
+    def add(pos, seq):
+        recs.append(dict(pos=pos, seq=seq, cigar=[(0, len(seq))]))
+    add(0, ref[0:40])                                            # byte mode
+    add(10, ref[10:72])                                          # 62 matches: 248 < 249 stays byte
+    add(20, ref[20:83])                                          # 63 matches: 252 -> word
+    add(30, "N" * 30)                                            # score 0 -> unchanged
+    add(40, ref[40:300] + ref[340:700])                          # 40-base deletion -> band doubling
+    add(50, ref[50:400] + "ACGTTGCA" * 6 + ref[400:800])         # 48-base insertion
+    add(60, ref[60:500].replace("A", "N", 5))                    # N in the read
+    add(70, "T" + ref[75:90])                                    # tiny
+    add(80, ref[700:900])                                        # placed far from its true origin: soft clips / begin shift
+    add(1300, ref[1300:1400] + "ACGTACGTACGTACGTACGTAAAA")       # runs past the reference end
+    add(1399, "G")                                               # one base against a one-base reference
+    recs.sort(key=lambda r: r["pos"])
+    reads = synth.make_batch(recs)
+    tab = np.array([[0, 1380, 0, 1380, 0, 1400, 0, reads.n_reads]], dtype=np.int64)
+    regions = synth.RegionTable(tab, np.frombuffer(ref.encode(), dtype=np.uint8))
+    want_pos, want_off, want_cig = oracle_realign(oracle_built, reads, regions)
+    ra = Realigner(0)
+    got = ra.realign(reads, regions)
+    assert np.array_equal(got.pos, want_pos)
+    assert np.array_equal(got.cigar_off, want_off)
+    assert np.array_equal(got.cigar, want_cig)
+    ra.close()
+
+
+def test_realign_rejects_reads_before_region():
+    from pepper_b200.realign import Realigner
+    from pepper_b200._lib import PepperB200Error
+    reads = synth.make_batch([dict(pos=5, seq="ACGTACGT", cigar=[(0, 8)])])
+    tab = np.array([[10, 100, 10, 100, 0, 50, 0, 1]], dtype=np.int64)
+    regions = synth.RegionTable(tab, np.frombuffer(b"ACGT" * 13, dtype=np.uint8)[:50].copy())
+    ra = Realigner(0)
+    with pytest.raises(PepperB200Error):
+        ra.realign(reads, regions)
+    ra.close()
