@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include <vector>
 #include <algorithm>
+#include <stdlib.h>
 
 using namespace pb;
 
@@ -208,6 +209,171 @@ __global__ void __launch_bounds__(128) k_sw(const Task *__restrict__ tasks, cons
         if (b.score > 1 && b.ref >= 0) {                       // results with score <= 1 are never used (simple_aligner.cpp:84)
             const SwBest rb = word ? sw_pass<R>(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 8, false, b.score, lane)
                                    : sw_pass<R>(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 16, true, b.score, lane);
+            res.ref_begin = rb.ref; res.read_begin = b.read - rb.read;
+            res.status = 1;
+        }
+    }
+    if (lane == 0) out[a] = res;
+}
+
+// ---------------------------------------------------------------------------------------------- packed s16x2 pass
+// Same recurrences, two rows per 32-bit register (VIADDMNMX.S16x2 / VIMNMX.S16x2 are native on sm_100a).
+// Row mapping: stripe segment s (length S) is split over G = 32 / lanesL consecutive GPU lanes (Rl = ceil(S / G) rows each), so
+// a stripe boundary is always a lane boundary and the restricted F chain differs from the unrestricted one only in the
+// cross-lane scan.  Inside a lane the rows are split in a low half (first ceil(cnt/2) rows, low 16 bits) and a high half
+// (the rest, high 16 bits): two independent sub-blocks that advance in the same instruction.  Pads sit at the end of each
+// half (mask registers keep them out of the maxima; -30000 keeps them out of the chain transfer).
+constexpr int NP = RMAX / 2;                               // row pairs per lane
+constexpr int SW16_SMEM_WARP = (5 * NP + NP) * 32 * 4;     // profile [5][NP][32] + best-column snapshot [NP][32]
+
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t) hi << 16) | ((uint32_t) lo & 0xffffu); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int) (int16_t) (v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int) (int16_t) (v >> 16); }
+
+__device__ __noinline__ SwBest sw_pass16(const int8_t *__restrict__ codes, int64_t qbase, int qstep, int readLen, const int8_t *__restrict__ ref,
+                                         int refLen, int ref_dir, int lanesL, bool byte_mode, int terminate, int lane, uint32_t *smem) {
+    uint32_t *prof = smem;                                  // [rc][pair][lane]
+    uint32_t *snap = smem + 5 * NP * 32;                    // [pair][lane]
+    const int G = 32 / lanesL;
+    const int S = (readLen + lanesL - 1) / lanesL;
+    const int Rl = (S + G - 1) / G;
+    const int seg = lane / G, sub = lane % G;
+    const int start = seg * S + sub * Rl;
+    const int endx = min(seg * S + min((sub + 1) * Rl, S), readLen);
+    const int cnt = max(0, endx - start);
+    const int cl = (cnt + 1) >> 1, ch = cnt - cl;
+    const bool seg_start = sub == 0;
+    constexpr int PADNEG = -30000;
+    uint32_t H2[NP], E2[NP], M2[NP];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < NP; r++) {
+        H2[r] = 0; E2[r] = 0;
+        M2[r] = (r < cl ? 0x0000ffffu : 0u) | (r < ch ? 0xffff0000u : 0u);
+        const int ql = r < cl ? codes[qbase + (int64_t) qstep * (start + r)] : 9;
+        const int qh = r < ch ? codes[qbase + (int64_t) qstep * (start + cl + r)] : 9;
+#pragma unroll
+        for (int rc = 0; rc < 5; rc++) {
+            const int sl = ql == 9 ? PADNEG : ((ql == rc && rc < 4) ? MATCH : -MISM);
+            const int sh = qh == 9 ? PADNEG : ((qh == rc && rc < 4) ? MATCH : -MISM);
+            prof[(rc * NP + r) * 32 + lane] = pack2(sl, sh);
+        }
+    }
+    __syncwarp();
+    const unsigned nonempty = __ballot_sync(FULL, cnt > 0);
+    const unsigned below = nonempty & ((1u << lane) - 1u);
+    const int src_lane = below ? 31 - __clz(below) : -1;
+    const uint32_t NGO2 = pack2(-GO, -GO), NGE2 = pack2(-GE, -GE), PAD2 = pack2(PADNEG, PADNEG);
+    const int npad_l = NP - cl, npad_h = NP - ch;
+    int hlast = 0, hmid = 0;                                 // H of the lane's last row / of the low half's last row (previous column)
+    int gbest = 0, gcol = 0;
+    bool overflow = false, have = false;
+    for (int c = 0; c < refLen; c++) {
+        const int i = ref_dir ? refLen - 1 - c : c;
+        const int rc = ref[i];
+        int up = __shfl_sync(FULL, hlast, src_lane < 0 ? 0 : src_lane);
+        if (src_lane < 0) up = 0;
+        const uint32_t up2 = pack2(up, hmid);
+        const uint32_t *pr = prof + rc * NP * 32 + lane;
+        // pass 1 (descending): H <- max(diag + s, E, 0)
+#pragma unroll
+        for (int r = NP - 1; r >= 0; r--) H2[r] = __viaddmax_s16x2_relu(r == 0 ? up2 : H2[r - 1], pr[r * 32], E2[r]);
+        // transfer of each half: chain value after its last valid row (pads only decay: compensated below)
+        uint32_t a2 = 0;
+#pragma unroll
+        for (int r = 0; r < NP; r++) {
+            uint32_t open2 = __viaddmax_s16x2_relu(H2[r], NGO2, 0u);
+            open2 = (open2 & M2[r]) | (PAD2 & ~M2[r]);
+            a2 = __viaddmax_s16x2(a2, NGE2, open2);
+        }
+        const int a_l = cl > 0 ? lo16(a2) + GE * npad_l : NEG;     // cl == 0: empty lane
+        const int a_h = ch > 0 ? hi16(a2) + GE * npad_h : NEG;
+        const int d_l = -GE * cl, d_h = -GE * ch;
+        // lane composite, then exclusive (d, A) scans over the lanes: unrestricted chain and stripe-restricted chain
+        int A = max(a_l + d_h, a_h), D = d_l + d_h;
+        if (cnt == 0) { A = NEG; D = 0; }
+        int af = A, df = D, al = A, dl = seg_start ? NEG : D;
+        if (cnt == 0) dl = seg_start ? NEG : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int uaf = __shfl_up_sync(FULL, af, d), udf = __shfl_up_sync(FULL, df, d);
+            const int ual = __shfl_up_sync(FULL, al, d), udl = __shfl_up_sync(FULL, dl, d);
+            if (lane >= d) {
+                af = max(af, max(uaf + df, NEG)); df = max(NEG, udf + df);
+                al = max(al, max(ual + dl, NEG)); dl = max(NEG, udl + dl);
+            }
+        }
+        int fin_full = __shfl_up_sync(FULL, af, 1), fin_loc = __shfl_up_sync(FULL, al, 1);
+        if (lane == 0) { fin_full = 0; fin_loc = 0; }
+        fin_full = max(fin_full, 0);
+        fin_loc = seg_start ? 0 : max(fin_loc, 0);
+        uint32_t ffull2 = pack2(fin_full, max(max(fin_full + d_l, a_l), 0));
+        uint32_t floc2 = pack2(fin_loc, max(max(fin_loc + d_l, a_l), 0));
+        // pass 2 (ascending)
+        uint32_t cm2 = 0;
+#pragma unroll
+        for (int r = 0; r < NP; r++) {
+            const uint32_t hm2 = __vmaxs2(H2[r], floc2);
+            const uint32_t open2 = __viaddmax_s16x2_relu(hm2, NGO2, 0u);
+            E2[r] = __viaddmax_s16x2(E2[r], NGE2, open2);
+            floc2 = __viaddmax_s16x2(floc2, NGE2, open2);
+            const uint32_t hf2 = __vmaxs2(hm2, ffull2);
+            ffull2 = __viaddmax_s16x2(ffull2, NGE2, open2);
+            H2[r] = hf2;
+            cm2 = __vmaxs2(cm2, hf2 & M2[r]);
+        }
+        // last rows of the halves (diag sources of the next column)
+        uint32_t hl2 = 0, hp2 = 0;
+        switch (cl) {
+#define PB_CASE(k) case k + 1: hl2 = H2[k]; hp2 = H2[k > 0 ? k - 1 : 0]; break;
+            PB_CASE(0) PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8) PB_CASE(9) PB_CASE(10)
+            PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15) PB_CASE(16) PB_CASE(17) PB_CASE(18) PB_CASE(19) PB_CASE(20)
+#undef PB_CASE
+            default: break;
+        }
+        hmid = lo16(hl2);
+        hlast = ch == 0 ? hmid : (ch == cl ? hi16(hl2) : hi16(hp2));
+        const int colmax = __reduce_max_sync(FULL, max(lo16(cm2), hi16(cm2)));
+        if (colmax > gbest) {
+            gbest = colmax; gcol = c; have = true;
+            if (byte_mode && colmax + BIAS >= 255) { overflow = true; break; }
+#pragma unroll
+            for (int r = 0; r < NP; r++) snap[r * 32 + lane] = H2[r];
+        }
+        if (colmax == terminate) break;
+    }
+    SwBest b;
+    if (overflow) { b.score = 255; b.ref = 0; b.read = 0; return b; }
+    if (!have) { b.score = 0; b.ref = byte_mode ? -1 : 0; b.read = readLen - 1; return b; }
+    __syncwarp();
+    int row = 0x7fffffff;
+    for (int r = cl - 1; r >= 0; r--) if (lo16(snap[r * 32 + lane]) == gbest) row = start + r;
+    if (row == 0x7fffffff) for (int r = ch - 1; r >= 0; r--) if (hi16(snap[r * 32 + lane]) == gbest) row = start + cl + r;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) row = min(row, __shfl_xor_sync(FULL, row, d));
+    b.score = gbest; b.ref = ref_dir ? refLen - 1 - gcol : gcol; b.read = row;
+    return b;
+}
+
+__global__ void __launch_bounds__(128) k_sw16(const Task *__restrict__ tasks, const int32_t *__restrict__ order, int64_t n, const int8_t *__restrict__ codes,
+                                              const int8_t *__restrict__ rcodes, Aln *__restrict__ out) {
+    extern __shared__ uint32_t sw_smem[];
+    const int64_t w = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    uint32_t *smem = sw_smem + (threadIdx.x >> 5) * (SW16_SMEM_WARP / 4);
+    const int64_t a = order[w];
+    const Task t = tasks[a];
+    Aln res = {0, -1, 0, -1, 0, 0};
+    if (t.q_len > 0 && t.r_len > 0) {
+        const int8_t *ref = rcodes + t.r_off;
+        bool word = false;
+        SwBest b = sw_pass16(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 16, true, 255, lane, smem);
+        if (b.score == 255) { b = sw_pass16(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 8, false, 65535, lane, smem); word = true; }
+        res.score = b.score; res.ref_end = b.ref; res.read_end = b.read;
+        if (b.score > 1 && b.ref >= 0) {
+            const SwBest rb = word ? sw_pass16(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 8, false, b.score, lane, smem)
+                                   : sw_pass16(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 16, true, b.score, lane, smem);
             res.ref_begin = rb.ref; res.read_begin = b.read - rb.read;
             res.status = 1;
         }
@@ -504,8 +670,17 @@ extern "C" int pb_realign_device(pb_realigner_t *t, const pb_reads_t *dr, const 
     PB_TRY(upload(t->order, order.data(), sizeof(int32_t) * n, st));
     if (n_big) k_sw<RBIG><<<(unsigned) ceil_div(n_big * 32, 128), 128, 0, st>>>(t->tasks.as<Task>(), t->order.as<int32_t>(), n_big, t->codes.as<int8_t>(),
                                                                                t->rcodes.as<int8_t>(), t->alns.as<Aln>());
-    if (n - n_big) k_sw<RMAX><<<(unsigned) ceil_div((n - n_big) * 32, 128), 128, 0, st>>>(t->tasks.as<Task>(), t->order.as<int32_t>() + n_big, n - n_big,
-                                                                                         t->codes.as<int8_t>(), t->rcodes.as<int8_t>(), t->alns.as<Aln>());
+    if (n - n_big) {
+        static const bool force_i32 = getenv("PB_REALIGN_I32") && atoi(getenv("PB_REALIGN_I32")) != 0;     // debug: int32 kernel for every read
+        if (force_i32) {
+            k_sw<RMAX><<<(unsigned) ceil_div((n - n_big) * 32, 128), 128, 0, st>>>(t->tasks.as<Task>(), t->order.as<int32_t>() + n_big, n - n_big,
+                                                                                  t->codes.as<int8_t>(), t->rcodes.as<int8_t>(), t->alns.as<Aln>());
+        } else {
+            PB_CUDA(cudaFuncSetAttribute(k_sw16, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SW16_SMEM_WARP));
+            k_sw16<<<(unsigned) ceil_div((n - n_big) * 32, 128), 128, 4 * SW16_SMEM_WARP, st>>>(t->tasks.as<Task>(), t->order.as<int32_t>() + n_big, n - n_big,
+                                                                                                t->codes.as<int8_t>(), t->rcodes.as<int8_t>(), t->alns.as<Aln>());
+        }
+    }
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaEventRecord(t->evt[1], st));
     int32_t h_err = 0;

@@ -88,3 +88,21 @@ def test_realign_rejects_reads_before_region():
     with pytest.raises(PepperB200Error):
         ra.realign(reads, regions)
     ra.close()
+
+
+def test_realign_long_reads_fallback_kernel(oracle_built):
+    """Reads longer than 1344 bases take the int32 local-memory kernel."""
+    from pepper_b200.realign import Realigner
+    rng = np.random.default_rng(8)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 3300))
+    q1 = ref[100:1500] + "ACGTAC" + ref[1500:2900]
+    q2 = ref[0:700] + ref[720:2200]
+    reads = synth.make_batch([dict(pos=0, seq=q2, cigar=[(0, len(q2))]), dict(pos=100, seq=q1, cigar=[(0, len(q1))]),
+                              dict(pos=200, seq=ref[200:900], cigar=[(0, 700)])])
+    tab = np.array([[0, 3280, 0, 3280, 0, 3300, 0, 3]], dtype=np.int64)
+    regions = synth.RegionTable(tab, np.frombuffer(ref.encode(), dtype=np.uint8))
+    want_pos, want_off, want_cig = oracle_realign(oracle_built, reads, regions)
+    ra = Realigner(0)
+    got = ra.realign(reads, regions)
+    assert np.array_equal(got.pos, want_pos) and np.array_equal(got.cigar_off, want_off) and np.array_equal(got.cigar, want_cig)
+    ra.close()
