@@ -223,13 +223,14 @@ __global__ void __launch_bounds__(128) k_sw(const Task *__restrict__ tasks, cons
 // cross-lane scan.  Inside a lane the rows are split in a low half (first ceil(cnt/2) rows, low 16 bits) and a high half
 // (the rest, high 16 bits): two independent sub-blocks that advance in the same instruction.  Pads sit at the end of each
 // half (mask registers keep them out of the maxima; -30000 keeps them out of the chain transfer).
-constexpr int NP = RMAX / 2;                               // row pairs per lane
-constexpr int SW16_SMEM_WARP = (5 * NP + NP) * 32 * 4;     // profile [5][NP][32] + best-column snapshot [NP][32]
+constexpr int NPMAX = RMAX / 2;                            // row pairs per lane (largest instantiation)
+constexpr int SW16_SMEM_WARP = (5 * NPMAX + NPMAX) * 32 * 4;   // profile [5][NP][32] + best-column snapshot [NP][32]
 
 __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t) hi << 16) | ((uint32_t) lo & 0xffffu); }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int) (int16_t) (v & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int) (int16_t) (v >> 16); }
 
+template <int NP>
 __device__ __noinline__ SwBest sw_pass16(const int8_t *__restrict__ codes, int64_t qbase, int qstep, int readLen, const int8_t *__restrict__ ref,
                                          int refLen, int ref_dir, int lanesL, bool byte_mode, int terminate, int lane, uint32_t *smem) {
     uint32_t *prof = smem;                                  // [rc][pair][lane]
@@ -325,7 +326,7 @@ __device__ __noinline__ SwBest sw_pass16(const int8_t *__restrict__ codes, int64
         // last rows of the halves (diag sources of the next column)
         uint32_t hl2 = 0, hp2 = 0;
         switch (cl) {
-#define PB_CASE(k) case k + 1: hl2 = H2[k]; hp2 = H2[k > 0 ? k - 1 : 0]; break;
+#define PB_CASE(k) case k + 1: if (k < NP) { hl2 = H2[k < NP ? k : 0]; hp2 = H2[(k > 0 && k < NP) ? k - 1 : 0]; } break;
             PB_CASE(0) PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8) PB_CASE(9) PB_CASE(10)
             PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15) PB_CASE(16) PB_CASE(17) PB_CASE(18) PB_CASE(19) PB_CASE(20)
 #undef PB_CASE
@@ -355,6 +356,7 @@ __device__ __noinline__ SwBest sw_pass16(const int8_t *__restrict__ codes, int64
     return b;
 }
 
+template <int NP>
 __global__ void __launch_bounds__(128) k_sw16(const Task *__restrict__ tasks, const int32_t *__restrict__ order, int64_t n, const int8_t *__restrict__ codes,
                                               const int8_t *__restrict__ rcodes, Aln *__restrict__ out) {
     extern __shared__ uint32_t sw_smem[];
@@ -368,12 +370,12 @@ __global__ void __launch_bounds__(128) k_sw16(const Task *__restrict__ tasks, co
     if (t.q_len > 0 && t.r_len > 0) {
         const int8_t *ref = rcodes + t.r_off;
         bool word = false;
-        SwBest b = sw_pass16(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 16, true, 255, lane, smem);
-        if (b.score == 255) { b = sw_pass16(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 8, false, 65535, lane, smem); word = true; }
+        SwBest b = sw_pass16<NP>(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 16, true, 255, lane, smem);
+        if (b.score == 255) { b = sw_pass16<NP>(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 8, false, 65535, lane, smem); word = true; }
         res.score = b.score; res.ref_end = b.ref; res.read_end = b.read;
         if (b.score > 1 && b.ref >= 0) {
-            const SwBest rb = word ? sw_pass16(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 8, false, b.score, lane, smem)
-                                   : sw_pass16(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 16, true, b.score, lane, smem);
+            const SwBest rb = word ? sw_pass16<NP>(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 8, false, b.score, lane, smem)
+                                   : sw_pass16<NP>(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 16, true, b.score, lane, smem);
             res.ref_begin = rb.ref; res.read_begin = b.read - rb.read;
             res.status = 1;
         }
@@ -384,17 +386,27 @@ __global__ void __launch_bounds__(128) k_sw16(const Task *__restrict__ tasks, co
 // ---------------------------------------------------------------------------------------------- banded_sw + cigar
 __device__ __forceinline__ int score_of(int a, int b) { return (a == b && a < 4) ? MATCH : -MISM; }
 
-// one warp per alignment; scratch slot: 3 int32 band arrays of band_words, path_words cigar words, then direction bytes
+// one warp per alignment; scratch slot: 3 int32 band arrays of band_words, path_words cigar words, then direction bytes.
+// Small bands and short sequences live in shared memory (band arrays, base codes); the trace-back stages 32 rows x 96
+// direction bytes at a time in shared memory so that the sequential walk of lane 0 never waits on HBM / L2.
+constexpr int BW_SH = 128;                                  // largest band width whose arrays stay in shared memory
+constexpr int BAND_SH = 2 * BW_SH + 8;
+constexpr int CODE_SH = 2816;                               // read + reference codes staged per warp
+constexpr int WIN_W = 96, WIN_H = 32;
+struct BandShared { int32_t band[3 * BAND_SH]; int8_t code[CODE_SH]; uint8_t win[WIN_H * WIN_W]; };
+
 __global__ void __launch_bounds__(128) k_banded(const Task *__restrict__ tasks, const int32_t *__restrict__ list, int64_t n, const int8_t *__restrict__ codes,
                                                 const int8_t *__restrict__ rcodes, Aln *__restrict__ alns, uint8_t *__restrict__ scratch,
                                                 int64_t slot_bytes, int band_words, int path_words, uint32_t *__restrict__ pool, unsigned long long pool_cap,
                                                 unsigned long long *__restrict__ pool_used, int64_t *__restrict__ cig_off, int32_t *__restrict__ cig_len) {
+    __shared__ BandShared sh_all[4];
+    BandShared &sh = sh_all[threadIdx.x >> 5];
     const int64_t w = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
     uint8_t *slot = scratch + w * slot_bytes;
-    int32_t *bufA = reinterpret_cast<int32_t *>(slot), *bufB = bufA + band_words, *e_b = bufB + band_words;
-    uint32_t *path = reinterpret_cast<uint32_t *>(e_b + band_words);
+    int32_t *gband = reinterpret_cast<int32_t *>(slot);
+    uint32_t *path = reinterpret_cast<uint32_t *>(gband + 3 * (size_t) band_words);
     uint8_t *dir = slot + sizeof(int32_t) * (3 * (size_t) band_words + path_words);
     const int64_t dir_bytes = slot_bytes - (int64_t) sizeof(int32_t) * (3 * (int64_t) band_words + path_words);
     for (int64_t it = w; it < n; it += n_warps) {
@@ -402,10 +414,17 @@ __global__ void __launch_bounds__(128) k_banded(const Task *__restrict__ tasks, 
         Aln al = alns[a];
         if (al.status != 1 && al.status != 3) continue;
         const Task t = tasks[a];
-        const int8_t *ref = rcodes + t.r_off + al.ref_begin;
-        const int8_t *read = codes + t.q_off + al.read_begin;
         const int refLen = al.ref_end - al.ref_begin + 1, readLen = al.read_end - al.read_begin + 1;
         if (refLen <= 0 || readLen <= 0) { if (lane == 0) { alns[a].status = -1; } continue; }
+        const int8_t *ref = rcodes + t.r_off + al.ref_begin;
+        const int8_t *read = codes + t.q_off + al.read_begin;
+        __syncwarp();
+        if (refLen + readLen <= CODE_SH) {                       // stage the two sequences
+            for (int k = lane; k < readLen; k += 32) sh.code[k] = read[k];
+            for (int k = lane; k < refLen; k += 32) sh.code[readLen + k] = ref[k];
+            read = sh.code; ref = sh.code + readLen;
+        }
+        __syncwarp();
         int bw = abs(refLen - readLen) + 1;
         int maxv = 0, width_d = 0;
         bool fits = true;
@@ -413,7 +432,8 @@ __global__ void __launch_bounds__(128) k_banded(const Task *__restrict__ tasks, 
             const int width = bw * 2 + 3;
             width_d = bw * 2 + 1;
             if (width + 2 > band_words || (int64_t) width_d * readLen > dir_bytes) { fits = false; break; }
-            int32_t *prev = bufA, *cur = bufB;
+            const bool in_sh = width + 2 <= BAND_SH;
+            int32_t *prev = in_sh ? sh.band : gband, *cur = prev + (in_sh ? BAND_SH : band_words), *e_b = cur + (in_sh ? BAND_SH : band_words);
             for (int k = lane; k < width + 2; k += 32) { prev[k] = 0; cur[k] = 0; e_b[k] = 0; }
             __syncwarp();
             int lmax = 0;
@@ -479,31 +499,55 @@ __global__ void __launch_bounds__(128) k_banded(const Task *__restrict__ tasks, 
         }
         if (!fits) { if (lane == 0) alns[a].status = 3; continue; }
         __syncwarp();
-        if (lane == 0) {
-            // trace back from the bottom-right corner (ssw.c:665-733); path ops are collected in reverse into the band arrays
-            const int path_cap = path_words;
-            int i = readLen - 1, j = refLen - 1, e = 0, l = 0, state = 2, status = 2;
-            int op = 0, prev_op = 0;                                 // 0 M, 1 I, 2 D
-            while (i > 0) {
-                const int x = max(0, i - bw), col = j - x;
-                if (col < 0 || col >= width_d) { status = -2; break; }
-                const int b = dir[(size_t) width_d * i + col];
-                const int code = state == 2 ? (b >> 2) : state == 0 ? ((b & 1) ? 3 : 2) : ((b & 2) ? 5 : 4);
-                if (code == 1) { i--; j--; state = 2; op = 0; }
-                else if (code == 2) { i--; state = 0; op = 1; }
-                else if (code == 3) { i--; state = 2; op = 1; }
-                else if (code == 4) { j--; state = 1; op = 2; }
-                else if (code == 5) { j--; state = 2; op = 2; }
-                else { status = -2; break; }
-                if (op == prev_op) e++;
-                else {
-                    if (l >= path_cap) { status = -3; break; }
-                    path[l++] = (uint32_t) e << 4 | (uint32_t) prev_op;
-                    prev_op = op; e = 1;
+        __threadfence_block();
+        // trace back from the bottom-right corner (ssw.c:665-733): 32 rows x 96 band columns are staged at a time
+        int i = readLen - 1, j = refLen - 1, status = 2;
+        int e = 0, l = 0, state = 2, op = 0, prev_op = 0;        // lane 0 only: 0 M, 1 I, 2 D
+        while (i > 0 && status == 2) {
+            const int x_top = max(0, i - bw);
+            const int c0 = (j - x_top) - WIN_W / 2;              // window start in band coordinates (same for the staged rows)
+            for (int rr = 0; rr < WIN_H; rr++) {
+                const int row = i - rr;
+                if (row < 1) break;
+                const uint8_t *src = dir + (size_t) width_d * row;
+#pragma unroll
+                for (int k = 0; k < WIN_W; k += 32) {
+                    const int cc = c0 + k + lane;
+                    sh.win[rr * WIN_W + k + lane] = (cc >= 0 && cc < width_d) ? src[cc] : (uint8_t) 0;
                 }
             }
+            __syncwarp();
+            if (lane == 0) {
+                const int i_top = i;
+                while (i > 0) {
+                    const int rr = i_top - i;
+                    if (rr >= WIN_H) break;
+                    const int col = j - max(0, i - bw);
+                    if (col < 0 || col >= width_d) { status = -2; break; }
+                    const int wc = col - c0;
+                    if (wc < 0 || wc >= WIN_W) break;            // drifted out of the staged window: restage
+                    const int b = sh.win[rr * WIN_W + wc];
+                    const int code = state == 2 ? (b >> 2) : state == 0 ? ((b & 1) ? 3 : 2) : ((b & 2) ? 5 : 4);
+                    if (code == 1) { i--; j--; state = 2; op = 0; }
+                    else if (code == 2) { i--; state = 0; op = 1; }
+                    else if (code == 3) { i--; state = 2; op = 1; }
+                    else if (code == 4) { j--; state = 1; op = 2; }
+                    else if (code == 5) { j--; state = 2; op = 2; }
+                    else { status = -2; break; }
+                    if (op == prev_op) e++;
+                    else {
+                        if (l >= path_words) { status = -3; break; }
+                        path[l++] = (uint32_t) e << 4 | (uint32_t) prev_op;
+                        prev_op = op; e = 1;
+                    }
+                }
+            }
+            i = __shfl_sync(FULL, i, 0); j = __shfl_sync(FULL, j, 0); status = __shfl_sync(FULL, status, 0);
+            __syncwarp();
+        }
+        if (lane == 0) {
             if (status == 2) {
-                if (l + 2 > path_cap) status = -3;
+                if (l + 2 > path_words) status = -3;
                 else if (op == 0) path[l++] = (uint32_t) (e + 1) << 4;
                 else { path[l++] = (uint32_t) e << 4 | (uint32_t) op; path[l++] = 1u << 4; }
             }
@@ -676,9 +720,31 @@ extern "C" int pb_realign_device(pb_realigner_t *t, const pb_reads_t *dr, const 
             k_sw<RMAX><<<(unsigned) ceil_div((n - n_big) * 32, 128), 128, 0, st>>>(t->tasks.as<Task>(), t->order.as<int32_t>() + n_big, n - n_big,
                                                                                   t->codes.as<int8_t>(), t->rcodes.as<int8_t>(), t->alns.as<Aln>());
         } else {
-            PB_CUDA(cudaFuncSetAttribute(k_sw16, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SW16_SMEM_WARP));
-            k_sw16<<<(unsigned) ceil_div((n - n_big) * 32, 128), 128, 4 * SW16_SMEM_WARP, st>>>(t->tasks.as<Task>(), t->order.as<int32_t>() + n_big, n - n_big,
-                                                                                                t->codes.as<int8_t>(), t->rcodes.as<int8_t>(), t->alns.as<Aln>());
+            // length-sorted order: launch each length class with the smallest register footprint that holds it
+            const int64_t lim[4] = {32 * 2 * 21, 32 * 2 * 16, 32 * 2 * 12, 32 * 2 * 8};
+            int64_t lo = n_big;
+            for (int cls = 0; cls < 4; cls++) {
+                int64_t hi = lo;
+                const int64_t next_lim = cls < 3 ? lim[cls + 1] : -1;
+                while (hi < n && so[order[hi] + 1] - so[order[hi]] > next_lim) hi++;
+                const int64_t m = hi - lo;
+                if (m > 0) {
+                    const unsigned grid = (unsigned) ceil_div(m * 32, 128);
+                    const int32_t *ord = t->order.as<int32_t>() + lo;
+#define PB_LAUNCH_SW16(NPT)                                                                                                          \
+    do {                                                                                                                             \
+        PB_CUDA(cudaFuncSetAttribute(k_sw16<NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SW16_SMEM_WARP));                 \
+        k_sw16<NPT><<<grid, 128, 4 * SW16_SMEM_WARP, st>>>(t->tasks.as<Task>(), ord, m, t->codes.as<int8_t>(), t->rcodes.as<int8_t>(), \
+                                                           t->alns.as<Aln>());                                                       \
+    } while (0)
+                    if (cls == 0) PB_LAUNCH_SW16(21);
+                    else if (cls == 1) PB_LAUNCH_SW16(16);
+                    else if (cls == 2) PB_LAUNCH_SW16(12);
+                    else PB_LAUNCH_SW16(8);
+#undef PB_LAUNCH_SW16
+                }
+                lo = hi;
+            }
         }
     }
     PB_CUDA(cudaGetLastError());
@@ -693,7 +759,7 @@ extern "C" int pb_realign_device(pb_realigner_t *t, const pb_reads_t *dr, const 
     PB_TRY(t->pool.reserve(sizeof(uint32_t) * (size_t) pool_cap));
     PB_CUDA(cudaMemsetAsync(t->pool_used.p, 0, 16, st));
     int band_bw = 128;
-    int64_t warps = (int64_t) t->sms * 8;
+    int64_t warps = (int64_t) t->sms * 24;
     for (int attempt = 0; attempt < 6; attempt++) {
         const int band_words = 2 * band_bw + 8;
         const int path_words = (int) (max_len + max_ref + 16);
