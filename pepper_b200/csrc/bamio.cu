@@ -20,6 +20,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <chrono>
 
 using namespace pb;
 
@@ -144,7 +145,19 @@ struct pb_bam {
     std::vector<RefIndex> index;
     size_t first_record_voff_block = 0;
     // fetch scratch / outputs
-    std::vector<uint8_t> ubuf;
+    struct RawBuf {                     // grow-only, never zero-filled; contents preserved up to `keep` bytes on growth
+        uint8_t *p = nullptr; size_t cap = 0;
+        bool ensure(size_t bytes, size_t keep) {
+            if (bytes <= cap) return true;
+            const size_t want = bytes + bytes / 4 + 4096;
+            uint8_t *q = (uint8_t *) malloc(want);
+            if (!q) return false;
+            if (p && keep) memcpy(q, p, keep);
+            free(p); p = q; cap = want;
+            return true;
+        }
+        ~RawBuf() { free(p); }
+    } ubuf;
     HostBuf o_pos, o_seq_off, o_cigar_off, o_flag, o_mapq, o_seq, o_qual, o_cigar;
     int64_t n_compressed = 0, n_inflated = 0;
 };
@@ -159,7 +172,7 @@ struct pb_fasta {
 namespace {
 
 // inflate the blocks covering compressed offsets [c0, c1_block] (c1_block = offset of the LAST block needed)
-int inflate_range(pb_bam *b, size_t c0, size_t c1_block, std::vector<Block> &blocks, std::vector<uint8_t> &out) {
+int inflate_range(pb_bam *b, size_t c0, size_t c1_block, std::vector<Block> &blocks, size_t base, size_t *utotal_out) {
     blocks.clear();
     size_t off = c0, utotal = 0;
     while (off <= c1_block && off < b->f.n) {
@@ -171,11 +184,13 @@ int inflate_range(pb_bam *b, size_t c0, size_t c1_block, std::vector<Block> &blo
         utotal += isize;
         off += bs;
     }
-    out.resize(utotal + 8);
+    if (!b->ubuf.ensure(base + utotal + 16, base)) { set_error("out of host memory"); return PB_ERR_ARG; }
+    uint8_t *out = b->ubuf.p + base;
+    *utotal_out = utotal;
     std::atomic<int> bad(0);
     parallel_for(b->n_threads, blocks.size(), [&](size_t i) {
         const Block &k = blocks[i];
-        if (k.isize && !inflate_block(b->f.p + k.coff + k.data_off, k.bsize - k.data_off - 8, out.data() + k.uoff, k.isize)) bad = 1;
+        if (k.isize && !inflate_block(b->f.p + k.coff + k.data_off, k.bsize - k.data_off - 8, out + k.uoff, k.isize)) bad = 1;
     });
     if (bad) { set_error("BGZF inflate failed"); return PB_ERR_ARG; }
     for (auto &k : blocks) { b->n_compressed += (int64_t) k.bsize; b->n_inflated += k.isize; }
@@ -192,14 +207,14 @@ size_t upos_of(const std::vector<Block> &blocks, uint64_t voff, size_t utotal) {
 int load_header(pb_bam *b) {
     // the header sits at the start of the file; inflate blocks until it is complete
     std::vector<Block> blocks;
-    std::vector<uint8_t> u;
     size_t want_blocks = 1;
     for (;;) {
         size_t off = 0, last = 0, cnt = 0;
         while (off < b->f.n && cnt < want_blocks) { size_t d; const size_t bs = bgzf_block_size(b->f.p, b->f.n, off, &d); if (!bs) break; last = off; off += bs; cnt++; }
         if (!cnt) { set_error("not a BGZF file"); return PB_ERR_ARG; }
-        PB_TRY(inflate_range(b, 0, last, blocks, u));
-        const size_t n = u.size() - 8;
+        size_t n = 0;
+        PB_TRY(inflate_range(b, 0, last, blocks, 0, &n));
+        struct { uint8_t *p; uint8_t *data() const { return p; } } u{b->ubuf.p};
         bool complete = false;
         if (n >= 12 && !memcmp(u.data(), "BAM\1", 4)) {
             const size_t l_text = rd32(u.data() + 4);
@@ -325,6 +340,11 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
     if (tid < 0 || tid >= (int) b->names.size()) { set_error("contig id %d out of range", tid); return PB_ERR_ARG; }
     if (beg < 0) beg = 0;
     if (end > (1ll << 29)) end = 1ll << 29;
+    static const bool dbg = getenv("PB_BAM_DEBUG") != nullptr;
+    auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = tnow();
+    double t_inflate = 0, t_walk = 0;
+    int n_groups = 0;
     std::vector<RecRef> recs;
     std::vector<int64_t> rpos;
     std::vector<Block> blocks;
@@ -354,9 +374,8 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
             // one inflate pass over the whole span of the merged chunks would decompress gaps too; inflate per chunk group:
             // chunks whose block ranges touch are handled together
             size_t gi = 0;
-            std::vector<uint8_t> &u = b->ubuf;
-            // collect (buffer copy) per group: to keep record pointers valid, every group's inflated bytes are appended to one store
-            std::vector<uint8_t> store;
+            // every group's inflated bytes are appended to b->ubuf; records are remembered as offsets (the buffer may move when it grows)
+            size_t store_size = 0;
             std::vector<size_t> rec_store_off;
             bool done = false;
             while (gi < merged.size() && !done) {
@@ -366,10 +385,14 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
                 const size_t c0 = (size_t) (merged[gi].beg >> 16);
                 size_t c1 = (size_t) (gend >> 16);
                 if ((gend & 0xffff) == 0 && c1 > c0) c1 -= 1;             // the block at gend is not needed; c1 then points inside the previous block: fine for `off <= c1`
-                PB_TRY(inflate_range(b, c0, c1, blocks, u));
-                const size_t utotal = u.size() - 8;
-                const size_t base = store.size();
-                store.insert(store.end(), u.begin(), u.begin() + utotal);
+                const double t_a = tnow();
+                const size_t base = store_size;
+                size_t utotal = 0;
+                PB_TRY(inflate_range(b, c0, c1, blocks, base, &utotal));
+                const double t_b = tnow();
+                t_inflate += t_b - t_a; n_groups++;
+                store_size = base + utotal;
+                struct { uint8_t *p; uint8_t *data() const { return p; } } u{b->ubuf.p + base};
                 for (size_t ci = gi; ci <= gj && !done; ci++) {
                     size_t p = upos_of(blocks, merged[ci].beg, utotal);
                     const size_t pe = std::min(upos_of(blocks, merged[ci].end, utotal), utotal);
@@ -420,10 +443,10 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
                         p += 4 + bs;
                     }
                 }
+                t_walk += tnow() - t_b;
                 gi = gj + 1;
             }
-            u.swap(store);                                                   // b->ubuf now holds every group's bytes
-            for (size_t i = 0; i < recs.size(); i++) recs[i].cigar = u.data() + rec_store_off[i];
+            for (size_t i = 0; i < recs.size(); i++) recs[i].cigar = b->ubuf.p + rec_store_off[i];
         }
     }
     const int64_t n = (int64_t) recs.size();
@@ -441,7 +464,7 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
     uint16_t *o_flag = b->o_flag.as<uint16_t>();
     uint8_t *o_mapq = b->o_mapq.as<uint8_t>(), *o_seq = b->o_seq.as<uint8_t>(), *o_qual = b->o_qual.as<uint8_t>();
     uint32_t *o_cigar = b->o_cigar.as<uint32_t>();
-    const uint8_t *u = b->ubuf.data();
+    const uint8_t *u = b->ubuf.p;
     auto seq_of = [&](int64_t i) { const uint8_t *r = u + recs[i].off; return r + 32 + r[8] + 4 * (size_t) rd16(r + 12); };
     auto code_at = [](const uint8_t *s, int64_t k) { return (k & 1) ? (s[k >> 1] & 15) : (s[k >> 1] >> 4); };
     const size_t grain = 64;
@@ -476,6 +499,8 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
         while (recs[last].l_seq == 0) last--;
         o_seq[nb >> 1] = (uint8_t) (code_at(seq_of(last), recs[last].l_seq - 1) << 4);
     }
+    if (dbg) fprintf(stderr, "pb_bam_fetch: %d groups, inflate %.1f ms, walk+copy %.1f ms, total %.1f ms, %lld records\n", n_groups, t_inflate, t_walk,
+                     tnow() - t_start, (long long) n);
     view->n_records = n;
     view->pos = o_pos; view->seq_off = b->o_seq_off.as<int64_t>(); view->cigar_off = b->o_cigar_off.as<int64_t>();
     view->flag = o_flag; view->mapq = o_mapq; view->seq = o_seq; view->qual = o_qual; view->cigar = o_cigar;

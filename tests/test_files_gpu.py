@@ -63,3 +63,68 @@ def test_files_to_candidates_like_alignment_summarizer(oracle_built, files):
     assert len(cands) == len(o["keys"]) > 5
     assert [c.position for c in cands] == o["positions"].tolist()
     assert [c.candidates[0] for c in cands] == o["keys"]
+
+
+def test_polish_chain_file_to_consensus(oracle_built, files):
+    """BAM file -> fetch -> get_reads -> realign -> polish encoder -> GRU -> bases, all on the device, against the same
+    caller fed with the ORACLE's get_reads + realign output (and the oracle polish encoder on those reads)."""
+    import torch
+    from pepper_b200 import weights
+    from pepper_b200.bamio import BamReader
+    from pepper_b200.reads import ReadTrimmer
+    from pepper_b200.realign import Realigner, realign_regions
+    from pepper_b200.pipeline import PolishCaller, DeviceReads, FetchedReads
+    from pepper_b200.polish import PolishEncoder
+    genome = files["genome"]
+    iv, rows = [], []
+    for p in range(4000, 9000, 1000):
+        rs, re_ = p - 100, p + 1100
+        iv.append((rs, re_))
+        rows.append([rs, re_, p, p + 1000, 0, 0, 0, 0])
+    regions = realign_regions(synth.RegionTable(np.array(rows, dtype=np.int64), np.zeros(1, np.uint8)), genome)
+    view = BamReader(files["bam"]).fetch("ctg", iv[0][0], iv[-1][1])
+    tr, ra = ReadTrimmer(0), Realigner(0)
+    got = tr.get_reads(view, iv, False, 0, 0)
+    fetched = FetchedReads(got, regions)
+    fetched.struct = ra.realign_device(fetched)
+    # oracle chain
+    batches, counts = [], []
+    for (s, e) in iv:
+        b, _, _ = oracle_built.get_reads(files["rec"], s, e, False, 0, 0, impl="port")
+        batches.append(b)
+        counts.append(b.n_reads)
+    reads = synth.concat_batches(batches)
+    tab = regions.table.copy()
+    tab[:, 7] = np.cumsum(counts)
+    tab[:, 6] = tab[:, 7] - counts
+    oregions = synth.RegionTable(tab, regions.ref)
+    pos, off, cig = [], [0], []
+    for r in range(len(iv)):
+        row = tab[r]
+        ref = regions.ref[int(row[4]):int(row[4] + row[5])].tobytes().decode()
+        p_, _, co, c = oracle_built.realign(reads, int(row[6]), int(row[7]), int(row[0]), int(row[1]) + 20, ref, impl="port")
+        pos.append(p_)
+        cig.append(c)
+        off.extend((co[1:] + off[-1]).tolist())
+    realigned = synth.ReadBatch(np.concatenate(pos), reads.seq_off, np.array(off, dtype=np.int64), reads.flags, reads.mapq, reads.seq,
+                                reads.qual, np.concatenate(cig))
+    # encoder parity on the realigned reads (host API vs oracle encoder)
+    enc = PolishEncoder(0)
+    s_gpu = enc.encode(realigned, oregions)
+    s_or = oracle_built.polish_encode(realigned, oregions, "port")
+    assert np.array_equal(s_gpu.image, s_or["image"]) and np.array_equal(s_gpu.pos, s_or["pos"])
+    # whole chain on the device == caller fed with the oracle's reads
+    pc = PolishCaller(weights.random_polish_state(0))
+    dev = torch.device("cuda", 0)
+
+    def outs(cap):
+        return dict(bases=torch.empty((cap, 1000), dtype=torch.uint8, device=dev), phred=torch.empty((cap, 1000), dtype=torch.uint8, device=dev),
+                    position=torch.empty((cap, 1000), dtype=torch.int64, device=dev), index=torch.empty((cap, 1000), dtype=torch.int32, device=dev),
+                    image_region=torch.empty(cap, dtype=torch.int32, device=dev), chunk_id=torch.empty(cap, dtype=torch.int32, device=dev))
+    a, b = outs(64), outs(64)
+    na = pc.call_device(fetched, a)
+    nb = pc.call_device(DeviceReads(realigned, oregions), b)
+    assert na == nb and na >= len(iv)
+    for k in a:
+        assert torch.equal(a[k][:na], b[k][:nb]), k
+    pc.close()
