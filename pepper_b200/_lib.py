@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpepper_b200.so")
+LIB_PATH = os.environ.get("PB_LIB_PATH") or os.path.join(HERE, "libpepper_b200.so")      # PB_LIB_PATH: A/B builds
 
 
 class PepperB200Error(RuntimeError):
