@@ -169,3 +169,36 @@ def test_chain_records_to_variant_calls(oracle_built, trimmer):
     assert np.array_equal(a["positions"][:na].cpu().numpy(), o["positions"])
     assert np.array_equal(a["images"][:na].cpu().numpy(), oracle_built.images_to_int8(o["images"]))
     vc.close()
+
+
+def test_properties_large_batch(trimmer):
+    """Size-independent properties at a size the oracle is not run at: every read starts on a match inside its query, CIGAR and
+    sequence lengths agree, the batch is idempotent (trimming the trimmed reads again with the same queries changes nothing)."""
+    from pepper_b200.reads import DeviceRecords
+    start = 0
+    rec, _ = synth.simulate_contig_records(300_000, 30, synth.ONT, 21, contig_start=start)
+    iv = [(max(0, p - 100), p + 1100) for p in range(0, 300_000, 1000)]
+    got = trimmer.get_reads(DeviceRecords(rec), iv, False, 0, 0)
+    b = got.to_host()
+    assert b.n_reads == int(got.total_reads.sum()) > 5000
+    ops, lens = b.cigar & 15, (b.cigar >> 4).astype(np.int64)
+    first = ops[b.cigar_off[:-1]]
+    assert np.isin(first, [0, 7, 8]).all()
+    read_cons = np.where(np.isin(ops, [0, 1, 4, 7, 8]), lens, 0)
+    ref_cons = np.where(np.isin(ops, [0, 2, 3, 7, 8]), lens, 0)
+    csum = np.concatenate([[0], np.cumsum(read_cons)])
+    rsum = np.concatenate([[0], np.cumsum(ref_cons)])
+    assert np.array_equal(csum[b.cigar_off[1:]] - csum[b.cigar_off[:-1]], np.diff(b.seq_off))
+    span = rsum[b.cigar_off[1:]] - rsum[b.cigar_off[:-1]]
+    qi = np.repeat(np.arange(len(iv)), got.read_end - got.read_begin)
+    starts, stops = np.array([s for s, _ in iv]), np.array([e for _, e in iv])
+    assert (b.pos >= starts[qi]).all() and (b.pos + span <= stops[qi] + 1).all()
+    assert (lens > 0).all() and not np.isin(ops, [5, 6]).any()
+    # idempotence, query by query on a sample
+    for q in (0, 57, 150, 299):
+        lo, hi = int(got.read_begin[q]), int(got.read_end[q])
+        sub = synth.take_reads(b, np.arange(lo, hi))
+        sub = synth.take_reads(sub, np.argsort(sub.pos, kind="stable"))      # trimmed starts need not be sorted
+        as_rec = synth.RecordBatch(sub.pos, sub.seq_off, sub.cigar_off, (sub.flags.astype(np.uint16) & 1) * 16, sub.mapq, sub.seq, sub.qual, sub.cigar)
+        again = trimmer.get_reads(as_rec, [iv[q]], False, 0, 0).to_host()
+        same(again, sub, q)

@@ -106,3 +106,28 @@ def test_realign_long_reads_fallback_kernel(oracle_built):
     got = ra.realign(reads, regions)
     assert np.array_equal(got.pos, want_pos) and np.array_equal(got.cigar_off, want_off) and np.array_equal(got.cigar, want_cig)
     ra.close()
+
+
+def test_realign_properties_large_batch():
+    """Properties at a size the oracle is not run at: sequences untouched, CIGAR read-consumption equals the read length, positions
+    only move right, the realigned span stays inside the region reference, and the result is deterministic."""
+    from pepper_b200.realign import Realigner
+    reads, regions = workload(60, 40, synth.ONT, 17)
+    ra = Realigner(0)
+    a = ra.realign(reads, regions)
+    st = ra.stats()
+    b = ra.realign(reads, regions)
+    assert np.array_equal(a.pos, b.pos) and np.array_equal(a.cigar, b.cigar) and np.array_equal(a.cigar_off, b.cigar_off)
+    assert st["aligned"] == reads.n_reads and st["realigned"] > 0.95 * reads.n_reads
+    ops, lens = a.cigar & 15, (a.cigar >> 4).astype(np.int64)
+    assert np.isin(ops, [0, 1, 2, 4]).all()
+    read_cons = np.where(np.isin(ops, [0, 1, 4]), lens, 0)
+    ref_cons = np.where(np.isin(ops, [0, 2]), lens, 0)
+    csum, rsum = np.concatenate([[0], np.cumsum(read_cons)]), np.concatenate([[0], np.cumsum(ref_cons)])
+    assert np.array_equal(csum[a.cigar_off[1:]] - csum[a.cigar_off[:-1]], np.diff(reads.seq_off))
+    assert (a.pos >= reads.pos).all()
+    span = rsum[a.cigar_off[1:]] - rsum[a.cigar_off[:-1]]
+    region_of = np.repeat(np.arange(regions.n_regions), regions.table[:, 7] - regions.table[:, 6])
+    ref_end = regions.table[region_of, 0] + regions.table[region_of, 5]
+    assert (a.pos + span <= ref_end).all()
+    ra.close()
