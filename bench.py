@@ -216,6 +216,7 @@ def run_ours(args):
             gather(len(calls))
     e1.record()
     barrier()
+    e2e_t = caller.timings()                                   # device time of the encoder / network kernels inside the last call
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3) / e2e_steps
     if world > 1:
         tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -262,6 +263,7 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": world * genomic_bases / (e2e_ms / 1e3), "unit": "bases/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "kernel_ms": {"encoder": e2e_t["encode_ms"], "network": e2e_t["network_ms"]},
                 "api": "pepper_b200.pipeline.VariantCaller.call -> pb_variant_call_host (pinned host buffers)"},
         "gpu_launches": int(gpu_launches),
         "phase_ms": {"encoder": float(np.mean(enc_ms)), "network": float(np.mean(net_ms)), "encoder_count_kernel": float(np.mean(count_ms)),

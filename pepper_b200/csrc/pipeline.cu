@@ -146,6 +146,9 @@ static int variant_call_host_single(pb_variant_encoder_t *e, pb_variant_net_t *n
 constexpr int64_t CALL_GROUP = 96;
 constexpr int64_t CALL_FIRST_GROUP = 24;
 
+// network chunk of the pipelined host entry == VARIANT_CHUNK of nets.cu (74 row tiles of 128 candidates)
+static constexpr int64_t PIPE_NET_CHUNK = 9472;
+
 extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *net, const pb_reads_t *h_reads,
                                     const pb_region_t *h_regions, int64_t n_regions, const char *h_ref, int64_t ref_bytes,
                                     const pb_variant_params_t *params, int64_t capacity, int8_t *h_images,
@@ -190,21 +193,40 @@ extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *n
     const int64_t n_groups = (int64_t) gb.size() - 1;
     GroupView V[2];
     PB_TRY(stage_group(e, 0, h_reads, h_regions, gb[0], gb[1], h_ref, V[0]));
-    int64_t done = 0;
+    int64_t done = 0, net_done = 0;
     float enc_ms = 0.f, net_ms = 0.f;
     int rc = PB_OK;
     for (int64_t g = 0; g < n_groups && rc == PB_OK; g++) {
         const int b = (int) (g & 1);
-        if (g + 1 < n_groups)
-            PB_TRY(stage_group(e, b ^ 1, h_reads, h_regions, gb[g + 1], gb[g + 2], h_ref, V[b ^ 1]));
         PB_CUDA(cudaStreamWaitEvent(st, e->copied[b], 0));
         int64_t n_g = 0;
         const int64_t room = std::max<int64_t>(capacity - done, 0);
-        rc = pb_variant_call_device(e, net, &V[b].d, V[b].d_regions, (int64_t) V[b].h_regions.size(), V[b].h_regions.data(), V[b].d_ref, 0,
-                                    params, room, e->p_images.as<int8_t>() + done * 33 * 26, e->p_positions.as<int64_t>() + done,
-                                    e->p_depths.as<uint8_t>() + done, e->p_freqs.as<uint8_t>() + done,
-                                    e->p_keys.as<char>() + done * PB_ALLELE_STRIDE, e->p_region_of.as<int32_t>() + done,
-                                    e->p_probs.as<float>() + done * 3, &n_g, stream_);
+        // encode this group behind the candidates of the previous ones; the network runs over WHOLE chunks of the accumulated
+        // candidates (the remainder rides along to the next group), so only the very last chunk of the call is partial
+        PB_CUDA(cudaEventRecord(e->pevt[0], st));
+        rc = pb_variant_encode_device(e, &V[b].d, V[b].d_regions, (int64_t) V[b].h_regions.size(), V[b].h_regions.data(), V[b].d_ref, 0, params, room,
+                                      e->p_images.as<int8_t>() + done * 33 * 26, e->p_positions.as<int64_t>() + done,
+                                      e->p_depths.as<uint8_t>() + done, e->p_freqs.as<uint8_t>() + done,
+                                      e->p_keys.as<char>() + done * PB_ALLELE_STRIDE, e->p_region_of.as<int32_t>() + done, nullptr, &n_g, stream_);
+        if (rc == PB_OK) {
+            PB_CUDA(cudaEventRecord(e->pevt[1], st));
+            const int64_t avail = done + n_g - net_done;
+            const int64_t run = (g + 1 == n_groups) ? avail : avail / PIPE_NET_CHUNK * PIPE_NET_CHUNK;
+            if (run > 0)
+                rc = pb_variant_net_forward_device(net, e->p_images.as<int8_t>() + net_done * 33 * 26, run, e->p_probs.as<float>() + net_done * 3,
+                                                   nullptr, stream_);
+            if (rc == PB_OK) {
+                net_done += run;
+                PB_CUDA(cudaEventRecord(e->pevt[2], st));
+                // the network of this group is queued: issue the next group's copies now, so that neither the host work of
+                // staging nor the copies themselves leave the compute stream idle
+                if (g + 1 < n_groups)
+                    PB_TRY(stage_group(e, b ^ 1, h_reads, h_regions, gb[g + 1], gb[g + 2], h_ref, V[b ^ 1]));
+                PB_CUDA(cudaStreamSynchronize(st));
+                cudaEventElapsedTime(&e->pms[0], e->pevt[0], e->pevt[1]);
+                cudaEventElapsedTime(&e->pms[1], e->pevt[1], e->pevt[2]);
+            }
+        }
         if (rc == PB_ERR_CAPACITY) {
             // the caller retries with the returned size: extrapolate from the regions seen so far (retried again if short)
             const int64_t seen = gb[g + 1];

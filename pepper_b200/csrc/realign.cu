@@ -276,16 +276,17 @@ __device__ __noinline__ SwBest sw_pass16(const int8_t *__restrict__ codes, int64
         if (src_lane < 0) up = 0;
         const uint32_t up2 = pack2(up, hmid);
         const uint32_t *pr = prof + rc * NP * 32 + lane;
-        // pass 1 (descending): H <- max(diag + s, E, 0)
-#pragma unroll
-        for (int r = NP - 1; r >= 0; r--) H2[r] = __viaddmax_s16x2_relu(r == 0 ? up2 : H2[r - 1], pr[r * 32], E2[r]);
+        // pass 1 (ascending, previous column's H carried in a register): H <- max(diag + s, E, 0); in the same sweep the
         // transfer of each half: chain value after its last valid row (pads only decay: compensated below)
-        uint32_t a2 = 0;
+        uint32_t a2 = 0, diag2 = up2;
+        uint32_t O2[NP];
 #pragma unroll
         for (int r = 0; r < NP; r++) {
-            uint32_t open2 = __viaddmax_s16x2_relu(H2[r], NGO2, 0u);
-            open2 = (open2 & M2[r]) | (PAD2 & ~M2[r]);
-            a2 = __viaddmax_s16x2(a2, NGE2, open2);
+            const uint32_t old = H2[r];
+            H2[r] = __viaddmax_s16x2_relu(diag2, pr[r * 32], E2[r]);
+            diag2 = old;
+            O2[r] = __viaddmax_s16x2_relu(H2[r], NGO2, 0u);            // max(H - gapO, 0): reused by pass 2
+            a2 = __viaddmax_s16x2(a2, NGE2, (O2[r] & M2[r]) | (PAD2 & ~M2[r]));
         }
         const int a_l = cl > 0 ? lo16(a2) + GE * npad_l : NEG;     // cl == 0: empty lane
         const int a_h = ch > 0 ? hi16(a2) + GE * npad_h : NEG;
@@ -314,11 +315,12 @@ __device__ __noinline__ SwBest sw_pass16(const int8_t *__restrict__ codes, int64
         uint32_t cm2 = 0;
 #pragma unroll
         for (int r = 0; r < NP; r++) {
-            const uint32_t hm2 = __vmaxs2(H2[r], floc2);
-            const uint32_t open2 = __viaddmax_s16x2_relu(hm2, NGO2, 0u);
+            // open = max(max(H, floc) - gapO, 0) = max(floc - gapO, max(H - gapO, 0)); the unrestricted chain dominates the
+            // restricted one, so the final H is max(H, ffull)
+            const uint32_t open2 = __viaddmax_s16x2(floc2, NGO2, O2[r]);
             E2[r] = __viaddmax_s16x2(E2[r], NGE2, open2);
             floc2 = __viaddmax_s16x2(floc2, NGE2, open2);
-            const uint32_t hf2 = __vmaxs2(hm2, ffull2);
+            const uint32_t hf2 = __vmaxs2(H2[r], ffull2);
             ffull2 = __viaddmax_s16x2(ffull2, NGE2, open2);
             H2[r] = hf2;
             cm2 = __vmaxs2(cm2, hf2 & M2[r]);
