@@ -757,7 +757,7 @@ extern "C" int pb_realign_device(pb_realigner_t *t, const pb_reads_t *dr, const 
     if (h_err == 1) { set_error("a read starts before its region start: the reference drops such reads (simple_aligner.cpp:73-77); fetch reads with get_reads(start = region start)"); return PB_ERR_ARG; }
     if (h_err == 2) { set_error("region read ranges do not cover the reads in order"); return PB_ERR_ARG; }
     // banded pass: persistent warps with one scratch slot each; alignments that outgrow the slot are retried with bigger slots
-    const int64_t pool_cap = nb / 2 + 4 * n + 1024;
+    const int64_t pool_cap = nb + 4 * n + 1024;             // worst case: one tuple per base (alternating = / X) + clips
     PB_TRY(t->pool.reserve(sizeof(uint32_t) * (size_t) pool_cap));
     PB_CUDA(cudaMemsetAsync(t->pool_used.p, 0, 16, st));
     int band_bw = 128;
