@@ -247,7 +247,7 @@ def run_ours(args):
                     executed_bf16_tflops=3 * tf, executed_frac=3 * tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
                     note="achieved = fp32-equivalent algorithmic FLOPs (161.4 MFLOP per candidate) / network time; every FLOP is "
                          "executed as three bf16 tensor-core products (hi/lo split), so the tensor pipe runs at executed_frac; "
-                         "ncu: linear_1 launch 95 % tensor-pipe active, decoder LSTM step 60 % (profiles/README.md)")
+                         "ncu: linear_1 launch 94.5 % tensor-pipe active, decoder LSTM step 79.8 %, encoder LSTM step 47.8 % (profiles/README.md)")
 
     line = {
         "metric": "genomic bases/sec (make_images+inference)", "value": value, "unit": "bases/s", "n_gpus": world,

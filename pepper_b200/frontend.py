@@ -1,0 +1,136 @@
+"""File -> predictions in one call: the per-process loops of the reference's make_images + inference steps
+(`pepper_variant ImageGenerationUI.generate_image_and_save_to_file` :191-251 + `AlignmentSummarizer.create_summary`
+:181-236 + `predict_distributed_gpu.predict` :58-70;  `pepper ImageGenerationUI.image_generator` :191-236 +
+`AlignmentSummarizer.create_summary` :296-356 + `predict_distributed_gpu.predict` :63-105) with every stage after the BGZF
+inflate on the GPU: `pb_bam_fetch` -> batched `get_reads` (+ reservoir sampling) -> [SSW realignment] -> pileup encoder
+-> recurrent network.  Nothing here is a CLI: intervals in, arrays out (what the reference writes to its HDF5 stores).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .bamio import BamReader, FastaReader
+from .pipeline import FetchedReads, PolishCaller, VariantCaller, PolishCalls, VariantCalls
+from .reads import ReadTrimmer
+from .realign import Realigner, ALIGNMENT_SAFE_BASES
+from .synth import RegionTable
+
+REGION_SAFE_BASES = 100              # ConsensCandidateFinder.REGION_SAFE_BASES (pepper_variant Options.py:2)
+MIN_IMAGE_OVERLAP = 100              # ImageSizeOptions.MIN_IMAGE_OVERLAP (pepper Options.py:10)
+VARIANT_MAX_READS = 5000             # AlingerOptions.MAX_READS_IN_REGION (pepper_variant Options.py:98)
+POLISH_MAX_READS = 1500              # AlingerOptions.MAX_READS_IN_REGION (pepper Options.py:28)
+
+
+def polish_intervals(interval_start: int, interval_end: int, max_size: int = 1000) -> list[tuple[int, int]]:
+    """pepper ImageGenerationUI.py:269-272."""
+    return [(max(interval_start, pos - MIN_IMAGE_OVERLAP), min(interval_end, pos + max_size + MIN_IMAGE_OVERLAP))
+            for pos in range(interval_start, interval_end, max_size)]
+
+
+def variant_intervals(interval_start: int, interval_end: int, region_size: int = 100_000) -> list[tuple[int, int]]:
+    """pepper_variant ImageGenerationUI.py:307-316."""
+    return [(max(interval_start, pos), min(interval_end, pos + region_size)) for pos in range(interval_start, interval_end, region_size)]
+
+
+class _FromFiles:
+    def __init__(self, bam_path: str, fasta_path: str, device: int = 0, threads: int = 0):
+        self.bam = BamReader(bam_path, threads)
+        self.fasta = FastaReader(fasta_path)
+        self.trimmer = ReadTrimmer(device)
+        self.device = device
+
+    def _ref_table(self, contig: str, rows: list[list[int]], spans: list[tuple[int, int]]) -> RegionTable:
+        refs, off = [], 0
+        for row, (a, b) in zip(rows, spans):
+            r = self.fasta.fetch_array(contig, a, b)
+            row[4], row[5] = off, int(r.shape[0])
+            refs.append(r)
+            off += int(r.shape[0])
+        return RegionTable(np.array(rows, dtype=np.int64).reshape(-1, 8), np.concatenate(refs) if refs else np.zeros(1, np.uint8))
+
+
+class VariantFromFiles(_FromFiles):
+    """call_variant's make_images + run_inference for a list of intervals of one contig."""
+
+    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0):
+        super().__init__(bam_path, fasta_path, device, threads)
+        self.caller = VariantCaller(state, device)
+
+    def call(self, contig: str, intervals: list[tuple[int, int]], params: dict, include_supplementary: bool = False,
+             min_mapq: int = 0, downsample_rate: float = 1.0, max_reads: int = VARIANT_MAX_READS,
+             capacity: int | None = None) -> tuple[VariantCalls, RegionTable]:
+        import torch
+        if not intervals:
+            raise ValueError("no intervals")
+        rows, queries, spans = [], [], []
+        for (s, e) in intervals:
+            rs, re_ = max(0, s - REGION_SAFE_BASES), e + REGION_SAFE_BASES          # AlignmentSummarizer.py:181-182
+            queries.append((rs, re_))                                               # get_reads(chrom, region_start, region_end, ...)
+            rows.append([rs, re_, s, e, 0, 0, 0, 0])
+            spans.append((rs, re_ + 1))                                             # get_reference_sequence(.., region_end + 1)
+        regions = self._ref_table(contig, rows, spans)
+        view = self.bam.fetch(contig, min(q[0] for q in queries), max(q[1] for q in queries))
+        got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
+                                     max_reads=max_reads, downsample_rate=downsample_rate)
+        fetched = FetchedReads(got, regions, self.device)
+        dev = torch.device("cuda", self.device)
+        cap = capacity or max(1024, int(sum(e - s + 1 for s, e in intervals)) // 16)
+        while True:
+            out = dict(images=torch.empty((cap, 33, 26), dtype=torch.int8, device=dev), positions=torch.empty(cap, dtype=torch.int64, device=dev),
+                       depths=torch.empty(cap, dtype=torch.uint8, device=dev), freqs=torch.empty(cap, dtype=torch.uint8, device=dev),
+                       keys=torch.empty((cap, 64), dtype=torch.uint8, device=dev), region_of=torch.empty(cap, dtype=torch.int32, device=dev),
+                       probs=torch.empty((cap, 3), dtype=torch.float32, device=dev))
+            try:
+                n = self.caller.call_device(fetched, params, out)
+                break
+            except Exception as ex:                        # capacity: the library reports the need in the message-less code -3
+                if "code -3" not in str(ex):
+                    raise
+                cap *= 2
+        h = {k: v[:n].cpu().numpy() for k, v in out.items()}
+        return VariantCalls(h["positions"], h["depths"], h["freqs"], h["keys"], h["region_of"], h["probs"], h["images"]), fetched_table(fetched, regions)
+
+
+class PolishFromFiles(_FromFiles):
+    """polish's make_images (with read realignment) + call_consensus for a list of regions of one contig."""
+
+    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0):
+        super().__init__(bam_path, fasta_path, device, threads)
+        self.caller = PolishCaller(state, device)
+        self.realigner = Realigner(device)
+
+    def call(self, contig: str, regions_se: list[tuple[int, int]], realign: bool = True, max_reads: int = POLISH_MAX_READS,
+             capacity: int | None = None) -> tuple[PolishCalls, RegionTable]:
+        import torch
+        if not regions_se:
+            raise ValueError("no regions")
+        rows, spans = [], []
+        for (rs, re_) in regions_se:
+            rows.append([rs, re_, rs, re_, 0, 0, 0, 0])
+            spans.append((rs, re_ + ALIGNMENT_SAFE_BASES))                         # AlignmentSummarizer.py:164-170
+        regions = self._ref_table(contig, rows, spans)
+        view = self.bam.fetch(contig, min(r[0] for r in regions_se), max(r[1] for r in regions_se))
+        got = self.trimmer.get_reads(view, regions_se, False, 0, 0, max_reads=max_reads, downsample_rate=1.0)   # :300-325
+        fetched = FetchedReads(got, regions, self.device)
+        if realign:
+            fetched.struct = self.realigner.realign_device(fetched)                # :328-332
+        dev = torch.device("cuda", self.device)
+        cap = capacity or 3 * (sum(e - s + 1 for s, e in regions_se) // 950 + len(regions_se)) + 8
+        while True:
+            out = dict(bases=torch.empty((cap, 1000), dtype=torch.uint8, device=dev), phred=torch.empty((cap, 1000), dtype=torch.uint8, device=dev),
+                       position=torch.empty((cap, 1000), dtype=torch.int64, device=dev), index=torch.empty((cap, 1000), dtype=torch.int32, device=dev),
+                       image_region=torch.empty(cap, dtype=torch.int32, device=dev), chunk_id=torch.empty(cap, dtype=torch.int32, device=dev))
+            try:
+                n = self.caller.call_device(fetched, out)
+                break
+            except Exception as ex:
+                if "code -3" not in str(ex):
+                    raise
+                cap *= 2
+        h = {k: v[:n].cpu().numpy() for k, v in out.items()}
+        return PolishCalls(h["bases"], h["phred"], h["position"], h["index"], h["image_region"], h["chunk_id"]), fetched_table(fetched, regions)
+
+
+def fetched_table(fetched: FetchedReads, regions: RegionTable) -> RegionTable:
+    """The region table with the read ranges get_reads produced (after down-sampling)."""
+    return RegionTable(fetched.table.copy(), regions.ref)

@@ -195,18 +195,23 @@ class PolishCaller:
         self.net.close()
 
     def call(self, reads: ReadBatch, regions: RegionTable, capacity: int | None = None, stream: int = 0) -> PolishCalls:
-        hr = HostReads(reads)
+        return self.call_prepared(HostReads(reads), regions, capacity, stream)
+
+    def call_prepared(self, hr: HostReads, regions: RegionTable, capacity: int | None = None, stream: int = 0,
+                      reuse_buffers: bool = False) -> PolishCalls:
+        """`reuse_buffers=True`: results land in page-locked buffers owned by the caller object (views, valid until the next
+        call) — the streaming mode of a pipeline worker; default: fresh arrays."""
         regs, keep = regions_array(regions)
         if capacity is None:
             span = int((regions.col("ref_end") - regions.col("ref_start") + 1).sum())
             capacity = 3 * (span // 950 + regions.n_regions) + 8
         while True:
-            bases = np.empty((capacity, POLISH_SEQ_LEN), dtype=np.uint8)
-            phred = np.empty((capacity, POLISH_SEQ_LEN), dtype=np.uint8)
-            position = np.empty((capacity, POLISH_SEQ_LEN), dtype=np.int64)
-            index = np.empty((capacity, POLISH_SEQ_LEN), dtype=np.int32)
-            ireg = np.empty(capacity, dtype=np.int32)
-            cid = np.empty(capacity, dtype=np.int32)
+            bases = self._out("bases", (capacity, POLISH_SEQ_LEN), np.uint8, reuse_buffers)
+            phred = self._out("phred", (capacity, POLISH_SEQ_LEN), np.uint8, reuse_buffers)
+            position = self._out("position", (capacity, POLISH_SEQ_LEN), np.int64, reuse_buffers)
+            index = self._out("index", (capacity, POLISH_SEQ_LEN), np.int32, reuse_buffers)
+            ireg = self._out("ireg", (capacity,), np.int32, reuse_buffers)
+            cid = self._out("cid", (capacity,), np.int32, reuse_buffers)
             n = C.c_int64(0)
             rc = self.L.pb_polish_call_host(self.enc.h, self.net.h, C.byref(hr.struct), regs, regions.n_regions, capacity,
                                             bases.ctypes.data, phred.ctypes.data, position.ctypes.data, index.ctypes.data,
@@ -217,6 +222,18 @@ class PolishCaller:
             _lib.check(rc, "pb_polish_call_host")
             k = int(n.value)
             return PolishCalls(bases[:k], phred[:k], position[:k], index[:k], ireg[:k], cid[:k])
+
+    def _out(self, name: str, shape, dtype, reuse: bool):
+        if not reuse:
+            return np.empty(shape, dtype=dtype)
+        import torch
+        cache = self.__dict__.setdefault("_pinned", {})
+        need = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        t = cache.get(name)
+        if t is None or t.numel() < need:
+            t = torch.empty(max(need, 1), dtype=torch.uint8).pin_memory()
+            cache[name] = t
+        return t.numpy()[:need].view(dtype).reshape(shape)
 
     def call_device(self, dreads: DeviceReads, out: dict, stream: int = 0) -> int:
         """Everything in HBM.  `out`: torch CUDA tensors bases/phred uint8 [cap,1000], position int64 [cap,1000],

@@ -1,0 +1,90 @@
+"""GPU: the one-call file -> predictions front ends (pepper_b200/frontend.py) against the oracle chain: get_reads (+ reservoir
+down-sampling) -> [realign] -> encoder, all oracle restatements, then the same network weights."""
+import numpy as np
+import pytest
+
+from pepper_b200 import synth, synth_files
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("frontend_gpu")
+    rec, genome = synth.simulate_contig_records(26000, 30, synth.ONT, 23)
+    bam, fa = str(d / "f.bam"), str(d / "f.fa")
+    synth_files.write_bam(bam, [("ctg", genome.shape[0])], {0: rec})
+    synth_files.write_fasta(fa, [("ctg", genome)])
+    return dict(bam=bam, fa=fa, rec=rec, genome=genome)
+
+
+def oracle_reads(oracle, rec, queries, supp, mq, bq, max_reads, rate=1.0):
+    from pepper_b200.reads import reservoir_select
+    batches, counts = [], []
+    for (s, e) in queries:
+        b, _, _ = oracle.get_reads(rec, s, e, supp, mq, bq, impl="port")
+        sel = reservoir_select(b.n_reads, int(min(max_reads, rate * b.n_reads)))
+        if sel is not None:
+            b = synth.take_reads(b, sel)
+        batches.append(b)
+        counts.append(b.n_reads)
+    return synth.concat_batches(batches), np.array(counts)
+
+
+def test_intervals_match_reference_tiling():
+    from pepper_b200.frontend import polish_intervals, variant_intervals
+    assert polish_intervals(0, 2499) == [(0, 1100), (900, 2100), (1900, 2499)]
+    assert variant_intervals(0, 250_000) == [(0, 100_000), (100_000, 200_000), (200_000, 250_000)]
+
+
+@pytest.mark.parametrize("max_reads", [5000, 25])
+def test_variant_from_files(oracle_built, files, max_reads):
+    from pepper_b200 import weights
+    from pepper_b200.frontend import VariantFromFiles, variant_intervals
+    params = synth.ont_params()
+    iv = variant_intervals(2000, 24000, 8000)
+    vf = VariantFromFiles(files["bam"], files["fa"], weights.random_variant_state(0))
+    calls, table = vf.call("ctg", iv, params, max_reads=max_reads)
+    queries = [(max(0, s - 100), e + 100) for s, e in iv]
+    reads, counts = oracle_reads(oracle_built, files["rec"], queries, False, 0, int(params["min_snp_baseq"]), max_reads)
+    assert np.array_equal(table.table[:, 7] - table.table[:, 6], counts)
+    if max_reads == 25:
+        assert (counts == 25).all()
+    tab = table.table.copy()
+    want = oracle_built.variant_encode(reads, synth.RegionTable(tab, table.ref), params, "port")
+    assert calls.keys == want["keys"] and np.array_equal(calls.positions, want["positions"])
+    assert np.array_equal(calls.images, oracle_built.images_to_int8(want["images"]))
+    assert len(calls) > (5 if max_reads == 25 else 20)
+
+
+def test_polish_from_files(oracle_built, files):
+    from pepper_b200 import weights
+    from pepper_b200.frontend import PolishFromFiles, polish_intervals
+    from pepper_b200.pipeline import PolishCaller
+    regs = polish_intervals(3000, 8000)
+    state = weights.random_polish_state(0)
+    pf = PolishFromFiles(files["bam"], files["fa"], state)
+    calls, table = pf.call("ctg", regs, realign=True, max_reads=30)
+    reads, counts = oracle_reads(oracle_built, files["rec"], regs, False, 0, 0, 30)
+    assert np.array_equal(table.table[:, 7] - table.table[:, 6], counts) and counts.max() == 30
+    otab = synth.RegionTable(table.table.copy(), table.ref)
+    pos, off, cig = [], [0], []
+    for r in range(len(regs)):
+        row = otab.table[r]
+        ref = otab.ref[int(row[4]):int(row[4] + row[5])].tobytes().decode()
+        p_, _, co, c = oracle_built.realign(reads, int(row[6]), int(row[7]), int(row[0]), int(row[1]) + 20, ref, impl="port")
+        pos.append(p_)
+        cig.append(c)
+        off.extend((co[1:] + off[-1]).tolist())
+    realigned = synth.ReadBatch(np.concatenate(pos), reads.seq_off, np.array(off, dtype=np.int64), reads.flags, reads.mapq, reads.seq,
+                                reads.qual, np.concatenate(cig))
+    pc = PolishCaller(state)
+    want = pc.call(realigned, otab)                    # encoder + GRU parity of this caller is covered by test_pipeline_gpu / smoke
+    assert np.array_equal(calls.position, want.position) and np.array_equal(calls.chunk_id, want.chunk_id)
+    assert np.array_equal(calls.bases, want.bases) and np.array_equal(calls.phred, want.phred)
+    # and the images behind it: the oracle polish encoder on the oracle-realigned reads
+    from pepper_b200.polish import PolishEncoder
+    s_gpu = PolishEncoder(0).encode(realigned, otab)
+    s_or = oracle_built.polish_encode(realigned, otab, "port")
+    assert np.array_equal(s_gpu.image, s_or["image"])
+    pc.close()
