@@ -94,7 +94,7 @@ static int launch_tc(const Args &A, int mt, int nt128, int ndir, cudaStream_t st
     if (nt128 % 2) { set_error("tcgen05 path needs N %% 256 == 0"); return PB_ERR_ARG; }
     const int nt = nt128 / 2;
     const int tiles = mt * nt * ndir;
-    tc::k_tc_gemm_p<EPI><<<(unsigned) std::min(tiles, g_num_sms), tc::THREADS, tc::PSMEM_BYTES, st>>>(A, mt, nt, ndir);
+    tc::k_tc_gemm_p<EPI><<<(unsigned) std::min(tiles, g_num_sms), tc::PG_THREADS, tc::PSMEM_BYTES, st>>>(A, mt, nt, ndir);
     return PB_OK;
 }
 // one 128x128 tile per CTA, two CTAs per SM (first tcgen05 version; kept for N %% 256 != 0 and as a cross-check)

@@ -320,7 +320,13 @@ constexpr int WTILE_BYTES = WTILE_ELEMS * 2;
 constexpr int PSTAGE_BYTES = 2 * TILE_BYTES + 2 * WTILE_BYTES;   // A_hi, A_lo, B_hi, B_lo = 48 KB
 constexpr int PSMEM_BYTES = PSTAGES * PSTAGE_BYTES + 256;
 constexpr int PTMEM_COLS = 2 * PBN;                   // double-buffered accumulator = all 512 TMEM columns
-constexpr int PEPI_COLS = PBN / 2;                    // columns per epilogue warp
+constexpr int PEPI_COLS = PBN / 2;                    // columns per epilogue warp (GRU window kernels: 8 epilogue warps)
+#ifndef PB_PG_EPI_WARPS
+#define PB_PG_EPI_WARPS 16
+#endif
+constexpr int PG_EPI_WARPS = PB_PG_EPI_WARPS;         // epilogue warps of k_tc_gemm_p: 4 TMEM lane quarters x column groups
+constexpr int PG_COLS = PBN / (PG_EPI_WARPS / 4);     // columns per epilogue warp
+constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS;
 constexpr uint32_t IDESC256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (PBN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
 __device__ __forceinline__ uint64_t smem_desc_lbo(uint32_t addr, uint32_t lbo) {
     uint64_t d = 0;
@@ -336,7 +342,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1) k_tc_gemm_p(Args G, int n_mt, int n_nt /* 256-column tiles */, int n_dir) {
+__global__ void __launch_bounds__(PG_THREADS, 1) k_tc_gemm_p(Args G, int n_mt, int n_nt /* 256-column tiles */, int n_dir) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PSTAGES * PSTAGE_BYTES);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + PSTAGES);
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm_p(Args G, int n_mt, int 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PSTAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 8); }
+        for (int b = 0; b < 2; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, PG_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -435,14 +441,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm_p(Args G, int n_mt, int 
             const uint32_t buf = it & 1u, use = it >> 1;
             const int row = mt * BM + r128;
             const bool valid = row < G.M;
-            float st[PEPI_COLS / 4];
-            const int ubase = nt * (PBN / 4) + half * (PEPI_COLS / 4);
+            float st[PG_COLS / 4];
+            const int ubase = nt * (PBN / 4) + half * (PG_COLS / 4);
             if (EPI == EPI_LSTM) {
 #pragma unroll
-                for (int u = 0; u < PEPI_COLS / 4; u++) st[u] = valid ? D.c[(int64_t) (ubase + u) * G.c_ld + row] : 0.f;
+                for (int u = 0; u < PG_COLS / 4; u++) st[u] = valid ? D.c[(int64_t) (ubase + u) * G.c_ld + row] : 0.f;
             } else if (EPI == EPI_GRU) {
 #pragma unroll
-                for (int u8 = 0; u8 < PEPI_COLS / 32; u8++) {
+                for (int u8 = 0; u8 < PG_COLS / 32; u8++) {
                     uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
                     if (valid && D.hp_hi) {
                         const int j0 = ubase + u8 * 8;
@@ -459,12 +465,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm_p(Args G, int n_mt, int 
             mbar_wait(bar_accf + 8 * buf, use & 1u);
             tc_fence_after();
 #pragma unroll
-            for (int cl = 0; cl < PEPI_COLS / 32; cl++) {
-                const int cc = half * (PEPI_COLS / 32) + cl;
+            for (int cl = 0; cl < PG_COLS / 32; cl++) {
+                const int cc = half * (PG_COLS / 32) + cl;
                 const int col0 = nt * PBN + cc * 32;
                 uint32_t acc[32];
                 tmem_ld32(tmem_base + buf * PBN + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
-                if (cl == PEPI_COLS / 32 - 1) {
+                if (cl == PG_COLS / 32 - 1) {
                     // last read of this accumulator buffer by this warp: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -529,7 +535,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm_p(Args G, int n_mt, int 
             }
             if (EPI == EPI_LSTM && valid) {
 #pragma unroll
-                for (int u = 0; u < PEPI_COLS / 4; u++) D.c[(int64_t) (ubase + u) * G.c_ld + row] = st[u];
+                for (int u = 0; u < PG_COLS / 4; u++) D.c[(int64_t) (ubase + u) * G.c_ld + row] = st[u];
             }
         }
     }
