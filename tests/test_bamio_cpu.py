@@ -133,3 +133,22 @@ def test_errors(tmp_path):
         BamReader(str(p))
     with pytest.raises(PepperB200Error):
         FastaReader(str(tmp_path / "missing.fa"))
+
+
+def test_records_without_sequence_and_odd_lengths(tmp_path):
+    """Secondary alignments are often stored without SEQ/QUAL (l_seq = 0); odd-length neighbours share packed bytes."""
+    from pepper_b200.bamio import BamReader
+    recs = [dict(pos=10, seq="ACGTA", cigar=[(0, 5)]), dict(pos=12, seq="", cigar=[(0, 30)], flag=256),
+            dict(pos=14, seq="", cigar=[(0, 30)], flag=256), dict(pos=15, seq="GGT", cigar=[(0, 3)]),
+            dict(pos=20, seq="", cigar=[(0, 9)], flag=256), dict(pos=30, seq="TTTTTTT", cigar=[(4, 2), (0, 5)])]
+    batch = synth.make_records(recs)
+    bam = str(tmp_path / "z.bam")
+    synth_files.write_bam(bam, [("c", 1000)], {0: batch})
+    got = BamReader(bam, threads=2).fetch("c", 0, 1000).to_batch()
+    for f in FIELDS:
+        assert np.array_equal(getattr(got, f), getattr(batch, f)), f
+    got = BamReader(bam, threads=1).fetch("c", 13, 16).to_batch()          # records 0, 1, 2, 3 overlap [13, 16)
+    assert got.pos.tolist() == [10, 12, 14, 15] and got.seq_off.tolist() == [0, 5, 5, 5, 8]
+    codes = np.empty(2 * got.seq.shape[0], dtype=np.uint8)
+    codes[0::2], codes[1::2] = got.seq >> 4, got.seq & 15
+    assert "".join(synth.NT16[c] for c in codes[:8]) == "ACGTAGGT"
