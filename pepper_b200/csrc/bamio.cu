@@ -393,6 +393,8 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
                 t_inflate += t_b - t_a; n_groups++;
                 store_size = base + utotal;
                 struct { uint8_t *p; uint8_t *data() const { return p; } } u{b->ubuf.p + base};
+                // pass 1 (sequential, cheap): hop over the records of the group's chunks, remember those of this contig left of `end`
+                std::vector<size_t> cand;
                 for (size_t ci = gi; ci <= gj && !done; ci++) {
                     size_t p = upos_of(blocks, merged[ci].beg, utotal);
                     const size_t pe = std::min(upos_of(blocks, merged[ci].end, utotal), utotal);
@@ -402,6 +404,20 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
                         const uint8_t *r = u.data() + p + 4;
                         const int32_t rtid = rdi32(r), pos = rdi32(r + 4);
                         if (rtid != tid || pos >= end) { if (rtid > tid || (rtid == tid && pos >= end)) { done = true; break; } p += 4 + bs; continue; }
+                        cand.push_back(p);
+                        p += 4 + bs;
+                    }
+                }
+                // pass 2 (parallel): long-CIGAR convention, reference length, overlap test
+                struct Parsed { uint32_t n_cigar; size_t cigar_off; uint8_t keep; };
+                std::vector<Parsed> parsed(cand.size());
+                const size_t pgrain = 256;
+                parallel_for(b->n_threads, (cand.size() + pgrain - 1) / pgrain, [&](size_t g) {
+                    for (size_t ii = g * pgrain; ii < std::min(cand.size(), (g + 1) * pgrain); ii++) {
+                        const size_t p = cand[ii];
+                        const uint32_t bs = rd32(u.data() + p);
+                        const uint8_t *r = u.data() + p + 4;
+                        const int32_t pos = rdi32(r + 4);
                         const uint32_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
                         const uint8_t *cig = r + 32 + l_name;
                         uint32_t n_cigar = n_cig;
@@ -435,13 +451,16 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
                             if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
                         }
                         if (n_cigar == 0) rlen = 1;
-                        if ((int64_t) pos + rlen > beg) {
-                            recs.push_back({base + p + 4, l_seq, n_cigar, nullptr});
-                            rec_store_off.push_back(base + (size_t) (cigar - u.data()));
-                            rpos.push_back(pos);
-                        }
-                        p += 4 + bs;
+                        parsed[ii] = {n_cigar, (size_t) (cigar - u.data()), (uint8_t) ((int64_t) pos + rlen > beg)};
                     }
+                });
+                // pass 3 (sequential): keep the overlapping ones in file order
+                for (size_t ii = 0; ii < cand.size(); ii++) {
+                    if (!parsed[ii].keep) continue;
+                    const uint8_t *r = u.data() + cand[ii] + 4;
+                    recs.push_back({base + cand[ii] + 4, rd32(r + 16), parsed[ii].n_cigar, nullptr});
+                    rec_store_off.push_back(base + parsed[ii].cigar_off);
+                    rpos.push_back(rdi32(r + 4));
                 }
                 t_walk += tnow() - t_b;
                 gi = gj + 1;

@@ -131,3 +131,30 @@ def test_realign_properties_large_batch():
     ref_end = regions.table[region_of, 0] + regions.table[region_of, 5]
     assert (a.pos + span <= ref_end).all()
     ra.close()
+
+
+def test_realign_length_class_boundaries(oracle_built):
+    """Read lengths at the register-class boundaries of the packed kernel (512/768/1024/1344 bases) and tiny reads."""
+    from pepper_b200.realign import Realigner
+    rng = np.random.default_rng(12)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 1500))
+    recs = []
+    for k, n in enumerate([1, 2, 15, 16, 17, 31, 32, 33, 63, 64, 65, 255, 256, 257, 511, 512, 513, 767, 768, 769, 1023, 1024, 1025,
+                           1343, 1344, 1345]):
+        start = k
+        body = list(ref[start:start + n])
+        for j in range(7, len(body), 53):                      # a few substitutions so that the CIGARs are not trivial
+            body[j] = "ACGT"[("ACGT".index(body[j]) + 1) % 4]
+        if n > 200:
+            del body[100:103]                                  # and a deletion / an insertion
+            body[150:150] = list("TTG")
+        seq = "".join(body)[:n] if len(body) >= n else "".join(body) + ref[start + n:start + 2 * n - len(body)]
+        recs.append(dict(pos=start, seq=seq[:n] if len(seq) >= n else seq, cigar=[(0, min(n, len(seq)))]))
+    reads = synth.make_batch(recs)
+    tab = np.array([[0, 1480, 0, 1480, 0, 1500, 0, reads.n_reads]], dtype=np.int64)
+    regions = synth.RegionTable(tab, np.frombuffer(ref.encode(), dtype=np.uint8))
+    want_pos, want_off, want_cig = oracle_realign(oracle_built, reads, regions)
+    ra = Realigner(0)
+    got = ra.realign(reads, regions)
+    assert np.array_equal(got.pos, want_pos) and np.array_equal(got.cigar_off, want_off) and np.array_equal(got.cigar, want_cig)
+    ra.close()
