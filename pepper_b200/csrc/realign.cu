@@ -508,15 +508,23 @@ __global__ void __launch_bounds__(128) k_banded(const Task *__restrict__ tasks, 
         while (i > 0 && status == 2) {
             const int x_top = max(0, i - bw);
             const int c0 = (j - x_top) - WIN_W / 2;              // window start in band coordinates (same for the staged rows)
-            for (int rr = 0; rr < WIN_H; rr++) {
-                const int row = i - rr;
-                if (row < 1) break;
-                const uint8_t *src = dir + (size_t) width_d * row;
+            // all loads of 8 rows are issued before the first store (the walk below is sequential: this is its only HBM / L2 wait)
+            for (int rr0 = 0; rr0 < WIN_H; rr0 += 8) {
+                uint8_t tmp[8][WIN_W / 32];
 #pragma unroll
-                for (int k = 0; k < WIN_W; k += 32) {
-                    const int cc = c0 + k + lane;
-                    sh.win[rr * WIN_W + k + lane] = (cc >= 0 && cc < width_d) ? src[cc] : (uint8_t) 0;
+                for (int r8 = 0; r8 < 8; r8++) {
+                    const int row = i - (rr0 + r8);
+                    const uint8_t *src = dir + (size_t) width_d * max(row, 0);
+#pragma unroll
+                    for (int k = 0; k < WIN_W / 32; k++) {
+                        const int cc = c0 + 32 * k + lane;
+                        tmp[r8][k] = (row >= 1 && cc >= 0 && cc < width_d) ? src[cc] : (uint8_t) 0;
+                    }
                 }
+#pragma unroll
+                for (int r8 = 0; r8 < 8; r8++)
+#pragma unroll
+                    for (int k = 0; k < WIN_W / 32; k++) sh.win[(rr0 + r8) * WIN_W + 32 * k + lane] = tmp[r8][k];
             }
             __syncwarp();
             if (lane == 0) {
