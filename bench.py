@@ -242,7 +242,12 @@ def run_ours(args):
     tf = n_cand * FLOP_PER_CAND / net_s / 1e12
     roof_net = dict(bound="tensor", kernel="k_tc_gemm (tcgen05 LSTM-step / MLP GEMMs, all launches of the step; 3 bf16 products per algorithmic FLOP)", achieved=tf,
                     peak=peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], unit="TFLOP/s",
-                    frac=tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), traffic=None, peak_source=peaks["source"] + ", sustained bf16",
+                    frac=tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
+                    traffic=int(n_cand / 9472.0 * (33 * (43.83e6 + 91.20e6) + 678.66e6)),
+                    traffic_note="dram__bytes_read+write of the ncu --set full captures (encoder LSTM step 43.8 MB, decoder LSTM step 91.2 MB, "
+                                 "linear_1 678.7 MB per launch at a 9,472-candidate chunk; profiles/r1_prof_tcp_*_final_raw.csv) summed over the "
+                                 "launches of this step (33 + 33 + 1 per chunk)",
+                    peak_source=peaks["source"] + ", sustained bf16",
                     flops_per_step=n_cand * FLOP_PER_CAND, step_ms=net_s * 1e3,
                     executed_bf16_tflops=3 * tf, executed_frac=3 * tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
                     note="achieved = fp32-equivalent algorithmic FLOPs (161.4 MFLOP per candidate) / network time; every FLOP is "
