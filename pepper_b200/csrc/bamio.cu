@@ -21,6 +21,9 @@
 #include <thread>
 #include <vector>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 
 using namespace pb;
 
@@ -87,14 +90,52 @@ bool inflate_block(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_
 
 struct Block { size_t coff, data_off, bsize; uint32_t isize; size_t uoff; };
 
-template <typename F> void parallel_for(int n_threads, size_t n, F f) {
-    if (n_threads <= 1 || n < 2) { for (size_t i = 0; i < n; i++) f(i); return; }
-    std::atomic<size_t> next(0);
-    std::vector<std::thread> th;
-    const int T = (int) std::min<size_t>((size_t) n_threads, n);
-    for (int t = 0; t < T; t++) th.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); });
-    for (auto &x : th) x.join();
-}
+// persistent worker pool (one per reader): spawning 128 threads per parallel loop costs more than a small inflate
+struct Pool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(size_t)> fn;
+    std::atomic<size_t> next{0};
+    size_t n = 0, generation = 0;
+    int running = 0;
+    bool stop = false;
+    explicit Pool(int threads) {
+        for (int t = 0; t < threads; t++) workers.emplace_back([this]() { loop(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> l(mu); stop = true; }
+        cv_work.notify_all();
+        for (auto &w : workers) w.join();
+    }
+    void loop() {
+        size_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cv_work.wait(l, [&]() { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+            {
+                std::lock_guard<std::mutex> l(mu);
+                if (--running == 0) cv_done.notify_all();
+            }
+        }
+    }
+    template <typename F> void run(size_t count, F f) {
+        if (workers.empty() || count < 2) { for (size_t i = 0; i < count; i++) f(i); return; }
+        {
+            std::lock_guard<std::mutex> l(mu);
+            fn = f; n = count; next = 0; running = (int) workers.size(); generation++;
+        }
+        cv_work.notify_all();
+        for (size_t i; (i = next.fetch_add(1)) < count;) f(i);          // the caller helps
+        std::unique_lock<std::mutex> l(mu);
+        cv_done.wait(l, [&]() { return running == 0; });
+    }
+};
 
 struct HostBuf {                 // grow-only; page-locked when a CUDA device is present (faster H2D), plain otherwise
     void *p = nullptr;
@@ -138,6 +179,7 @@ struct RecRef { size_t off; uint32_t l_seq, n_cigar; const uint8_t *cigar; };   
 struct pb_bam {
     MappedFile f;
     int n_threads = 1;
+    Pool *pool = nullptr;
     bool pinned = false;
     std::string text;
     std::vector<std::string> names;
@@ -188,9 +230,16 @@ int inflate_range(pb_bam *b, size_t c0, size_t c1_block, std::vector<Block> &blo
     uint8_t *out = b->ubuf.p + base;
     *utotal_out = utotal;
     std::atomic<int> bad(0);
-    parallel_for(b->n_threads, blocks.size(), [&](size_t i) {
+    // the compressed bytes are pread() into a per-thread buffer: faulting the mmap'ed file in from 100+ threads at once
+    // serialises on the address-space lock (measured: 1.8 GB/s at 460 MB vs 5 GB/s at 115 MB)
+    b->pool->run(blocks.size(), [&](size_t i) {
+        static thread_local std::vector<uint8_t> cbuf;
         const Block &k = blocks[i];
-        if (k.isize && !inflate_block(b->f.p + k.coff + k.data_off, k.bsize - k.data_off - 8, out + k.uoff, k.isize)) bad = 1;
+        if (!k.isize) return;
+        if (cbuf.size() < k.bsize) cbuf.resize(65536 + 64);
+        const ssize_t got = pread(b->f.fd, cbuf.data(), k.bsize, (off_t) k.coff);
+        const uint8_t *src = (got == (ssize_t) k.bsize) ? cbuf.data() : b->f.p + k.coff;
+        if (!inflate_block(src + k.data_off, k.bsize - k.data_off - 8, out + k.uoff, k.isize)) bad = 1;
     });
     if (bad) { set_error("BGZF inflate failed"); return PB_ERR_ARG; }
     for (auto &k : blocks) { b->n_compressed += (int64_t) k.bsize; b->n_inflated += k.isize; }
@@ -286,6 +335,7 @@ extern "C" int pb_bam_open(pb_bam_t **out, const char *path, int n_threads) {
     auto *b = new pb_bam();
     if (!b->f.open(path)) { delete b; set_error("cannot open BAM file %s", path); return PB_ERR_ARG; }
     b->n_threads = n_threads > 0 ? n_threads : (int) std::max(1u, std::thread::hardware_concurrency());
+    b->pool = new Pool(b->n_threads - 1);
     int ndev = 0;
     b->pinned = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
     if (!b->pinned) cudaGetLastError();
@@ -300,7 +350,7 @@ extern "C" int pb_bam_open(pb_bam_t **out, const char *path, int n_threads) {
         }
         rc = load_bai(b, bai.c_str());
     }
-    if (rc != PB_OK) { b->f.close(); delete b; return rc; }
+    if (rc != PB_OK) { b->f.close(); delete b->pool; delete b; return rc; }
     *out = b;
     return PB_OK;
 }
@@ -310,6 +360,7 @@ extern "C" int pb_bam_close(pb_bam_t *b) {
     HostBuf *bufs[] = {&b->o_pos, &b->o_seq_off, &b->o_cigar_off, &b->o_flag, &b->o_mapq, &b->o_seq, &b->o_qual, &b->o_cigar};
     for (auto *x : bufs) x->release();
     b->f.close();
+    delete b->pool;
     delete b;
     return PB_OK;
 }
@@ -412,7 +463,7 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
                 struct Parsed { uint32_t n_cigar; size_t cigar_off; uint8_t keep; };
                 std::vector<Parsed> parsed(cand.size());
                 const size_t pgrain = 256;
-                parallel_for(b->n_threads, (cand.size() + pgrain - 1) / pgrain, [&](size_t g) {
+                b->pool->run((cand.size() + pgrain - 1) / pgrain, [&](size_t g) {
                     for (size_t ii = g * pgrain; ii < std::min(cand.size(), (g + 1) * pgrain); ii++) {
                         const size_t p = cand[ii];
                         const uint32_t bs = rd32(u.data() + p);
@@ -487,7 +538,7 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
     auto seq_of = [&](int64_t i) { const uint8_t *r = u + recs[i].off; return r + 32 + r[8] + 4 * (size_t) rd16(r + 12); };
     auto code_at = [](const uint8_t *s, int64_t k) { return (k & 1) ? (s[k >> 1] & 15) : (s[k >> 1] >> 4); };
     const size_t grain = 64;
-    parallel_for(b->n_threads, ((size_t) n + grain - 1) / grain, [&](size_t g) {
+    b->pool->run(((size_t) n + grain - 1) / grain, [&](size_t g) {
         for (int64_t i = (int64_t) (g * grain); i < std::min<int64_t>(n, (int64_t) ((g + 1) * grain)); i++) {
             const uint8_t *r = u + recs[i].off;
             o_pos[i] = rpos[i];

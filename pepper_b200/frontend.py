@@ -40,13 +40,14 @@ class _FromFiles:
         self.device = device
 
     def _ref_table(self, contig: str, rows: list[list[int]], spans: list[tuple[int, int]]) -> RegionTable:
-        refs, off = [], 0
+        """Region table + reference strings: ONE faidx fetch of the covering span, the (overlapping) per-region strings are
+        offsets into it (get_reference_sequence clamps at the contig end; so do the lengths here)."""
+        lo, hi = min(a for a, _ in spans), max(b for _, b in spans)
+        ref = self.fasta.fetch_array(contig, lo, hi)
+        clen = self.fasta.get_chromosome_sequence_length(contig)
         for row, (a, b) in zip(rows, spans):
-            r = self.fasta.fetch_array(contig, a, b)
-            row[4], row[5] = off, int(r.shape[0])
-            refs.append(r)
-            off += int(r.shape[0])
-        return RegionTable(np.array(rows, dtype=np.int64).reshape(-1, 8), np.concatenate(refs) if refs else np.zeros(1, np.uint8))
+            row[4], row[5] = a - lo, max(0, min(b, clen) - a)
+        return RegionTable(np.array(rows, dtype=np.int64).reshape(-1, 8), ref if ref.shape[0] else np.zeros(1, np.uint8))
 
 
 class VariantFromFiles(_FromFiles):
@@ -58,7 +59,7 @@ class VariantFromFiles(_FromFiles):
 
     def call(self, contig: str, intervals: list[tuple[int, int]], params: dict, include_supplementary: bool = False,
              min_mapq: int = 0, downsample_rate: float = 1.0, max_reads: int = VARIANT_MAX_READS,
-             capacity: int | None = None) -> tuple[VariantCalls, RegionTable]:
+             capacity: int | None = None, want_images: bool = True, _view=None) -> tuple[VariantCalls, RegionTable]:
         import torch
         if not intervals:
             raise ValueError("no intervals")
@@ -69,7 +70,7 @@ class VariantFromFiles(_FromFiles):
             rows.append([rs, re_, s, e, 0, 0, 0, 0])
             spans.append((rs, re_ + 1))                                             # get_reference_sequence(.., region_end + 1)
         regions = self._ref_table(contig, rows, spans)
-        view = self.bam.fetch(contig, min(q[0] for q in queries), max(q[1] for q in queries))
+        view = _view if _view is not None else self.bam.fetch(contig, min(q[0] for q in queries), max(q[1] for q in queries))
         got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
                                      max_reads=max_reads, downsample_rate=downsample_rate)
         fetched = FetchedReads(got, regions, self.device)
@@ -87,8 +88,35 @@ class VariantFromFiles(_FromFiles):
                 if "code -3" not in str(ex):
                     raise
                 cap *= 2
-        h = {k: v[:n].cpu().numpy() for k, v in out.items()}
-        return VariantCalls(h["positions"], h["depths"], h["freqs"], h["keys"], h["region_of"], h["probs"], h["images"]), fetched_table(fetched, regions)
+        h = {k: v[:n].cpu().numpy() for k, v in out.items() if want_images or k != "images"}
+        return VariantCalls(h["positions"], h["depths"], h["freqs"], h["keys"], h["region_of"], h["probs"], h.get("images")), fetched_table(fetched, regions)
+
+
+    def call_batches(self, contig: str, intervals: list[tuple[int, int]], params: dict, batch: int = 32, **kw):
+        """Streaming form: yields (VariantCalls, RegionTable) per batch of `batch` intervals while a helper thread inflates the next
+        batch's BAM span with a second reader (pb_bam_fetch runs outside the GIL), so the host inflate overlaps the GPU work."""
+        import threading
+        if not hasattr(self, "_bam2"):
+            self._bam2 = BamReader(self.bam.path, 0)
+        readers = [self.bam, self._bam2]
+        groups = [intervals[i:i + batch] for i in range(0, len(intervals), batch)]
+
+        def span(g):
+            return max(0, min(s for s, _ in g) - REGION_SAFE_BASES), max(e for _, e in g) + REGION_SAFE_BASES
+
+        box = {}
+
+        def prefetch(k):
+            box[k] = readers[k & 1].fetch(contig, *span(groups[k]))
+        th = threading.Thread(target=prefetch, args=(0,))
+        th.start()
+        for k, g in enumerate(groups):
+            th.join()
+            view = box.pop(k)
+            if k + 1 < len(groups):
+                th = threading.Thread(target=prefetch, args=(k + 1,))
+                th.start()
+            yield self.call(contig, g, params, _view=view, **kw)
 
 
 class PolishFromFiles(_FromFiles):

@@ -88,3 +88,18 @@ def test_polish_from_files(oracle_built, files):
     s_or = oracle_built.polish_encode(realigned, otab, "port")
     assert np.array_equal(s_gpu.image, s_or["image"])
     pc.close()
+
+
+def test_variant_batches_equal_single_call(files):
+    from pepper_b200 import weights
+    from pepper_b200.frontend import VariantFromFiles, variant_intervals
+    params = synth.ont_params()
+    iv = variant_intervals(1000, 25000, 4000)
+    vf = VariantFromFiles(files["bam"], files["fa"], weights.random_variant_state(0))
+    whole, _ = vf.call("ctg", iv, params)
+    parts = list(vf.call_batches("ctg", iv, params, batch=2))
+    assert len(parts) == 3
+    assert np.array_equal(np.concatenate([p[0].positions for p in parts]), whole.positions)
+    assert sum((p[0].keys for p in parts), []) == whole.keys
+    assert np.array_equal(np.concatenate([p[0].images for p in parts]), whole.images)
+    assert np.abs(np.concatenate([p[0].probs for p in parts]) - whole.probs).max() < 1e-5
