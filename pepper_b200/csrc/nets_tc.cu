@@ -142,6 +142,32 @@ int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, flo
         PB_CUDA(cudaMemsetAsync(T.c.p, 0, sizeof(float) * 2 * VH * Bp, st));
         bf16 *y_hi = layer == 0 ? T.yenc_hi.as<bf16>() : T.ydec_hi.as<bf16>();
         bf16 *y_lo = layer == 0 ? T.yenc_lo.as<bf16>() : T.ydec_lo.as<bf16>();
+        static const bool persist = !(getenv("PB_LSTM_PERSIST") && atoi(getenv("PB_LSTM_PERSIST")) == 0);
+        if (persist) {
+            // one launch per layer: every CTA keeps its (direction, row tile) for all 33 steps (k_lstm_layer)
+            tc::LstmLayer L;
+            memset(&L, 0, sizeof(L));
+            if (layer == 0) { L.x_hi = T.img_op.as<bf16>(); L.x_lo = nullptr; L.x_mt_stride = (int64_t) VT * TILE_ELEMS; L.x_nkt = 1; }
+            else { L.x_hi = T.yenc_hi.as<bf16>(); L.x_lo = T.yenc_lo.as<bf16>(); L.x_mt_stride = (int64_t) VT * 16 * TILE_ELEMS; L.x_nkt = 16; }
+            for (int d = 0; d < 2; d++) {
+                TcRnn &W = layer == 0 ? T.enc[d] : T.dec[d];
+                L.w_hi[d] = W.w_hi.as<bf16>(); L.w_lo[d] = W.w_lo.as<bf16>();
+                L.bias[d] = (layer == 0 ? N->enc[d] : N->dec[d]).bias.as<float>();
+                L.c[d] = T.c.as<float>() + (int64_t) d * VH * Bp;
+                if (W.nkt_x != L.x_nkt || W.nkt_h != 8) { set_error("unexpected packed LSTM weight shape"); return PB_ERR_STATE; }
+            }
+            L.y_hi = y_hi; L.y_lo = y_lo; L.y_mt_stride = (int64_t) VT * 16 * TILE_ELEMS;
+            if (layer == 1 && d_hidden_dbg) { L.y_f32 = d_hidden_dbg; L.ldy = (int64_t) VT * 512; }
+            L.M = (int) B; L.n_mt = (int) Mt; L.T = VT; L.c_ld = Bp;
+            static bool attr_set = false;
+            if (!attr_set) {
+                PB_CUDA(cudaFuncSetAttribute(tc::k_lstm_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSMEM_BYTES));
+                attr_set = true;
+            }
+            tc::k_lstm_layer<<<(unsigned) (2 * Mt), tc::PG_THREADS, tc::PSMEM_BYTES, st>>>(L);
+            N->launches++;
+            continue;
+        }
         for (int t = 0; t < VT; t++) {
             Args A;
             A.M = (int) B; A.N = 4 * VH; A.c_ld = Bp;

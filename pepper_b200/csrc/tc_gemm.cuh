@@ -546,6 +546,199 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_tc_gemm_p(Args G, int n_mt, i
     }
 }
 
+// ---------------------------------------------------------------- persistent LSTM layer kernel (variant)
+// All T time steps of one bidirectional LSTM layer in ONE launch.  CTA b owns (direction, 128-candidate row tile) for the
+// whole sequence and computes all four 256-column gate tiles of every step itself, so the recurrence never leaves the
+// CTA: the epilogue writes h_t as bf16 hi/lo operand tiles into the layer's output sequence, arrives on a CTA-local
+// mbarrier, and the producer thread loads those tiles back as the h-part of step t+1 (generic -> async proxy fence in
+// between).  The x-part of step t+1 (1 k-tile for the encoder layer, 16 for the decoder layer) does not depend on h_t and
+// is streamed / multiplied while the last epilogue of step t drains; the TMEM accumulator stays double buffered across
+// tiles and steps.  One chunk of 9,472 candidates = 74 row tiles x 2 directions = 148 CTAs = one per SM; 33 x fewer
+// launches, prologues and tails than the per-step kernel above (kept as the cross-check path).
+struct LstmLayer {
+    const __nv_bfloat16 *x_hi, *x_lo;           // input sequence operand: tile (mt, t, kt) at mt * x_mt_stride + (t * x_nkt + kt) * TILE_ELEMS
+    int64_t x_mt_stride;
+    int x_nkt;
+    const __nv_bfloat16 *w_hi[2], *w_lo[2];     // per direction: [4 n-tiles][x_nkt + 8][WTILE_ELEMS]
+    const float *bias[2];
+    float *c[2];                                // cell state per direction [256][c_ld], zero initialised
+    __nv_bfloat16 *y_hi, *y_lo;                 // output sequence operand [mt][T][16] tiles; (time tt, direction d) -> k-tiles tt * 16 + d * 8 ...
+    int64_t y_mt_stride;
+    float *y_f32;                               // optional fp32 copy [row][T][512]
+    int64_t ldy;
+    int M, n_mt, T;
+    int64_t c_ld;
+};
+
+__global__ void __launch_bounds__(PG_THREADS, 1) k_lstm_layer(LstmLayer G) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PSTAGES * PSTAGE_BYTES);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + PSTAGES);
+    const uint32_t bar_accf = smem_u32(bars + 2 * PSTAGES), bar_acce = smem_u32(bars + 2 * PSTAGES + 2);
+    const uint32_t bar_h = smem_u32(bars + 2 * PSTAGES + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * PSTAGES + 5);
+    const uint32_t smem_base = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.x / G.n_mt, mt = blockIdx.x % G.n_mt;
+    const int w_nkt = G.x_nkt + 8;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PSTAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, PG_EPI_WARPS); }
+        mbar_init(bar_h, PG_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) PTMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = 0; t < G.T; t++) {
+                const int tt = dir ? G.T - 1 - t : t, tp = dir ? tt + 1 : tt - 1;
+                const int nkt = G.x_nkt + (t > 0 ? 8 : 0);
+                for (int nt = 0; nt < 4; nt++) {
+                    for (int kt = 0; kt < nkt; kt++, g++) {
+                        const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                        const __nv_bfloat16 *a_hi, *a_lo;
+                        if (kt < G.x_nkt) {
+                            const int64_t off = (int64_t) mt * G.x_mt_stride + ((int64_t) tt * G.x_nkt + kt) * TILE_ELEMS;
+                            a_hi = G.x_hi + off; a_lo = G.x_lo ? G.x_lo + off : nullptr;
+                        } else {
+                            const int kk = kt - G.x_nkt;
+                            if (kk == 0 && nt == 0) {
+                                // every epilogue warp has written its part of h_{t-1}: make it visible to the bulk-copy engine
+                                mbar_wait(bar_h, (uint32_t) (t - 1) & 1u);
+                                asm volatile("fence.proxy.async;" ::: "memory");
+                            }
+                            const int64_t off = (int64_t) mt * G.y_mt_stride + ((int64_t) tp * 16 + dir * 8 + kk) * TILE_ELEMS;
+                            a_hi = G.y_hi + off; a_lo = G.y_lo + off;
+                        }
+                        const uint32_t st = smem_base + s * PSTAGE_BYTES;
+                        mbar_expect_tx(bar_full + 8 * s, (a_lo ? 2u : 1u) * TILE_BYTES + 2u * WTILE_BYTES);
+                        bulk_g2s(st, a_hi, TILE_BYTES, bar_full + 8 * s);
+                        if (a_lo) bulk_g2s(st + TILE_BYTES, a_lo, TILE_BYTES, bar_full + 8 * s);
+                        const int64_t woff = ((int64_t) nt * w_nkt + kt) * WTILE_ELEMS;
+                        bulk_g2s(st + 2 * TILE_BYTES, G.w_hi[dir] + woff, WTILE_BYTES, bar_full + 8 * s);
+                        bulk_g2s(st + 2 * TILE_BYTES + WTILE_BYTES, G.w_lo[dir] + woff, WTILE_BYTES, bar_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t g = 0, it = 0;
+            for (int t = 0; t < G.T; t++) {
+                const int nkt = G.x_nkt + (t > 0 ? 8 : 0);
+                for (int nt = 0; nt < 4; nt++, it++) {
+                    const uint32_t buf = it & 1u, use = it >> 1;
+                    mbar_wait(bar_acce + 8 * buf, (use & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + buf * PBN;
+                    for (int kt = 0; kt < nkt; kt++, g++) {
+                        const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
+                        mbar_wait(bar_full + 8 * s, ph);
+                        tc_fence_after();
+                        const bool has_lo = kt >= G.x_nkt || G.x_lo != nullptr;
+                        const uint32_t st = smem_base + s * PSTAGE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ks++) {
+                            const uint64_t a_hi = smem_desc_lbo(st + ks * 4096, 2048), a_lo = smem_desc_lbo(st + TILE_BYTES + ks * 4096, 2048);
+                            const uint64_t b_hi = smem_desc_lbo(st + 2 * TILE_BYTES + ks * 8192, 4096);
+                            const uint64_t b_lo = smem_desc_lbo(st + 2 * TILE_BYTES + WTILE_BYTES + ks * 8192, 4096);
+                            tc_mma(tacc, a_hi, b_hi, IDESC256, (kt > 0 || ks > 0) ? 1u : 0u);
+                            tc_mma(tacc, a_hi, b_lo, IDESC256, 1u);
+                            if (has_lo) tc_mma(tacc, a_lo, b_hi, IDESC256, 1u);
+                        }
+                        tc_commit(bar_empty + 8 * s);
+                    }
+                    tc_commit(bar_accf + 8 * buf);
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;                        // column group of this warp inside a 256-column tile
+        const int r128 = q * 32 + lane;
+        const int row = mt * BM + r128;
+        const bool valid = row < G.M;
+        float *cst = G.c[dir];
+        const float *bias = G.bias[dir];
+        uint32_t it = 0;
+        for (int t = 0; t < G.T; t++) {
+            const int tt = dir ? G.T - 1 - t : t;
+            const int y_kt0 = tt * 16 + dir * 8;
+            for (int nt = 0; nt < 4; nt++, it++) {
+                const uint32_t buf = it & 1u, use = it >> 1;
+                float st[PG_COLS / 4];
+                const int ubase = nt * (PBN / 4) + grp * (PG_COLS / 4);
+#pragma unroll
+                for (int u = 0; u < PG_COLS / 4; u++) st[u] = valid ? cst[(int64_t) (ubase + u) * G.c_ld + row] : 0.f;
+                mbar_wait(bar_accf + 8 * buf, use & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int cl = 0; cl < PG_COLS / 32; cl++) {
+                    const int cc = grp * (PG_COLS / 32) + cl;
+                    const int col0 = nt * PBN + cc * 32;
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + buf * PBN + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
+                    if (cl == PG_COLS / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+                    }
+                    const int j0 = col0 >> 2;
+                    float hn[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias + col0 + 4 * u));
+                        const float v0 = __uint_as_float(acc[4 * u + 0]) + bz.x, v1 = __uint_as_float(acc[4 * u + 1]) + bz.y;
+                        const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
+                        const float ig = sigm(v0), fg = sigm(v1), gg = tanh_fast(v2), og = sigm(v3);
+                        const float cn = fg * st[cl * 8 + u] + ig * gg;
+                        st[cl * 8 + u] = cn;
+                        hn[u] = og * tanh_fast(cn);
+                    }
+                    if (valid) {
+                        uint4 hi, lo;
+                        split8(hn, hi, lo);
+                        const int64_t o = (int64_t) mt * G.y_mt_stride + (int64_t) (y_kt0 + (j0 >> 5)) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                        *reinterpret_cast<uint4 *>(G.y_hi + o) = hi;
+                        *reinterpret_cast<uint4 *>(G.y_lo + o) = lo;
+                        if (G.y_f32) {
+                            float4 *dst = reinterpret_cast<float4 *>(G.y_f32 + (int64_t) row * G.ldy + (int64_t) tt * 512 + dir * 256 + j0);
+                            dst[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                            dst[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                        }
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int u = 0; u < PG_COLS / 4; u++) cst[(int64_t) (ubase + u) * G.c_ld + row] = st[u];
+                }
+                if (nt == 3) {
+                    // h_t of this warp's rows / columns is complete (all four gate tiles): publish it to the producer thread
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_h);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) PTMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- persistent GRU window kernel (polish)
 // All 100 time steps of one bidirectional GRU layer of one window in ONE launch.  CTA b owns tile
 // (dir, row tile mt, gate-column half nt) for every step; its sibling (same dir / mt, other half) produces the other 64
