@@ -240,19 +240,19 @@ def run_ours(args):
                     algorithmic_bytes_per_launch=alg_bytes, launch_ms=count_s * 1e3,
                     note="algorithmic bytes of the whole encoder (SURVEY 8d) over the pileup-count kernel's time")
     tf = n_cand * FLOP_PER_CAND / net_s / 1e12
-    roof_net = dict(bound="tensor", kernel="k_tc_gemm (tcgen05 LSTM-step / MLP GEMMs, all launches of the step; 3 bf16 products per algorithmic FLOP)", achieved=tf,
+    roof_net = dict(bound="tensor", kernel="k_lstm_layer + k_tc_gemm_p (tcgen05 LSTM layers / MLP GEMMs, all launches of the step; 3 bf16 products per algorithmic FLOP)", achieved=tf,
                     peak=peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], unit="TFLOP/s",
                     frac=tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
-                    traffic=int(n_cand / 9472.0 * (33 * (43.83e6 + 91.20e6) + 678.66e6)),
-                    traffic_note="dram__bytes_read+write of the ncu --set full captures (encoder LSTM step 43.8 MB, decoder LSTM step 91.2 MB, "
-                                 "linear_1 678.7 MB per launch at a 9,472-candidate chunk; profiles/r1_prof_tcp_*_final_raw.csv) summed over the "
-                                 "launches of this step (33 + 33 + 1 per chunk)",
+                    traffic=int(n_cand * (237.36e6 / 3840 + 767.39e6 / 3840 + 678.66e6 / 9472)),
+                    traffic_note="dram__bytes_read+write of the ncu --set full captures, per candidate: encoder LSTM layer (k_lstm_layer) 237.4 MB and "
+                                 "decoder LSTM layer 767.4 MB per launch over 3,840 candidates, linear_1 678.7 MB per launch over 9,472 "
+                                 "(profiles/r1_prof_lstm_*_raw.csv, r1_prof_tcp_lin1_final_raw.csv), scaled to the candidates of this step",
                     peak_source=peaks["source"] + ", sustained bf16",
                     flops_per_step=n_cand * FLOP_PER_CAND, step_ms=net_s * 1e3,
                     executed_bf16_tflops=3 * tf, executed_frac=3 * tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
                     note="achieved = fp32-equivalent algorithmic FLOPs (161.4 MFLOP per candidate) / network time; every FLOP is "
                          "executed as three bf16 tensor-core products (hi/lo split), so the tensor pipe runs at executed_frac; "
-                         "ncu: linear_1 launch 94.5 % tensor-pipe active, decoder LSTM step 79.8 %, encoder LSTM step 47.8 % (profiles/README.md)")
+                         "ncu: decoder LSTM layer 92.8 % tensor-pipe active, encoder LSTM layer 59.1 %, linear_1 94.5 % (profiles/README.md); the step runs under the board power cap (clocks.reasons)")
 
     line = {
         "metric": "genomic bases/sec (make_images+inference)", "value": value, "unit": "bases/s", "n_gpus": world,
