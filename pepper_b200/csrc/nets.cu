@@ -13,6 +13,7 @@
 //  * polish: Linear(256->5) + softmax + window accumulate is one warp-per-column kernel per window, argmax +
 //    phred one kernel at the end (predict_distributed_cpu.py:77-90).
 #include "handles.cuh"
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 #include <math.h>
@@ -637,7 +638,9 @@ extern "C" int pb_polish_net_forward_device(pb_polish_net_t *N, const uint8_t *d
     if (N->mode == 1) {
         int sms = 0;
         PB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, N->device));
-        chunk = std::max<int64_t>(1, sms / 4) * 128;
+        // k_gru_layer: one CTA per (direction, row tile) -> sms / 2 row tiles fill the GPU; the pair kernels need 4 CTAs per row tile
+        const bool layer = !(getenv("PB_GRU_LAYER") && atoi(getenv("PB_GRU_LAYER")) == 0);
+        chunk = std::max<int64_t>(1, sms / (layer ? 2 : 4)) * 128;
     }
     for (int64_t b0 = 0; b0 < n; b0 += chunk) {
         const int64_t B = std::min(chunk, n - b0);

@@ -335,7 +335,13 @@ static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi
     G.y_hi = y_hi; G.y_lo = y_lo; G.flags = T.flags.as<int>();
     G.M = (int) B; G.n_mt = (int) Mt; G.T = PWIN;
     if (W[0].nkt_x != xkt || W[0].nkt_h != 4) { set_error("gru_layer_tc: weight / operand k-tile mismatch"); return PB_ERR_STATE; }
-    if (use_cluster) {
+    static const bool use_layer = !(getenv("PB_GRU_LAYER") && atoi(getenv("PB_GRU_LAYER")) == 0);
+    if (use_layer) {
+        static bool la = false;
+        if (!la) { PB_CUDA(cudaFuncSetAttribute(tc::k_gru_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSMEM_BYTES)); la = true; }
+        tc::k_gru_layer<<<(unsigned) (2 * Mt), tc::PG_THREADS, tc::PSMEM_BYTES, st>>>(G);    // one CTA per (direction, row tile), no h exchange
+        PB_CUDA(cudaGetLastError());
+    } else if (use_cluster) {
         tc::k_gru_cluster<<<(unsigned) (4 * Mt), tc::THREADS, tc::CSMEM_BYTES, st>>>(G);      // clusters of 2 CTAs (__cluster_dims__)
         PB_CUDA(cudaGetLastError());
     } else {

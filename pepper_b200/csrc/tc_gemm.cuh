@@ -1136,6 +1136,184 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gru_cl
     }
 }
 
+// ---------------------------------------------------------------- persistent GRU layer kernel, one CTA per (direction, row tile)
+// Same ownership as k_lstm_layer: the CTA computes both 256-column gate tiles (128 hidden units x {r, z, n_x, n_h}) of every
+// step, so h never has to be exchanged with a sibling CTA (k_gru_cluster / k_gru_window split the hidden units over a CTA
+// pair).  h_t goes out as operand tiles of the layer's output sequence and comes back through the bulk-copy ring as the
+// h-part of step t+1; the previous hidden values of the cell update are re-read from those tiles (L2).  Step 0 takes h0.
+__global__ void __launch_bounds__(PG_THREADS, 1) k_gru_layer(GruWin G) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PSTAGES * PSTAGE_BYTES);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + PSTAGES);
+    const uint32_t bar_accf = smem_u32(bars + 2 * PSTAGES), bar_acce = smem_u32(bars + 2 * PSTAGES + 2);
+    const uint32_t bar_h = smem_u32(bars + 2 * PSTAGES + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * PSTAGES + 5);
+    const uint32_t smem_base = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.x / G.n_mt, mt = blockIdx.x % G.n_mt;
+    const int nkt = G.x_kt + 4;
+    const int64_t seq_stride = (int64_t) G.T * 8 * TILE_ELEMS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PSTAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, PG_EPI_WARPS); }
+        mbar_init(bar_h, PG_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) PTMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = 0; t < G.T; t++) {
+                const int tt = dir ? G.T - 1 - t : t, tp = dir ? tt + 1 : tt - 1;
+                for (int nt = 0; nt < 2; nt++) {
+                    for (int kt = 0; kt < nkt; kt++, g++) {
+                        const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                        const __nv_bfloat16 *a_hi, *a_lo;
+                        if (kt < G.x_kt) {
+                            const int64_t off = ((int64_t) (mt * G.T + tt) * G.x_kt + kt) * TILE_ELEMS;
+                            a_hi = G.x_hi + off; a_lo = G.x_lo ? G.x_lo + off : nullptr;
+                        } else {
+                            const int kk = kt - G.x_kt;
+                            if (t == 0) {
+                                const int64_t off = (int64_t) mt * G.h0_mt_stride + (int64_t) kk * TILE_ELEMS;
+                                a_hi = G.h0_hi[dir] + off; a_lo = G.h0_lo[dir] + off;
+                            } else {
+                                if (kk == 0 && nt == 0) {
+                                    mbar_wait(bar_h, (uint32_t) (t - 1) & 1u);      // every epilogue warp has written its part of h_{t-1}
+                                    asm volatile("fence.proxy.async;" ::: "memory");
+                                }
+                                const int64_t off = (int64_t) mt * seq_stride + ((int64_t) tp * 8 + dir * 4 + kk) * TILE_ELEMS;
+                                a_hi = G.y_hi + off; a_lo = G.y_lo + off;
+                            }
+                        }
+                        const uint32_t st = smem_base + s * PSTAGE_BYTES;
+                        mbar_expect_tx(bar_full + 8 * s, (a_lo ? 2u : 1u) * TILE_BYTES + 2u * WTILE_BYTES);
+                        bulk_g2s(st, a_hi, TILE_BYTES, bar_full + 8 * s);
+                        if (a_lo) bulk_g2s(st + TILE_BYTES, a_lo, TILE_BYTES, bar_full + 8 * s);
+                        const int64_t woff = ((int64_t) nt * nkt + kt) * WTILE_ELEMS;
+                        bulk_g2s(st + 2 * TILE_BYTES, G.w_hi[dir] + woff, WTILE_BYTES, bar_full + 8 * s);
+                        bulk_g2s(st + 2 * TILE_BYTES + WTILE_BYTES, G.w_lo[dir] + woff, WTILE_BYTES, bar_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t g = 0, it = 0;
+            for (int t = 0; t < G.T; t++) {
+                for (int nt = 0; nt < 2; nt++, it++) {
+                    const uint32_t buf = it & 1u, use = it >> 1;
+                    mbar_wait(bar_acce + 8 * buf, (use & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + buf * PBN;
+                    for (int kt = 0; kt < nkt; kt++, g++) {
+                        const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
+                        mbar_wait(bar_full + 8 * s, ph);
+                        tc_fence_after();
+                        const bool has_lo = kt >= G.x_kt || G.x_lo != nullptr;
+                        const uint32_t st = smem_base + s * PSTAGE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ks++) {
+                            const uint64_t a_hi = smem_desc_lbo(st + ks * 4096, 2048), a_lo = smem_desc_lbo(st + TILE_BYTES + ks * 4096, 2048);
+                            const uint64_t b_hi = smem_desc_lbo(st + 2 * TILE_BYTES + ks * 8192, 4096);
+                            const uint64_t b_lo = smem_desc_lbo(st + 2 * TILE_BYTES + WTILE_BYTES + ks * 8192, 4096);
+                            tc_mma(tacc, a_hi, b_hi, IDESC256, (kt > 0 || ks > 0) ? 1u : 0u);
+                            tc_mma(tacc, a_hi, b_lo, IDESC256, 1u);
+                            if (has_lo) tc_mma(tacc, a_lo, b_hi, IDESC256, 1u);
+                        }
+                        tc_commit(bar_empty + 8 * s);
+                    }
+                    tc_commit(bar_accf + 8 * buf);
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const int r128 = q * 32 + lane;
+        const int row = mt * BM + r128;
+        const bool valid = row < G.M;
+        const float *bias = G.bias[dir];
+        uint32_t it = 0;
+        for (int t = 0; t < G.T; t++) {
+            const int tt = dir ? G.T - 1 - t : t, tp = dir ? tt + 1 : tt - 1;
+            for (int nt = 0; nt < 2; nt++, it++) {
+                const uint32_t buf = it & 1u, use = it >> 1;
+                const int ubase = nt * (PBN / 4) + grp * (PG_COLS / 4);
+                // previous hidden values of this thread's units (own writes of step t-1, or h0)
+                float hp[PG_COLS / 4];
+#pragma unroll
+                for (int u8 = 0; u8 < PG_COLS / 32; u8++) {
+                    uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+                    if (valid) {
+                        const int j0 = ubase + u8 * 8;
+                        const int64_t rel = (int64_t) (j0 >> 5) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                        const int64_t o = t == 0 ? (int64_t) mt * G.h0_mt_stride + rel : (int64_t) mt * seq_stride + ((int64_t) tp * 8 + dir * 4) * TILE_ELEMS + rel;
+                        h = *reinterpret_cast<const uint4 *>((t == 0 ? G.h0_hi[dir] : G.y_hi) + o);
+                        l = *reinterpret_cast<const uint4 *>((t == 0 ? G.h0_lo[dir] : G.y_lo) + o);
+                    }
+                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                    for (int e = 0; e < 8; e++)
+                        hp[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+                }
+                mbar_wait(bar_accf + 8 * buf, use & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int cl = 0; cl < PG_COLS / 32; cl++) {
+                    const int cc = grp * (PG_COLS / 32) + cl;
+                    const int col0 = nt * PBN + cc * 32;
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + buf * PBN + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
+                    if (cl == PG_COLS / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+                    }
+                    const int j0 = col0 >> 2;
+                    float hn[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias + col0 + 4 * u));
+                        const float v0 = __uint_as_float(acc[4 * u + 0]) + bz.x, v1 = __uint_as_float(acc[4 * u + 1]) + bz.y;
+                        const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
+                        const float r = sigm(v0), z = sigm(v1);
+                        const float n = tanh_fast(v2 + r * v3);
+                        hn[u] = (1.0f - z) * n + z * hp[cl * 8 + u];
+                    }
+                    if (valid) {
+                        uint4 hi, lo;
+                        split8(hn, hi, lo);
+                        const int64_t o = (int64_t) mt * seq_stride + ((int64_t) tt * 8 + dir * 4 + (j0 >> 5)) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
+                        *reinterpret_cast<uint4 *>(G.y_hi + o) = hi;
+                        *reinterpret_cast<uint4 *>(G.y_lo + o) = lo;
+                    }
+                }
+                if (nt == 1) {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_h);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) PTMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- operand preparation kernels
 // int8 images [B][T][F] -> tiled operand [mt][T][1 k-tile] (hi only; |v| <= 128 is exact in bf16)
 __global__ void k_tc_pack_images(const int8_t *__restrict__ img, __nv_bfloat16 *__restrict__ op, int64_t B, int T, int F) {
