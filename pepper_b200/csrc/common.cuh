@@ -83,17 +83,23 @@ __device__ __forceinline__ int nt16_code_of_rank(int rank) {
 __device__ __forceinline__ bool is_upper_acgt(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 __device__ __forceinline__ char to_upper(char c) { return (c >= 'a' && c <= 'z') ? (char) (c - 32) : c; }
 // ------------------------------------------------------------------ single-CTA exclusive scan (n <= a few 1e6)
+// out[i] = sum(in[0..i)), out[n] = total (also *total).  Each thread scans 8 consecutive elements per round, so one round of
+// the 1024-thread block covers 8192 inputs with two block barriers.
 static __global__ void k_scan_excl(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n, int64_t *__restrict__ total) {
+    constexpr int PER = 8;
     __shared__ int64_t s_warp[32];
     __shared__ int64_t s_carry, s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = (int) (blockDim.x >> 5);
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int64_t b = 0; b < n; b += blockDim.x) {
-        const int64_t i = b + tid;
-        const int64_t v = (i < n) ? (int64_t) in[i] : 0;
-        int64_t inc = v;
+    for (int64_t b = 0; b < n; b += (int64_t) blockDim.x * PER) {
+        const int64_t i0 = b + (int64_t) tid * PER;
+        int32_t v[PER];
+        int64_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; mine += v[k]; }
+        int64_t inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int64_t u = __shfl_up_sync(0xffffffffu, inc, d);
@@ -113,7 +119,9 @@ static __global__ void k_scan_excl(const int32_t *__restrict__ in, int64_t *__re
             if (lane == 31) s_total = winc;
         }
         __syncthreads();
-        if (i < n) out[i] = s_carry + s_warp[warp] + inc - v;
+        int64_t run = s_carry + s_warp[warp] + inc - mine;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
         __syncthreads();
         if (tid == 0) s_carry += s_total;
         __syncthreads();
