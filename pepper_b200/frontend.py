@@ -159,6 +159,28 @@ class PolishFromFiles(_FromFiles):
         return PolishCalls(h["bases"], h["phred"], h["position"], h["index"], h["image_region"], h["chunk_id"]), fetched_table(fetched, regions)
 
 
+def _polish_contig(self, contig: str, start: int = 0, end: int | None = None, batch: int = 2000, realign: bool = True,
+                   return_calls: bool = False):
+    """The whole polish path of one contig span: tiling (ImageGenerationUI.py:262-272: the span is [start, length - 1]),
+    make_images + call_consensus in batches of `batch` regions, then the stitch (Stitch.py:36-128) -> polished sequence."""
+    from .polish import stitch
+    if end is None:
+        end = self.fasta.get_chromosome_sequence_length(contig) - 1
+    regs = polish_intervals(start, end)
+    parts = []
+    for i in range(0, len(regs), batch):
+        calls, _ = self.call(contig, regs[i:i + batch], realign=realign)
+        parts.append((calls, i))
+    cat = lambda f: np.concatenate([getattr(c, f) for c, _ in parts])       # noqa: E731
+    image_region = np.concatenate([c.image_region + off for c, off in parts]).astype(np.int32)
+    allc = PolishCalls(cat("bases"), cat("phred"), cat("position"), cat("index"), image_region, cat("chunk_id"))
+    seq = stitch(allc.bases, allc.position, allc.index, allc.image_region, allc.chunk_id, np.array([r[0] for r in regs], dtype=np.int64))
+    return (seq, allc, regs) if return_calls else seq
+
+
+PolishFromFiles.polish_contig = _polish_contig
+
+
 def fetched_table(fetched: FetchedReads, regions: RegionTable) -> RegionTable:
     """The region table with the read ranges get_reads produced (after down-sampling)."""
     return RegionTable(fetched.table.copy(), regions.ref)

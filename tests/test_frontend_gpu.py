@@ -103,3 +103,18 @@ def test_variant_batches_equal_single_call(files):
     assert sum((p[0].keys for p in parts), []) == whole.keys
     assert np.array_equal(np.concatenate([p[0].images for p in parts]), whole.images)
     assert np.abs(np.concatenate([p[0].probs for p in parts]) - whole.probs).max() < 1e-5
+
+
+def test_polish_contig_from_files_to_consensus(files):
+    """files -> tiling -> get_reads -> realign -> encoder -> GRU -> stitch, in batches, equals the oracle stitch of the same calls
+    and does not depend on the batch size."""
+    from oracle import stitch as ostitch
+    from pepper_b200 import weights
+    from pepper_b200.frontend import PolishFromFiles
+    pf = PolishFromFiles(files["bam"], files["fa"], weights.random_polish_state(1))
+    seq, calls, regs = pf.polish_contig("ctg", 2000, 9999, batch=3, return_calls=True)
+    starts = np.array([r[0] for r in regs], dtype=np.int64)
+    ends = np.array([r[1] for r in regs], dtype=np.int64)
+    want = ostitch.stitch(calls.bases, calls.position, calls.index, calls.image_region, calls.chunk_id, starts, ends)
+    assert seq == want and len(seq) > 6000
+    assert pf.polish_contig("ctg", 2000, 9999, batch=100) == seq
