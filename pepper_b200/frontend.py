@@ -92,6 +92,14 @@ class VariantFromFiles(_FromFiles):
         return VariantCalls(h["positions"], h["depths"], h["freqs"], h["keys"], h["region_of"], h["probs"], h.get("images")), fetched_table(fetched, regions)
 
 
+    def find_candidates(self, contig: str, intervals: list[tuple[int, int]], params: dict, options: dict | None = None, **kw):
+        """make_images + run_inference + the per-record candidate selection of find_candidates (CandidateFinder.py:356-530):
+        returns (margin_records, deepvariant_records) in the tuple layouts VcfWriter consumes."""
+        from .candidates import find_candidates, ONT_OPTIONS
+        calls, table = self.call(contig, intervals, params, want_images=False, **kw)
+        return find_candidates(contig, calls.positions, calls.region_of, calls.depths, calls.freqs, calls.keys_raw, calls.probs, table,
+                               options or ONT_OPTIONS)
+
     def call_batches(self, contig: str, intervals: list[tuple[int, int]], params: dict, batch: int = 32, **kw):
         """Streaming form: yields (VariantCalls, RegionTable) per batch of `batch` intervals while a helper thread inflates the next
         batch's BAM span with a second reader (pb_bam_fetch runs outside the GIL), so the host inflate overlaps the GPU work."""

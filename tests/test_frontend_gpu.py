@@ -118,3 +118,22 @@ def test_polish_contig_from_files_to_consensus(files):
     want = ostitch.stitch(calls.bases, calls.position, calls.index, calls.image_region, calls.chunk_id, starts, ends)
     assert seq == want and len(seq) > 6000
     assert pf.polish_contig("ctg", 2000, 9999, batch=100) == seq
+
+
+def test_variant_files_to_vcf_records(oracle_built, files):
+    """BAM + FASTA -> candidates -> LSTM -> candidate selection == the oracle selection on the same prediction records."""
+    from oracle import nets, find_candidates as ofc
+    from pepper_b200.candidates import ONT_OPTIONS
+    from pepper_b200.frontend import VariantFromFiles, variant_intervals
+    from tests.test_candidates import _norm
+    params = synth.ont_params()
+    iv = variant_intervals(2000, 24000, 8000)
+    vf = VariantFromFiles(files["bam"], files["fa"], nets.make_variant_weights(2))
+    opts = dict(ONT_OPTIONS); opts["report_indel_above_freq"] = 0.5
+    m, d = vf.find_candidates("ctg", iv, params, opts)
+    calls, _ = vf.call("ctg", iv, params, want_images=False)
+    gs = files["genome"].tobytes().decode()
+    wm, wd = ofc.select(opts, "ctg", calls.positions, calls.depths, calls.keys, calls.freqs, calls.probs, lambda c, a, b: gs[max(0, a):max(0, b)])
+    assert [_norm(r) for r in m] == [_norm(r) for r in wm]
+    assert [_norm(r) for r in d] == [_norm(r) for r in wd]
+    assert len(d) > 10
