@@ -192,3 +192,26 @@ PolishFromFiles.polish_contig = _polish_contig
 def fetched_table(fetched: FetchedReads, regions: RegionTable) -> RegionTable:
     """The region table with the read ranges get_reads produced (after down-sampling)."""
     return RegionTable(fetched.table.copy(), regions.ref)
+
+
+# ---------------------------------------------------------------------------------------------- prediction stores
+def write_variant_predictions(store, contig: str, calls: VariantCalls, batch_size: int = 512, first_batch: int = 0) -> int:
+    """What run_inference leaves on disk: predictions/batch_<n>/... in batches of `batch_size` candidates
+    (pepper_variant predict_distributed_gpu.py:58-70 -> DataStorePredict.write_prediction).  Returns the next batch number."""
+    keys = calls.keys
+    b = first_batch
+    for lo in range(0, len(calls), batch_size):
+        hi = min(len(calls), lo + batch_size)
+        store.write_prediction(b, [contig] * (hi - lo), calls.positions[lo:hi], calls.depths[lo:hi], keys[lo:hi], calls.freqs[lo:hi],
+                               calls.probs[lo:hi])
+        b += 1
+    return b
+
+
+def write_polish_predictions(store, contig: str, calls: PolishCalls, regions_se: list[tuple[int, int]]) -> None:
+    """What call_consensus leaves on disk: one predictions/<contig>/<contig>-<start>-<end>/<chunk> group per image
+    (pepper predict_distributed_gpu.py:107-109 -> DataStorePredict.write_prediction)."""
+    for i in range(calls.bases.shape[0]):
+        rs, re_ = regions_se[int(calls.image_region[i])]
+        store.write_prediction(contig, rs, re_, int(calls.chunk_id[i]), calls.position[i], calls.index[i], calls.bases[i], calls.phred[i])
+

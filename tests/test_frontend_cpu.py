@@ -40,3 +40,28 @@ def test_reservoir_matches_numpy_stream_for_region_limits():
     for total, allowed in [(1501, 1500), (6000, 5000)]:
         s = reservoir_select(total, allowed)
         assert s.shape[0] == allowed and len(set(s.tolist())) == allowed and s.max() < total
+
+
+def test_prediction_store_writers(tmp_path):
+    """frontend.write_*_predictions lay the calls out the way the reference's predict loops do (DataStorePredict layouts)."""
+    from pepper_b200.datastore import VariantPredictionStore, PolishPredictionStore
+    from pepper_b200.frontend import write_variant_predictions, write_polish_predictions
+    from pepper_b200.pipeline import VariantCalls, PolishCalls
+    n = 1030
+    keys = np.zeros((n, 64), dtype=np.uint8)
+    keys[:, 0], keys[:, 1] = ord("1"), ord("T")
+    vc = VariantCalls(np.arange(n, dtype=np.int64), np.full(n, 30, np.uint8), np.full(n, 9, np.uint8), keys, np.zeros(n, np.int32),
+                      np.tile(np.array([[0.1, 0.2, 0.7]], np.float32), (n, 1)))
+    with VariantPredictionStore(str(tmp_path / "v.hdf"), "w", backend="npz") as st:
+        assert write_variant_predictions(st, "chr20", vc, batch_size=512) == 3
+    st = VariantPredictionStore(str(tmp_path / "v.hdf"), "r", backend="npz")
+    assert st.keys("predictions") == ["batch_0", "batch_1", "batch_2"]
+    assert st.get("predictions/batch_2/positions").tolist() == list(range(1024, 1030))
+    assert st.get("predictions/batch_0/base_prediction").shape == (512, 3) and st.get("predictions/batch_0/candidates")[0, 0] == b"1T"
+    pc = PolishCalls(np.ones((3, 1000), np.uint8), np.full((3, 1000), 20, np.uint8), np.tile(np.arange(1000, dtype=np.int64), (3, 1)),
+                     np.zeros((3, 1000), np.int32), np.array([0, 0, 1], np.int32), np.array([0, 1, 0], np.int32))
+    with PolishPredictionStore(str(tmp_path / "p.hdf"), "w", backend="npz") as st:
+        write_polish_predictions(st, "ctg", pc, [(0, 1100), (900, 2100)])
+    st = PolishPredictionStore(str(tmp_path / "p.hdf"), "r", backend="npz")
+    assert st.keys("predictions/ctg") == ["ctg-0-1100", "ctg-900-2100"]
+    assert st.get("predictions/ctg/ctg-0-1100/1/bases").shape == (1000,) and int(st.get("predictions/ctg/ctg-900-2100/contig_end")) == 2100
