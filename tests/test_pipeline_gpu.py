@@ -31,14 +31,15 @@ def test_variant_call_matches_separate_stages(oracle_built):
 
 def test_polish_call_matches_separate_stages(oracle_built):
     from oracle import nets
+    from oracle import chunk_images as och          # pinned to the unmodified AlignmentSummarizer.chunk_images
     from pepper_b200.pipeline import PolishCaller
-    from pepper_b200.polish import PolishSummary, chunk_images
     state = nets.make_polish_weights(2)
     reads, regions = synth.make_polish_workload(6, 35, synth.ONT, seed=32)
     pc = PolishCaller(state)
     calls = pc.call(reads, regions)
     w = oracle_built.polish_encode(reads, regions, "port")
-    imgs, pos, idx, cids, regs = chunk_images(PolishSummary(w["image"], w["pos"], w["idx"], w["col_off"]))
+    imgs, pos, idx, cids, regs = och.chunk_images(w["image"], w["pos"], w["idx"], w["col_off"])
+    assert len(set(cids.tolist())) > 1               # multi-chunk regions present (k_polish_chunk's overlap rule exercised)
     assert np.array_equal(calls.position, pos) and np.array_equal(calls.index.astype(np.int64), idx)
     assert np.array_equal(calls.chunk_id, cids) and np.array_equal(calls.image_region, regs)
     b, p = pc.net.predict(imgs)
