@@ -327,6 +327,27 @@ int pb_variant_net_destroy(pb_variant_net_t *net);
 int pb_variant_net_forward_device(pb_variant_net_t *net, const int8_t *d_images,
                                   int64_t n, float *d_probs, float *d_hidden_dbg,
                                   void *stream);
+/* The prediction record a rank-0 writer needs for one candidate (3 x f32 probabilities, i32 position, i32 region
+ * id, u8 depth, u8 frequency, 62 B allele key = 84 B): what pepper_variant DataStorePredict.write_prediction stores per
+ * candidate (DataStorePredict.py:49-66).  Written by the head kernel (512 -> 3 + softmax) itself when a record sink is
+ * given, so that the buffer an NCCL all-gather sends needs no staging copy.                                               */
+typedef struct {
+    float   probs[3];
+    int32_t position;          /* contig position (int32 as in the reference's HDF5 'contig_pos' dataset) */
+    int32_t region;            /* global region (interval) id */
+    uint8_t depth, freq;
+    char    key[62];           /* NUL padded allele key, <= 61 characters */
+} pb_pred_record_t;
+/* the per-candidate columns the encoder produced for the candidates of one forward call (device pointers) */
+typedef struct {
+    const int64_t *positions;
+    const int32_t *region_of;
+    const uint8_t *depths, *freqs;
+    const char    *keys;       /* [n][PB_ALLELE_STRIDE] */
+} pb_candidate_columns_t;
+/* as pb_variant_net_forward_device; additionally writes d_records[i] for every candidate (cols / d_records may be NULL) */
+int pb_variant_net_forward_records_device(pb_variant_net_t *net, const int8_t *d_images, int64_t n, float *d_probs,
+                                          const pb_candidate_columns_t *cols, pb_pred_record_t *d_records, void *stream);
 int pb_variant_net_forward_host(pb_variant_net_t *net, const int8_t *h_images,
                                 int64_t n, float *h_probs, float *h_hidden_dbg,
                                 void *stream);
@@ -391,6 +412,32 @@ int pb_variant_call_device(pb_variant_encoder_t *enc, pb_variant_net_t *net,
                            uint8_t *d_depths, uint8_t *d_freqs, char *d_keys,
                            int32_t *d_region_of, float *d_probs,
                            int64_t *n_out, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Streaming session over region GROUPS (the unit a multi-GPU job hands out; replaces the reference's file-chunk round
+ * robin, pepper_variant/modules/python/RunInference.py:70-72,104-106 + ImageGenerationUI.py:307-316).  Candidates
+ * accumulate in library-owned device buffers; the network runs over whole 9,472-candidate chunks as they fill, the tail
+ * at _end.  Typical loop:  begin; stage(g0); { run(last?); stage(next); sync; }*; end; fetch / use d_records.
+ *   d_records  optional device buffer [capacity] (e.g. this rank's slice of an all-gather buffer): the network's head
+ *              kernel writes one pb_pred_record_t per candidate straight into it
+ *   region_id0 global id of the group's first region (added to region_of / record.region)
+ * pb_variant_stream_run returns while the network is still running; PB_ERR_CAPACITY ends the session (*n_total = need so far).
+ * ---------------------------------------------------------------------- */
+int pb_variant_stream_begin(pb_variant_encoder_t *enc, pb_variant_net_t *net, const pb_variant_params_t *params,
+                            int64_t capacity, pb_pred_record_t *d_records, void *stream);
+int pb_variant_stream_stage_host(pb_variant_encoder_t *enc, const pb_reads_t *h_reads, const pb_region_t *h_regions,
+                                 int64_t g0, int64_t g1, const char *h_ref, int32_t region_id0);
+int pb_variant_stream_stage_device(pb_variant_encoder_t *enc, const pb_reads_t *d_reads, const pb_region_t *h_regions,
+                                   int64_t g0, int64_t g1, const char *d_ref, int32_t region_id0);
+int pb_variant_stream_run(pb_variant_encoder_t *enc, pb_variant_net_t *net, int flush, int64_t *n_total);
+int pb_variant_stream_sync(pb_variant_encoder_t *enc);
+int pb_variant_stream_end(pb_variant_encoder_t *enc, pb_variant_net_t *net, int64_t *n_out);
+/* encoder device time per phase (ms: cigar prefix, pileup count, site index, alleles, windows) and kernel launches
+ * [encoder, network] of the last session, summed over its groups */
+int pb_variant_stream_stats(pb_variant_encoder_t *enc, float *ms5, int64_t *launches2, int64_t *groups);
+int pb_variant_stream_columns(pb_variant_encoder_t *enc, pb_candidate_columns_t *cols, const float **d_probs, const int8_t **d_images);
+int pb_variant_stream_fetch(pb_variant_encoder_t *enc, int64_t n, int8_t *h_images, int64_t *h_positions, uint8_t *h_depths,
+                            uint8_t *h_freqs, char *h_keys, int32_t *h_region_of, float *h_probs, void *stream);
 
 /* Fused make_images + call_consensus for the polish path (polish.py:14 steps
  * 1+2): encode, chunk into 1000-column images with 50 overlap

@@ -12,7 +12,11 @@ LIB_PATH = os.environ.get("PB_LIB_PATH") or os.path.join(HERE, "libpepper_b200.s
 
 
 class PepperB200Error(RuntimeError):
-    pass
+    """`rc` carries the C-ABI return code (PB_ERR_*), so callers compare codes instead of parsing the message."""
+
+    def __init__(self, msg: str, rc: int = 0):
+        super().__init__(msg)
+        self.rc = rc
 
 
 _lib = None
@@ -35,7 +39,7 @@ def lib() -> C.CDLL:
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().pb_last_error().decode(errors="replace")
-        raise PepperB200Error(f"{what} failed (code {rc}): {msg}")
+        raise PepperB200Error(f"{what} failed (code {rc}): {msg}", rc)
 
 
 def device_count() -> int:

@@ -54,6 +54,17 @@ class PbVariantParams(C.Structure):
                 ("candidate_support_threshold", C.c_double), ("skip_indels", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PbCandidateColumns(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("region_of", C.c_void_p), ("depths", C.c_void_p), ("freqs", C.c_void_p),
+                ("keys", C.c_void_p)]
+
+
+# pb_pred_record_t: the 84-byte prediction record of one candidate (what a rank-0 writer needs)
+PRED_RECORD = np.dtype([("probs", np.float32, (3,)), ("position", np.int32), ("region", np.int32), ("depth", np.uint8),
+                        ("freq", np.uint8), ("key", "S62")])
+assert PRED_RECORD.itemsize == 84
+
+
 def _c(a: np.ndarray, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
 

@@ -4,6 +4,7 @@
 #include <vector>
 
 namespace pb {
+struct VariantStream;      // streaming session state (pipeline.cu)
 struct DevRnn { DevBuf W, bias; int K0, K0p, K1, Kp, H; };
 struct DevLin { DevBuf W, bias; int N, K, Kp; };
 // tcgen05 path (nets_tc.cu): weights as bf16 hi/lo tile images + per-chunk tiled operands
@@ -17,6 +18,19 @@ struct TcVariant {
 struct TcPolish {
     TcRnn enc[2], dec[2];
     DevBuf img_op, yenc_hi, yenc_lo, ydec_hi, ydec_lo, zero, flags;
+};
+// optional record sink of the variant head kernel: the encoder's columns of the candidates of this forward call + output records
+struct OutSink {
+    pb_candidate_columns_t cols{nullptr, nullptr, nullptr, nullptr, nullptr};
+    pb_pred_record_t *records = nullptr;
+    OutSink at(int64_t b0) const {
+        OutSink S = *this;
+        if (records) {
+            S.cols.positions += b0; S.cols.region_of += b0; S.cols.depths += b0; S.cols.freqs += b0; S.cols.keys += b0 * PB_ALLELE_STRIDE;
+            S.records += b0;
+        }
+        return S;
+    }
 };
 int tc_upload_rnn(TcRnn &T, const float *Wp, int K0, int K0p_src, int H, int Kp_src);
 int tc_upload_lin(TcLin &T, const float *w, int N, int K);
@@ -47,6 +61,7 @@ struct pb_variant_encoder {
     pb::DevBuf g_buf[2][10];
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr};
+    pb::VariantStream *vstream = nullptr;
 };
 
 struct pb_polish_encoder {
@@ -89,7 +104,8 @@ struct pb_polish_net {
 
 namespace pb {
 int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, float *d_probs, float *d_hidden_dbg, cudaStream_t st,
-                       void (*out_kernel)(const float *, const float *, const float *, float *, int64_t, cudaStream_t));
+                       void (*out_kernel)(const float *, const float *, const float *, float *, int64_t, const OutSink &, cudaStream_t),
+                       const OutSink &sink);
 int polish_forward_tc(pb_polish_net *N, const uint8_t *d_images, int64_t B, int64_t n_total, int64_t b0, float *d_hidden_dbg,
                       cudaStream_t st);
 }  // namespace pb

@@ -179,9 +179,11 @@ __global__ void __launch_bounds__(GTHREADS, 2) k_gemm_fused(GemmArgs G) {
 }
 
 // ------------------------------------------------------------------ small kernels
-// variant head: logits = W[3][512] x + b, softmax (simple_model.py:76-82); one warp per candidate
+// variant head: logits = W[3][512] x + b, softmax (simple_model.py:76-82); one warp per candidate.  With a record sink the
+// warp also assembles the candidate's 84-byte prediction record (probabilities + the encoder's columns) in place, so the
+// buffer a gather sends is produced by the network itself.
 __global__ void k_variant_out(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ b,
-                              float *__restrict__ probs, int64_t n) {
+                              float *__restrict__ probs, int64_t n, pb::OutSink S) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -194,12 +196,23 @@ __global__ void k_variant_out(const float *__restrict__ x, const float *__restri
     for (int d = 16; d >= 1; d >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, d); s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d);
     }
-    if (lane == 0) {
-        s0 += b[0]; s1 += b[1]; s2 += b[2];
-        const float m = fmaxf(s0, fmaxf(s1, s2));
-        const float e0 = expf(s0 - m), e1 = expf(s1 - m), e2 = expf(s2 - m);
-        const float inv = 1.0f / (e0 + e1 + e2);
-        probs[row * 3 + 0] = e0 * inv; probs[row * 3 + 1] = e1 * inv; probs[row * 3 + 2] = e2 * inv;
+    s0 += b[0]; s1 += b[1]; s2 += b[2];
+    const float m = fmaxf(s0, fmaxf(s1, s2));
+    const float e0 = expf(s0 - m), e1 = expf(s1 - m), e2 = expf(s2 - m);
+    const float inv = 1.0f / (e0 + e1 + e2);
+    if (lane == 0) { probs[row * 3 + 0] = e0 * inv; probs[row * 3 + 1] = e1 * inv; probs[row * 3 + 2] = e2 * inv; }
+    if (S.records) {
+        pb_pred_record_t *r = S.records + row;
+        if (lane == 0) {
+            r->probs[0] = e0 * inv; r->probs[1] = e1 * inv; r->probs[2] = e2 * inv;
+            r->position = (int32_t) S.cols.positions[row];
+            r->region = S.cols.region_of[row];
+            r->depth = S.cols.depths[row]; r->freq = S.cols.freqs[row];
+        } else {
+            // lanes 1..31: two key bytes each (62 = 31 x 2); the key field starts at byte 22 of the 84-byte record
+            const uint16_t kb = *reinterpret_cast<const uint16_t *>(S.cols.keys + row * PB_ALLELE_STRIDE + 2 * (lane - 1));
+            *reinterpret_cast<uint16_t *>(r->key + 2 * (lane - 1)) = kb;
+        }
     }
 }
 
@@ -423,8 +436,8 @@ extern "C" int pb_variant_net_launches(pb_variant_net_t *N, int64_t *n) {
     return PB_OK;
 }
 
-static void launch_variant_out(const float *x, const float *W, const float *b, float *probs, int64_t n, cudaStream_t st) {
-    k_variant_out<<<(unsigned) ceil_div(n, 8), 256, 0, st>>>(x, W, b, probs, n);
+static void launch_variant_out(const float *x, const float *W, const float *b, float *probs, int64_t n, const pb::OutSink &S, cudaStream_t st) {
+    k_variant_out<<<(unsigned) ceil_div(n, 8), 256, 0, st>>>(x, W, b, probs, n, S);
 }
 
 static int variant_reserve(pb_variant_net *N, int64_t B) {
@@ -466,8 +479,28 @@ static int lstm_layer(pb_variant_net *N, DevRnn *L, const void *x, int64_t lda0,
     return PB_OK;
 }
 
+static int variant_forward(pb_variant_net_t *N, const int8_t *d_images, int64_t n, float *d_probs, float *d_hidden_dbg,
+                           const pb::OutSink &sink, void *stream_);
+
 extern "C" int pb_variant_net_forward_device(pb_variant_net_t *N, const int8_t *d_images, int64_t n, float *d_probs,
                                              float *d_hidden_dbg, void *stream_) {
+    return variant_forward(N, d_images, n, d_probs, d_hidden_dbg, pb::OutSink{}, stream_);
+}
+
+extern "C" int pb_variant_net_forward_records_device(pb_variant_net_t *N, const int8_t *d_images, int64_t n, float *d_probs,
+                                                     const pb_candidate_columns_t *cols, pb_pred_record_t *d_records, void *stream_) {
+    pb::OutSink S{};
+    if (d_records) {
+        if (!cols || !cols->positions || !cols->region_of || !cols->depths || !cols->freqs || !cols->keys) {
+            set_error("record sink needs all candidate columns"); return PB_ERR_ARG;
+        }
+        S.cols = *cols; S.records = d_records;
+    }
+    return variant_forward(N, d_images, n, d_probs, nullptr, S, stream_);
+}
+
+static int variant_forward(pb_variant_net_t *N, const int8_t *d_images, int64_t n, float *d_probs, float *d_hidden_dbg,
+                           const pb::OutSink &sink, void *stream_) {
     if (!N || (n > 0 && (!d_images || !d_probs))) { set_error("null argument"); return PB_ERR_ARG; }
     cudaStream_t st = (cudaStream_t) stream_;
     PB_CUDA(cudaSetDevice(N->device));
@@ -475,8 +508,9 @@ extern "C" int pb_variant_net_forward_device(pb_variant_net_t *N, const int8_t *
     for (int64_t b0 = 0; b0 < n; b0 += VARIANT_CHUNK) {
         const int64_t B = std::min(VARIANT_CHUNK, n - b0);
         const int8_t *img = d_images + b0 * VT * 26;
-        if (N->mode == 1) {
-            PB_TRY(variant_forward_tc(N, img, B, d_probs + b0 * 3, d_hidden_dbg ? d_hidden_dbg + b0 * VT * 512 : nullptr, st, launch_variant_out));
+        if (N->mode >= 1) {
+            PB_TRY(variant_forward_tc(N, img, B, d_probs + b0 * 3, d_hidden_dbg ? d_hidden_dbg + b0 * VT * 512 : nullptr, st, launch_variant_out,
+                                      sink.at(b0)));
             continue;
         }
         PB_TRY(variant_reserve(N, B));
@@ -499,7 +533,7 @@ extern "C" int pb_variant_net_forward_device(pb_variant_net_t *N, const int8_t *
             N->launches++;
             cur = N->l[i & 1].as<float>(); ld = 512;
         }
-        k_variant_out<<<(unsigned) ceil_div(B, 8), 256, 0, st>>>(cur, N->outl.W.as<float>(), N->outl.bias.as<float>(), d_probs + b0 * 3, B);
+        k_variant_out<<<(unsigned) ceil_div(B, 8), 256, 0, st>>>(cur, N->outl.W.as<float>(), N->outl.bias.as<float>(), d_probs + b0 * 3, B, sink.at(b0));
         N->launches++;
         PB_CUDA(cudaGetLastError());
     }

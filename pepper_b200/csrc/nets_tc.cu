@@ -119,7 +119,8 @@ static Dir empty_dir() {
 constexpr int VT = 33, VH = 256;
 
 int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, float *d_probs, float *d_hidden_dbg, cudaStream_t st,
-                       void (*out_kernel)(const float *, const float *, const float *, float *, int64_t, cudaStream_t)) {
+                       void (*out_kernel)(const float *, const float *, const float *, float *, int64_t, const OutSink &, cudaStream_t),
+                       const OutSink &sink) {
     TcVariant &T = *N->tc;
     const int64_t Mt = ceil_div(B, 128), Bp = Mt * 128;
     const int64_t seq_tiles = Mt * VT * 16;                 // [mt][t][16 k-tiles] of a 512-feature sequence operand
@@ -218,7 +219,7 @@ int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, flo
         PB_TRY(launch_tc<tc::EPI_SELU>(A, (int) Mt, 4, 1, st));
         N->launches++;
     }
-    out_kernel(T.final_f32.as<float>(), N->outl.W.as<float>(), N->outl.bias.as<float>(), d_probs, B, st);
+    out_kernel(T.final_f32.as<float>(), N->outl.W.as<float>(), N->outl.bias.as<float>(), d_probs, B, sink, st);
     N->launches++;
     PB_CUDA(cudaGetLastError());
     return PB_OK;

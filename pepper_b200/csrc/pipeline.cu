@@ -141,22 +141,254 @@ static int variant_call_host_single(pb_variant_encoder_t *e, pb_variant_net_t *n
     return PB_OK;
 }
 
-// Host entry: regions are processed in groups; the H2D copy of group g+1 (copy stream, pinned source) overlaps the
-// encoder + network kernels of group g, so PCIe time hides behind compute for all but the first group.
+// ------------------------------------------------------------------------------------------------- streaming session
+// The unit of work is a GROUP of regions.  A session accumulates the candidates of the groups pushed so far in the
+// library's device buffers, runs the network over WHOLE 9,472-candidate chunks of the accumulated candidates as they fill
+// (the remainder rides along to the next group, so only the very last chunk of a session is partial), and lets the caller
+// stage group g+1 (copy stream, pinned source) while the kernels of group g run.  pb_variant_call_host is a session over a
+// fixed group list; the multi-GPU callers (pepper_b200/dist.py) push whatever group a rank claims next.
 constexpr int64_t CALL_GROUP = 96;
 constexpr int64_t CALL_FIRST_GROUP = 24;
 
 // network chunk of the pipelined host entry == VARIANT_CHUNK of nets.cu (74 row tiles of 128 candidates)
 static constexpr int64_t PIPE_NET_CHUNK = 9472;
 
+namespace pb {
+struct VariantStream {
+    bool active = false;
+    pb_variant_params_t params;
+    int64_t capacity = 0, done = 0, net_done = 0;
+    pb_pred_record_t *d_records = nullptr;
+    cudaStream_t st = nullptr;
+    GroupView V[2];
+    int32_t region_id0[2] = {0, 0};
+    bool staged[2] = {false, false}, from_host[2] = {false, false};
+    int next_stage = 0, next_run = 0;
+    bool timing_pending = false;
+    float enc_ms = 0.f, net_ms = 0.f;
+    float enc_phase_ms[5] = {0, 0, 0, 0, 0};        // prefix, count, sites, alleles, windows — summed over the groups
+    int64_t enc_launches = 0, net_launches = 0, groups = 0;
+};
+}  // namespace pb
+
+static int session(pb_variant_encoder_t *e, VariantStream **S, bool need_active) {
+    if (!e) { set_error("null handle"); return PB_ERR_ARG; }
+    if (!e->vstream) e->vstream = new VariantStream();
+    *S = e->vstream;
+    if (need_active && !(*S)->active) { set_error("no active stream session: call pb_variant_stream_begin first"); return PB_ERR_STATE; }
+    return PB_OK;
+}
+
+extern "C" int pb_variant_stream_begin(pb_variant_encoder_t *e, pb_variant_net_t *net, const pb_variant_params_t *params,
+                                       int64_t capacity, pb_pred_record_t *d_records, void *stream_) {
+    if (!e || !net || !params) { set_error("null argument"); return PB_ERR_ARG; }
+    VariantStream *S;
+    PB_TRY(session(e, &S, false));
+    PB_CUDA(cudaSetDevice(e->device));
+    if (!e->copy_stream) {
+        PB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) PB_CUDA(cudaEventCreateWithFlags(&e->copied[b], cudaEventDisableTiming));
+    }
+    PB_TRY(ensure_events(e->pevt, 3));
+    const int64_t cap = std::max<int64_t>(capacity, 1);
+    PB_TRY(e->p_images.reserve((size_t) cap * 33 * 26));
+    PB_TRY(e->p_positions.reserve(sizeof(int64_t) * cap));
+    PB_TRY(e->p_depths.reserve(cap));
+    PB_TRY(e->p_freqs.reserve(cap));
+    PB_TRY(e->p_keys.reserve((size_t) cap * PB_ALLELE_STRIDE));
+    PB_TRY(e->p_region_of.reserve(sizeof(int32_t) * cap));
+    PB_TRY(e->p_probs.reserve(sizeof(float) * 3 * cap));
+    S->active = true; S->params = *params; S->capacity = capacity; S->done = 0; S->net_done = 0; S->d_records = d_records;
+    S->st = (cudaStream_t) stream_;
+    S->staged[0] = S->staged[1] = false; S->next_stage = 0; S->next_run = 0; S->timing_pending = false;
+    S->enc_ms = S->net_ms = 0.f;
+    for (int i = 0; i < 5; i++) S->enc_phase_ms[i] = 0.f;
+    S->enc_launches = S->net_launches = S->groups = 0;
+    return PB_OK;
+}
+
+// stage regions [g0, g1) of a host-resident workload into the free staging buffer (asynchronous H2D on the copy stream)
+extern "C" int pb_variant_stream_stage_host(pb_variant_encoder_t *e, const pb_reads_t *h_reads, const pb_region_t *h_regions,
+                                            int64_t g0, int64_t g1, const char *h_ref, int32_t region_id0) {
+    VariantStream *S;
+    PB_TRY(session(e, &S, true));
+    if (!h_reads || !h_regions || g0 < 0 || g1 <= g0) { set_error("bad group [%lld, %lld)", (long long) g0, (long long) g1); return PB_ERR_ARG; }
+    const int b = S->next_stage;
+    if (S->staged[b]) { set_error("both staging buffers are in use: run a staged group first"); return PB_ERR_STATE; }
+    for (int64_t r = g0; r < g1; r++) {
+        if (h_regions[r].read_begin < 0 || h_regions[r].read_end > h_reads->n_reads || h_regions[r].read_begin > h_regions[r].read_end ||
+            (r > g0 && h_regions[r].read_begin < h_regions[r - 1].read_end)) {
+            set_error("region %lld: read range out of bounds or not ascending", (long long) r);
+            return PB_ERR_ARG;
+        }
+    }
+    PB_TRY(stage_group(e, b, h_reads, h_regions, g0, g1, h_ref, S->V[b]));
+    S->staged[b] = true; S->from_host[b] = true; S->region_id0[b] = region_id0; S->next_stage = b ^ 1;
+    return PB_OK;
+}
+
+// the same for a workload that is already resident in HBM: no copies of the reads, only the re-based region rows
+extern "C" int pb_variant_stream_stage_device(pb_variant_encoder_t *e, const pb_reads_t *d_reads, const pb_region_t *h_regions,
+                                              int64_t g0, int64_t g1, const char *d_ref, int32_t region_id0) {
+    VariantStream *S;
+    PB_TRY(session(e, &S, true));
+    if (!d_reads || !h_regions || g0 < 0 || g1 <= g0) { set_error("bad group [%lld, %lld)", (long long) g0, (long long) g1); return PB_ERR_ARG; }
+    const int b = S->next_stage;
+    if (S->staged[b]) { set_error("both staging buffers are in use: run a staged group first"); return PB_ERR_STATE; }
+    GroupView &V = S->V[b];
+    const int64_t r0 = h_regions[g0].read_begin, r1 = h_regions[g1 - 1].read_end;
+    if (r0 < 0 || r1 > d_reads->n_reads || r1 < r0) { set_error("group read range out of bounds"); return PB_ERR_ARG; }
+    V.h_regions.assign(h_regions + g0, h_regions + g1);
+    for (auto &rg : V.h_regions) { rg.read_begin -= r0; rg.read_end -= r0; }
+    PB_TRY(upload(e->g_buf[b][8], V.h_regions.data(), sizeof(pb_region_t) * V.h_regions.size(), e->copy_stream));
+    PB_CUDA(cudaEventRecord(e->copied[b], e->copy_stream));
+    V.d = *d_reads;
+    V.d.n_reads = r1 - r0;
+    V.d.pos += r0; V.d.seq_off += r0; V.d.cigar_off += r0; V.d.flags += r0; V.d.mapq += r0;     // seq / qual / cigar keep absolute offsets
+    V.d_regions = e->g_buf[b][8].as<pb_region_t>();
+    V.d_ref = d_ref;
+    S->staged[b] = true; S->from_host[b] = false; S->region_id0[b] = region_id0; S->next_stage = b ^ 1;
+    return PB_OK;
+}
+
+static void stream_collect_timing(pb_variant_encoder_t *e, VariantStream *S) {
+    if (!S->timing_pending) return;
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, e->pevt[0], e->pevt[1]);
+    cudaEventElapsedTime(&b, e->pevt[1], e->pevt[2]);
+    S->enc_ms += a; S->net_ms += b;
+    S->timing_pending = false;
+}
+
+static int stream_network(pb_variant_encoder_t *e, pb_variant_net_t *net, VariantStream *S, int64_t run) {
+    if (run <= 0) return PB_OK;
+    pb_candidate_columns_t cols{e->p_positions.as<int64_t>() + S->net_done, e->p_region_of.as<int32_t>() + S->net_done,
+                                e->p_depths.as<uint8_t>() + S->net_done, e->p_freqs.as<uint8_t>() + S->net_done,
+                                e->p_keys.as<char>() + S->net_done * PB_ALLELE_STRIDE};
+    PB_TRY(pb_variant_net_forward_records_device(net, e->p_images.as<int8_t>() + S->net_done * 33 * 26, run, e->p_probs.as<float>() + S->net_done * 3,
+                                                 &cols, S->d_records ? S->d_records + S->net_done : nullptr, (void *) S->st));
+    S->net_done += run;
+    int64_t nl = 0;
+    pb_variant_net_launches(net, &nl);
+    S->net_launches += nl;
+    return PB_OK;
+}
+
+// Encode the oldest staged group behind the accumulated candidates and queue the network over the whole chunks available
+// (`flush` != 0: over everything, partial tail included).  Returns with the network still running: stage the next group, then
+// call pb_variant_stream_sync.  On PB_ERR_CAPACITY *n_total holds the candidates needed so far (this group included).
+extern "C" int pb_variant_stream_run(pb_variant_encoder_t *e, pb_variant_net_t *net, int flush, int64_t *n_total) {
+    VariantStream *S;
+    PB_TRY(session(e, &S, true));
+    if (!net) { set_error("null handle"); return PB_ERR_ARG; }
+    const int b = S->next_run;
+    if (!S->staged[b]) { set_error("no staged group"); return PB_ERR_STATE; }
+    cudaStream_t st = S->st;
+    if (S->timing_pending) { PB_CUDA(cudaStreamSynchronize(st)); stream_collect_timing(e, S); }
+    PB_CUDA(cudaStreamWaitEvent(st, e->copied[b], 0));
+    GroupView &V = S->V[b];
+    int64_t n_g = 0;
+    const int64_t done = S->done, room = std::max<int64_t>(S->capacity - done, 0);
+    PB_CUDA(cudaEventRecord(e->pevt[0], st));
+    int rc = pb_variant_encode_device(e, &V.d, V.d_regions, (int64_t) V.h_regions.size(), V.h_regions.data(), V.d_ref, 0, &S->params, room,
+                                      e->p_images.as<int8_t>() + done * 33 * 26, e->p_positions.as<int64_t>() + done,
+                                      e->p_depths.as<uint8_t>() + done, e->p_freqs.as<uint8_t>() + done,
+                                      e->p_keys.as<char>() + done * PB_ALLELE_STRIDE, e->p_region_of.as<int32_t>() + done, nullptr, &n_g, (void *) st);
+    S->staged[b] = false; S->next_run = b ^ 1;
+    if (n_total) *n_total = done + n_g;
+    if (rc != PB_OK) { if (rc == PB_ERR_CAPACITY) cudaStreamSynchronize(e->copy_stream); return rc; }
+    for (int i = 0; i < 5; i++) S->enc_phase_ms[i] += e->ms[i];
+    S->enc_launches += e->launches; S->groups++;
+    if (n_g > 0 && S->region_id0[b] != 0)
+        k_add_offset_i32<<<(unsigned) ceil_div(n_g, 256), 256, 0, st>>>(e->p_region_of.as<int32_t>() + done, n_g, S->region_id0[b]);
+    PB_CUDA(cudaEventRecord(e->pevt[1], st));
+    S->done = done + n_g;
+    const int64_t avail = S->done - S->net_done;
+    PB_TRY(stream_network(e, net, S, flush ? avail : avail / PIPE_NET_CHUNK * PIPE_NET_CHUNK));
+    PB_CUDA(cudaEventRecord(e->pevt[2], st));
+    S->timing_pending = true;
+    return PB_OK;
+}
+
+extern "C" int pb_variant_stream_sync(pb_variant_encoder_t *e) {
+    VariantStream *S;
+    PB_TRY(session(e, &S, true));
+    PB_CUDA(cudaStreamSynchronize(S->st));
+    stream_collect_timing(e, S);
+    return PB_OK;
+}
+
+// network over whatever is still waiting, wait for everything; *n_out = candidates of the session
+extern "C" int pb_variant_stream_end(pb_variant_encoder_t *e, pb_variant_net_t *net, int64_t *n_out) {
+    VariantStream *S;
+    PB_TRY(session(e, &S, true));
+    if (!net || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
+    cudaStream_t st = S->st;
+    PB_CUDA(cudaStreamSynchronize(st));
+    stream_collect_timing(e, S);
+    if (S->done > S->net_done) {
+        PB_CUDA(cudaEventRecord(e->pevt[0], st));
+        PB_CUDA(cudaEventRecord(e->pevt[1], st));
+        PB_TRY(stream_network(e, net, S, S->done - S->net_done));
+        PB_CUDA(cudaEventRecord(e->pevt[2], st));
+        S->timing_pending = true;
+        PB_CUDA(cudaStreamSynchronize(st));
+        stream_collect_timing(e, S);
+    }
+    PB_CUDA(cudaStreamSynchronize(e->copy_stream));
+    e->pms[0] = S->enc_ms; e->pms[1] = S->net_ms;
+    *n_out = S->done;
+    S->active = false;
+    return PB_OK;
+}
+
+// per-phase encoder device time (ms: prefix, count, sites, alleles, windows) and kernel launches (encoder, network) of the
+// last session, summed over its groups
+extern "C" int pb_variant_stream_stats(pb_variant_encoder_t *e, float *ms5, int64_t *launches2, int64_t *groups) {
+    if (!e || !e->vstream) { set_error("no session"); return PB_ERR_STATE; }
+    VariantStream *S = e->vstream;
+    if (ms5) for (int i = 0; i < 5; i++) ms5[i] = S->enc_phase_ms[i];
+    if (launches2) { launches2[0] = S->enc_launches; launches2[1] = S->net_launches; }
+    if (groups) *groups = S->groups;
+    return PB_OK;
+}
+
+// device pointers of the session's accumulated columns and probabilities (valid until the next session begins)
+extern "C" int pb_variant_stream_columns(pb_variant_encoder_t *e, pb_candidate_columns_t *cols, const float **d_probs, const int8_t **d_images) {
+    if (!e || !cols) { set_error("null argument"); return PB_ERR_ARG; }
+    cols->positions = e->p_positions.as<int64_t>(); cols->region_of = e->p_region_of.as<int32_t>();
+    cols->depths = e->p_depths.as<uint8_t>(); cols->freqs = e->p_freqs.as<uint8_t>(); cols->keys = e->p_keys.as<char>();
+    if (d_probs) *d_probs = e->p_probs.as<float>();
+    if (d_images) *d_images = e->p_images.as<int8_t>();
+    return PB_OK;
+}
+
+// D2H of the first n candidates of the last session (any pointer may be NULL)
+extern "C" int pb_variant_stream_fetch(pb_variant_encoder_t *e, int64_t n, int8_t *h_images, int64_t *h_positions, uint8_t *h_depths,
+                                       uint8_t *h_freqs, char *h_keys, int32_t *h_region_of, float *h_probs, void *stream_) {
+    if (!e) { set_error("null handle"); return PB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t) stream_;
+    if (n > 0) {
+        if (h_images) PB_CUDA(cudaMemcpyAsync(h_images, e->p_images.p, (size_t) n * 33 * 26, cudaMemcpyDeviceToHost, st));
+        if (h_positions) PB_CUDA(cudaMemcpyAsync(h_positions, e->p_positions.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+        if (h_depths) PB_CUDA(cudaMemcpyAsync(h_depths, e->p_depths.p, n, cudaMemcpyDeviceToHost, st));
+        if (h_freqs) PB_CUDA(cudaMemcpyAsync(h_freqs, e->p_freqs.p, n, cudaMemcpyDeviceToHost, st));
+        if (h_keys) PB_CUDA(cudaMemcpyAsync(h_keys, e->p_keys.p, (size_t) n * PB_ALLELE_STRIDE, cudaMemcpyDeviceToHost, st));
+        if (h_region_of) PB_CUDA(cudaMemcpyAsync(h_region_of, e->p_region_of.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        if (h_probs) PB_CUDA(cudaMemcpyAsync(h_probs, e->p_probs.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+    }
+    PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+// Host entry: regions are processed in groups; the H2D copy of group g+1 (copy stream, pinned source) overlaps the
+// encoder + network kernels of group g, so PCIe time hides behind compute for all but the first group.
 extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *net, const pb_reads_t *h_reads,
                                     const pb_region_t *h_regions, int64_t n_regions, const char *h_ref, int64_t ref_bytes,
                                     const pb_variant_params_t *params, int64_t capacity, int8_t *h_images,
                                     int64_t *h_positions, uint8_t *h_depths, uint8_t *h_freqs, char *h_keys,
                                     int32_t *h_region_of, float *h_probs, int64_t *n_out, void *stream_) {
     if (!e || !net || !h_reads || !h_regions || !params || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
-    (void) ref_bytes;
-    cudaStream_t st = (cudaStream_t) stream_;
     PB_CUDA(cudaSetDevice(e->device));
     *n_out = 0;
     if (n_regions <= 0) return PB_OK;
@@ -171,91 +403,33 @@ extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *n
     if (n_regions <= CALL_GROUP || !ascending)
         return variant_call_host_single(e, net, h_reads, h_regions, n_regions, h_ref, ref_bytes, params, capacity, h_images, h_positions,
                                         h_depths, h_freqs, h_keys, h_region_of, h_probs, n_out, stream_);
-    if (!e->copy_stream) {
-        PB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) PB_CUDA(cudaEventCreateWithFlags(&e->copied[b], cudaEventDisableTiming));
-    }
-    PB_TRY(ensure_events(e->pevt, 3));
-    const int64_t cap = std::max<int64_t>(capacity, 1);
-    PB_TRY(e->p_images.reserve((size_t) cap * 33 * 26));
-    PB_TRY(e->p_positions.reserve(sizeof(int64_t) * cap));
-    PB_TRY(e->p_depths.reserve(cap));
-    PB_TRY(e->p_freqs.reserve(cap));
-    PB_TRY(e->p_keys.reserve((size_t) cap * PB_ALLELE_STRIDE));
-    PB_TRY(e->p_region_of.reserve(sizeof(int32_t) * cap));
-    PB_TRY(e->p_probs.reserve(sizeof(float) * 3 * cap));
-
     // group boundaries: a short first group keeps the un-overlapped first copy small
     std::vector<int64_t> gb;
     gb.push_back(0);
     for (int64_t r = std::min<int64_t>(CALL_FIRST_GROUP, n_regions); r < n_regions; r += CALL_GROUP) gb.push_back(r);
     gb.push_back(n_regions);
     const int64_t n_groups = (int64_t) gb.size() - 1;
-    GroupView V[2];
-    PB_TRY(stage_group(e, 0, h_reads, h_regions, gb[0], gb[1], h_ref, V[0]));
-    int64_t done = 0, net_done = 0;
-    float enc_ms = 0.f, net_ms = 0.f;
-    int rc = PB_OK;
-    for (int64_t g = 0; g < n_groups && rc == PB_OK; g++) {
-        const int b = (int) (g & 1);
-        PB_CUDA(cudaStreamWaitEvent(st, e->copied[b], 0));
-        int64_t n_g = 0;
-        const int64_t room = std::max<int64_t>(capacity - done, 0);
-        // encode this group behind the candidates of the previous ones; the network runs over WHOLE chunks of the accumulated
-        // candidates (the remainder rides along to the next group), so only the very last chunk of the call is partial
-        PB_CUDA(cudaEventRecord(e->pevt[0], st));
-        rc = pb_variant_encode_device(e, &V[b].d, V[b].d_regions, (int64_t) V[b].h_regions.size(), V[b].h_regions.data(), V[b].d_ref, 0, params, room,
-                                      e->p_images.as<int8_t>() + done * 33 * 26, e->p_positions.as<int64_t>() + done,
-                                      e->p_depths.as<uint8_t>() + done, e->p_freqs.as<uint8_t>() + done,
-                                      e->p_keys.as<char>() + done * PB_ALLELE_STRIDE, e->p_region_of.as<int32_t>() + done, nullptr, &n_g, stream_);
-        if (rc == PB_OK) {
-            PB_CUDA(cudaEventRecord(e->pevt[1], st));
-            const int64_t avail = done + n_g - net_done;
-            const int64_t run = (g + 1 == n_groups) ? avail : avail / PIPE_NET_CHUNK * PIPE_NET_CHUNK;
-            if (run > 0)
-                rc = pb_variant_net_forward_device(net, e->p_images.as<int8_t>() + net_done * 33 * 26, run, e->p_probs.as<float>() + net_done * 3,
-                                                   nullptr, stream_);
-            if (rc == PB_OK) {
-                net_done += run;
-                PB_CUDA(cudaEventRecord(e->pevt[2], st));
-                // the network of this group is queued: issue the next group's copies now, so that neither the host work of
-                // staging nor the copies themselves leave the compute stream idle
-                if (g + 1 < n_groups)
-                    PB_TRY(stage_group(e, b ^ 1, h_reads, h_regions, gb[g + 1], gb[g + 2], h_ref, V[b ^ 1]));
-                PB_CUDA(cudaStreamSynchronize(st));
-                cudaEventElapsedTime(&e->pms[0], e->pevt[0], e->pevt[1]);
-                cudaEventElapsedTime(&e->pms[1], e->pevt[1], e->pevt[2]);
-            }
-        }
+    PB_TRY(pb_variant_stream_begin(e, net, params, capacity, nullptr, stream_));
+    PB_TRY(pb_variant_stream_stage_host(e, h_reads, h_regions, gb[0], gb[1], h_ref, 0));
+    for (int64_t g = 0; g < n_groups; g++) {
+        int64_t n_tot = 0;
+        const int rc = pb_variant_stream_run(e, net, g + 1 == n_groups, &n_tot);
         if (rc == PB_ERR_CAPACITY) {
             // the caller retries with the returned size: extrapolate from the regions seen so far (retried again if short)
-            const int64_t seen = gb[g + 1];
-            const int64_t need = (int64_t) ((double) (done + n_g) * (double) n_regions / (double) seen * 1.25) + 4096;
-            cudaStreamSynchronize(e->copy_stream);
+            const int64_t need = (int64_t) ((double) n_tot * (double) n_regions / (double) gb[g + 1] * 1.25) + 4096;
+            e->vstream->active = false;
             *n_out = need;
             set_error("candidate capacity %lld too small (estimated need %lld)", (long long) capacity, (long long) need);
             return PB_ERR_CAPACITY;
         }
-        if (rc != PB_OK) return rc;
-        if (n_g > 0 && g > 0)
-            k_add_offset_i32<<<(unsigned) ceil_div(n_g, 256), 256, 0, st>>>(e->p_region_of.as<int32_t>() + done, n_g, (int32_t) gb[g]);
-        enc_ms += e->pms[0]; net_ms += e->pms[1];
-        done += n_g;
+        if (rc != PB_OK) { e->vstream->active = false; return rc; }
+        // the network of this group is queued: issue the next group's copies now, so that neither the host work of staging nor
+        // the copies themselves leave the compute stream idle
+        if (g + 1 < n_groups) PB_TRY(pb_variant_stream_stage_host(e, h_reads, h_regions, gb[g + 1], gb[g + 2], h_ref, (int32_t) gb[g + 1]));
+        PB_TRY(pb_variant_stream_sync(e));
     }
-    e->pms[0] = enc_ms; e->pms[1] = net_ms;
-    *n_out = done;
-    const int64_t n = done;
-    if (n > 0) {
-        if (h_images) PB_CUDA(cudaMemcpyAsync(h_images, e->p_images.p, (size_t) n * 33 * 26, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(h_positions, e->p_positions.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(h_depths, e->p_depths.p, n, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(h_freqs, e->p_freqs.p, n, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(h_keys, e->p_keys.p, (size_t) n * PB_ALLELE_STRIDE, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(h_region_of, e->p_region_of.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(h_probs, e->p_probs.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
-    }
-    PB_CUDA(cudaStreamSynchronize(st));
-    return PB_OK;
+    PB_TRY(pb_variant_stream_end(e, net, n_out));
+    return pb_variant_stream_fetch(e, *n_out, h_images, h_positions, h_depths, h_freqs, h_keys, h_region_of, h_probs, stream_);
 }
 
 extern "C" int pb_variant_call_timings(pb_variant_encoder_t *e, float *ms2) {

@@ -1,14 +1,29 @@
-"""Multi-GPU plumbing of the hot path: regions are independent units, so ranks take contiguous
-blocks of regions balanced by aligned-base count and the only collective is one all-gather of the per-candidate
-predictions at the end (preceded by a tiny count all-gather for the ragged sizes).  Backend-agnostic
-(`nccl` on GPUs, `gloo` in the CPU tests)."""
+"""Multi-GPU product path of the variant hot path (replaces the reference's file-chunk round robin over
+processes / DataParallel, pepper_variant RunInference.py:70-72,104-106, ImageGenerationUI.py:307-316,
+predict_distributed_gpu.py:41).
+
+Regions (100 kb intervals) are independent units.  A job is cut into region GROUPS; every rank runs a streaming session
+(`pipeline.VariantStream`) over the groups it owns and the network's head kernel writes each candidate's 84-byte prediction
+record straight into this rank's slice of ONE gather buffer; a single fixed-capacity all-gather (no host round trip for the
+ragged counts, which travel in a second tiny all-gather) then gives every rank the whole job's records.
+
+Two schedules:
+  * static  — contiguous blocks of groups balanced by aligned-base count (`shard_regions`): rank-major order == genomic order;
+  * dynamic — ranks claim the next group from an atomic counter in the rendezvous store (`GroupClaimer`), so a GPU that runs
+              slower under the board power cap simply takes fewer groups; genomic order is restored from the region ids the
+              records carry (`order_records`).
+Backend-agnostic (`nccl` on GPUs, `gloo` in the CPU tests)."""
 from __future__ import annotations
 
 import numpy as np
 
+from .abi import PRED_RECORD
+
+RECORD_BYTES = PRED_RECORD.itemsize
+
 
 def shard_regions(work: np.ndarray, world: int) -> list[tuple[int, int]]:
-    """Contiguous blocks [begin, end) of regions per rank, balanced by `work` (e.g. aligned bases per region).
+    """Contiguous blocks [begin, end) of units per rank, balanced by `work` (e.g. aligned bases per region / group).
     Contiguity keeps rank-major order == genomic order after the gather."""
     n = int(work.shape[0])
     if n == 0:
@@ -28,25 +43,253 @@ def shard_regions(work: np.ndarray, world: int) -> list[tuple[int, int]]:
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def gather_predictions(probs, n_valid: int, world: int):
-    """All-gather of per-candidate predictions with ragged counts.  `probs` is a [cap, C] tensor whose first
-    `n_valid` rows are valid.  Returns (all_probs [sum n, C] in rank-major order, counts list)."""
-    import torch
-    import torch.distributed as dist
-    if world == 1:
-        return probs[:n_valid], [n_valid]
-    dev = probs.device
-    cnt = torch.tensor([n_valid], dtype=torch.int64, device=dev)
-    cnts = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(cnts, cnt)
-    counts = [int(c) for c in cnts.tolist()]
-    m = max(counts)
-    if m == 0:
-        return probs[:0], counts
-    mine = probs[:m]
-    if mine.shape[0] < m:                      # capacity smaller than the largest shard: pad
-        pad = torch.zeros((m - mine.shape[0],) + tuple(probs.shape[1:]), dtype=probs.dtype, device=dev)
-        mine = torch.cat([mine, pad])
-    allp = torch.empty((world * m,) + tuple(probs.shape[1:]), dtype=probs.dtype, device=dev)   # concatenated layout
-    dist.all_gather_into_tensor(allp, mine.contiguous())
-    return torch.cat([allp[r * m:r * m + counts[r]] for r in range(world)]), counts
+def plan_groups(n_regions: int, group: int = 32) -> list[tuple[int, int]]:
+    """Region groups [g0, g1) of a job: the hand-out unit (about 50 k candidates = 5 network chunks at ONT 30x)."""
+    return [(g, min(n_regions, g + group)) for g in range(0, n_regions, group)]
+
+
+def group_work(seq_off: np.ndarray, table: np.ndarray, groups: list[tuple[int, int]]) -> np.ndarray:
+    """Aligned bases per group (the balance criterion of SURVEY 8e) from the reads' sequence offsets."""
+    return np.array([int(seq_off[int(table[g1 - 1, 7])] - seq_off[int(table[g0, 6])]) for g0, g1 in groups], dtype=np.int64)
+
+
+class GroupClaimer:
+    """Hands out group indices.  `dynamic`: an atomic counter in the process group's rendezvous store (TCPStore.add is atomic;
+    ~20 us per claim against ~20 ms of GPU work per group).  `static`: this rank's contiguous block."""
+
+    def __init__(self, n_groups: int, rank: int, world: int, schedule: str = "dynamic", work: np.ndarray | None = None,
+                 store=None, key: str = "pb_claim"):
+        self.n, self.rank, self.world, self.schedule = n_groups, rank, world, schedule
+        if schedule == "static" or world == 1:
+            b, e = shard_regions(work if work is not None else np.ones(n_groups), world)[rank]
+            self._it = iter(range(b, e))
+            self.store = None
+        elif schedule == "dynamic":
+            if store is None:
+                import torch.distributed as dist
+                store = dist.distributed_c10d._get_default_store()
+            self.store, self.key = store, key
+            self._it = None
+        else:
+            raise ValueError("schedule must be 'static' or 'dynamic'")
+
+    def next(self):
+        if self._it is not None:
+            return next(self._it, None)
+        g = int(self.store.add(self.key, 1)) - 1
+        return g if g < self.n else None
+
+
+class GatherBuffer:
+    """[world][capacity] prediction records + [world] counts.  On NCCL the record tensor is allocated from NCCL's own
+    allocator (ncclMemAlloc through torch.cuda.MemPool) when this torch build offers it, so the collective works on registered
+    user buffers; otherwise a plain tensor."""
+
+    def __init__(self, capacity: int, world: int, rank: int, device=None, max_groups: int = 0):
+        import torch
+        self.capacity, self.world, self.rank = int(capacity), world, rank
+        self.max_groups = int(max_groups)
+        self.registered = False
+        nbytes = world * self.capacity * RECORD_BYTES
+        dev = device if device is not None else torch.device("cpu")
+        self.records = None
+        if getattr(dev, "type", "cpu") == "cuda" and world > 1:
+            try:
+                import torch.distributed as dist
+                backend = dist.distributed_c10d._get_default_group()._get_backend(dev)
+                pool = torch.cuda.MemPool(backend.mem_allocator)
+                with torch.cuda.use_mem_pool(pool):
+                    self.records = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                backend.register_mem_pool(pool)
+                self._pool = pool
+                self.registered = True
+            except Exception:
+                self.records = None
+        if self.records is None:
+            self.records = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        # per rank: [n_valid, (group id, candidates) x max_groups] — the ragged counts and, for the dynamic schedule, the order
+        # in which the rank ran its groups (group id -1 = unused slot)
+        self._w = 1 + 2 * self.max_groups
+        self.meta = torch.zeros((world, self._w), dtype=torch.int64, device=dev)
+        self._mine = torch.zeros(self._w, dtype=torch.int64, device=dev)
+        self._mine_host = torch.zeros(self._w, dtype=torch.int64).pin_memory() if getattr(dev, "type", "cpu") == "cuda" else torch.zeros(self._w, dtype=torch.int64)
+
+    @property
+    def counts(self):
+        return self.meta[:, 0]
+
+    @property
+    def slice_bytes(self) -> int:
+        return self.capacity * RECORD_BYTES
+
+    def my_slice(self):
+        return self.records[self.rank * self.slice_bytes:(self.rank + 1) * self.slice_bytes]
+
+    def my_ptr(self) -> int:
+        return self.records.data_ptr() + self.rank * self.slice_bytes
+
+    def set_mine(self, n_valid: int, segments=None):
+        """This rank's row of the meta table: candidate count and the (group id, candidates) list in processing order."""
+        if n_valid > self.capacity:
+            raise ValueError("n_valid %d > capacity %d" % (n_valid, self.capacity))
+        h = self._mine_host
+        h.zero_()
+        h[0] = n_valid
+        if self.max_groups:
+            h[1::2] = -1
+            for i, (g, c) in enumerate(segments or []):
+                h[1 + 2 * i], h[2 + 2 * i] = g, c
+        self._mine.copy_(h, non_blocking=True)
+
+    def gather_meta(self, group=None):
+        import torch.distributed as dist
+        if self.world == 1:
+            self.meta[0].copy_(self._mine)
+        else:
+            dist.all_gather_into_tensor(self.meta.view(-1), self._mine, group=group)
+
+    def gather_records(self, group=None):
+        """In place: this rank's input is its own slice of the output."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.records, self.my_slice(), group=group)
+
+    def gather(self, n_valid: int, segments=None, group=None):
+        """Both collectives are enqueued back to back; nothing is read on the host here."""
+        self.set_mine(n_valid, segments)
+        self.gather_meta(group)
+        self.gather_records(group)
+
+    def to_host(self, order: bool = True) -> np.ndarray:
+        """The valid records of every rank (one host sync: the meta table), rank-major; `order` restores genomic order — by
+        copying whole group segments when the ranks reported them, else by a stable sort on the region ids."""
+        meta = self.meta.cpu().numpy()
+        parts, segs = [], []
+        base = 0
+        for r in range(self.world):
+            c = int(meta[r, 0])
+            a = self.records[r * self.slice_bytes: r * self.slice_bytes + c * RECORD_BYTES].cpu().numpy()
+            parts.append(a.view(PRED_RECORD))
+            off = base
+            for i in range(self.max_groups):
+                g, k = int(meta[r, 1 + 2 * i]), int(meta[r, 2 + 2 * i])
+                if g < 0:
+                    break
+                segs.append((g, off, k))
+                off += k
+            base += c
+        rec = np.concatenate(parts) if parts else np.zeros(0, PRED_RECORD)
+        if not order:
+            return rec
+        if segs and sum(k for _, _, k in segs) == rec.shape[0]:
+            segs.sort()
+            if all(segs[i][1] + segs[i][2] == segs[i + 1][1] for i in range(len(segs) - 1)):
+                return rec                                     # already in group order (static schedule)
+            return np.concatenate([rec[o:o + k] for _, o, k in segs]) if segs else rec
+        return order_records(rec)
+
+
+def order_records(rec: np.ndarray) -> np.ndarray:
+    """Genomic order = region id order (within a region the encoder's order is kept: stable sort)."""
+    if rec.shape[0] == 0 or np.all(np.diff(rec["region"]) >= 0):
+        return rec
+    return rec[np.argsort(rec["region"], kind="stable")]
+
+
+def records_from_calls(calls) -> np.ndarray:
+    """A single-GPU VariantCalls as prediction records (the 1-rank answer the N-rank gather must reproduce)."""
+    rec = np.zeros(len(calls), PRED_RECORD)
+    rec["probs"] = calls.probs
+    rec["position"] = calls.positions.astype(np.int32)
+    rec["region"] = calls.region_of
+    rec["depth"] = calls.depths
+    rec["freq"] = calls.freqs
+    rec["key"] = np.ascontiguousarray(calls.keys_raw[:, :62]).view("S62")[:, 0]
+    return rec
+
+
+class DistributedVariantCaller:
+    """make_images + run_inference of ONE job (a region list every rank can read) over all ranks of the default process group.
+
+        dvc = DistributedVariantCaller(state, local_device, capacity)
+        dvc.run(source, regions, params)        # source: abi.HostReads (pinned host buffers) or pipeline.DeviceReads
+        records = dvc.buffer.to_host()          # every rank holds the whole job's records after the gather
+    """
+
+    def __init__(self, state: dict, device: int, capacity: int, schedule: str = "dynamic", group_regions: int = 32):
+        import torch
+        import torch.distributed as dist
+        from .pipeline import VariantCaller
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.caller = VariantCaller(state, device)
+        self.device = torch.device("cuda", device)
+        self.schedule, self.group_regions = schedule, group_regions
+        self.buffer = None
+        self._capacity = capacity
+        self._calls = 0
+        self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.phase_ms = {}
+        self.groups_done = 0
+
+    def close(self):
+        self.caller.close()
+
+    def run(self, source, regions, params: dict, seq_off: np.ndarray | None = None, replicas: int = 1) -> int:
+        """Returns this rank's candidate count; the gathered records are in self.buffer (device).
+        `replicas` > 1 (benchmarks only): the job is `replicas` copies of the region list laid end to end — job group J is local
+        group J mod G with region ids shifted by (J div G) * n_regions — so that a weak-scaling run can hand out N x the
+        per-GPU block without holding N copies of it."""
+        import torch
+        from .abi import HostReads, regions_array
+        from .pipeline import DeviceReads
+        groups = plan_groups(regions.n_regions, self.group_regions)
+        G, n_reg = len(groups), regions.n_regions
+        work = group_work(seq_off, regions.table, groups) if seq_off is not None else None
+        if work is not None and replicas > 1:
+            work = np.tile(work, replicas)
+        n_job = G * replicas
+        if self.buffer is None or self.buffer.max_groups < n_job:
+            self.buffer = GatherBuffer(self._capacity, self.world, self.rank, self.device, max_groups=n_job)
+        self._calls += 1
+        claimer = GroupClaimer(n_job, self.rank, self.world, self.schedule, work, key="pb_claim_%d" % self._calls)
+        s = self.caller.stream(params, self.buffer.capacity, d_records=self.buffer.my_ptr())
+        if isinstance(source, DeviceReads):
+            def stage(j):
+                g0, g1 = groups[j % G]
+                s.stage_device(source, g0, g1, (j // G) * n_reg + g0)
+        else:
+            assert isinstance(source, HostReads)
+            regs, keep = regions_array(regions)
+            ref = np.ascontiguousarray(regions.ref, dtype=np.uint8)
+
+            def stage(j):
+                g0, g1 = groups[j % G]
+                s.stage_host(source, regs, g0, g1, ref, (j // G) * n_reg + g0)
+        cur = claimer.next()
+        if cur is not None:
+            stage(cur)
+        segments, seen = [], 0
+        while cur is not None:
+            nxt = claimer.next()                  # claimed one ahead, so that its copies overlap this group's kernels
+            tot = s.run(flush=False)
+            segments.append((cur, tot - seen))
+            seen = tot
+            if nxt is not None:
+                stage(nxt)
+            s.sync()
+            cur = nxt
+        n = s.end()
+        self.groups_done = len(segments)
+        t = self.caller.timings()
+        self.stats = s.stats()
+        self.buffer.set_mine(n, segments)
+        self._ev[0].record()
+        self.buffer.gather_meta()                 # tiny: completes when the slowest rank arrives -> the wait, not the transfer
+        self._ev[1].record()
+        self.buffer.gather_records()
+        self._ev[2].record()
+        torch.cuda.synchronize(self.device)
+        self.phase_ms = dict(encoder_ms=t["encode_ms"], network_ms=t["network_ms"], wait_ms=self._ev[0].elapsed_time(self._ev[1]),
+                             gather_ms=self._ev[1].elapsed_time(self._ev[2]), groups=len(segments))
+        return n

@@ -10,6 +10,8 @@ from __future__ import annotations
 import numpy as np
 
 from .bamio import BamReader, FastaReader
+from ._lib import PepperB200Error
+from .abi import PB_ERR_CAPACITY
 from .pipeline import FetchedReads, PolishCaller, VariantCaller, PolishCalls, VariantCalls
 from .reads import ReadTrimmer
 from .realign import Realigner, ALIGNMENT_SAFE_BASES
@@ -38,6 +40,24 @@ class _FromFiles:
         self.fasta = FastaReader(fasta_path)
         self.trimmer = ReadTrimmer(device)
         self.device = device
+        self._bam2 = None
+
+    def close(self):
+        """Releases the file readers (the second reader of call_batches included) and the trimmer."""
+        for name in ("bam", "_bam2"):
+            r = getattr(self, name, None)
+            if r is not None and hasattr(r, "close"):
+                r.close()
+            setattr(self, name, None)
+        if getattr(self, "trimmer", None) is not None:
+            self.trimmer.close()
+            self.trimmer = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
     def _ref_table(self, contig: str, rows: list[list[int]], spans: list[tuple[int, int]]) -> RegionTable:
         """Region table + reference strings: ONE faidx fetch of the covering span, the (overlapping) per-region strings are
@@ -84,8 +104,8 @@ class VariantFromFiles(_FromFiles):
             try:
                 n = self.caller.call_device(fetched, params, out)
                 break
-            except Exception as ex:                        # capacity: the library reports the need in the message-less code -3
-                if "code -3" not in str(ex):
+            except PepperB200Error as ex:                  # candidate capacity too small: retry with twice the room
+                if ex.rc != PB_ERR_CAPACITY:
                     raise
                 cap *= 2
         h = {k: v[:n].cpu().numpy() for k, v in out.items() if want_images or k != "images"}
@@ -103,8 +123,8 @@ class VariantFromFiles(_FromFiles):
     def call_batches(self, contig: str, intervals: list[tuple[int, int]], params: dict, batch: int = 32, **kw):
         """Streaming form: yields (VariantCalls, RegionTable) per batch of `batch` intervals while a helper thread inflates the next
         batch's BAM span with a second reader (pb_bam_fetch runs outside the GIL), so the host inflate overlaps the GPU work."""
-        import threading
-        if not hasattr(self, "_bam2"):
+        from concurrent.futures import ThreadPoolExecutor
+        if self._bam2 is None:
             self._bam2 = BamReader(self.bam.path, 0)
         readers = [self.bam, self._bam2]
         groups = [intervals[i:i + batch] for i in range(0, len(intervals), batch)]
@@ -112,19 +132,16 @@ class VariantFromFiles(_FromFiles):
         def span(g):
             return max(0, min(s for s, _ in g) - REGION_SAFE_BASES), max(e for _, e in g) + REGION_SAFE_BASES
 
-        box = {}
-
         def prefetch(k):
-            box[k] = readers[k & 1].fetch(contig, *span(groups[k]))
-        th = threading.Thread(target=prefetch, args=(0,))
-        th.start()
-        for k, g in enumerate(groups):
-            th.join()
-            view = box.pop(k)
-            if k + 1 < len(groups):
-                th = threading.Thread(target=prefetch, args=(k + 1,))
-                th.start()
-            yield self.call(contig, g, params, _view=view, **kw)
+            return readers[k & 1].fetch(contig, *span(groups[k]))
+        # a Future re-raises the worker's exception (bad contig, corrupt BGZF block) in the consumer
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(prefetch, 0)
+            for k, g in enumerate(groups):
+                view = fut.result()
+                if k + 1 < len(groups):
+                    fut = pool.submit(prefetch, k + 1)
+                yield self.call(contig, g, params, _view=view, **kw)
 
 
 class PolishFromFiles(_FromFiles):
@@ -159,8 +176,8 @@ class PolishFromFiles(_FromFiles):
             try:
                 n = self.caller.call_device(fetched, out)
                 break
-            except Exception as ex:
-                if "code -3" not in str(ex):
+            except PepperB200Error as ex:
+                if ex.rc != PB_ERR_CAPACITY:
                     raise
                 cap *= 2
         h = {k: v[:n].cpu().numpy() for k, v in out.items()}

@@ -18,8 +18,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from .abi import (HostReads, PbReads, PbRegion, PbVariantParams, regions_array, variant_params, WINDOW, FEATURES,
-                  ALLELE_STRIDE, POLISH_SEQ_LEN, PB_ERR_CAPACITY)
+from .abi import (HostReads, PbReads, PbRegion, PbVariantParams, PbCandidateColumns, regions_array, variant_params, WINDOW,
+                  FEATURES, ALLELE_STRIDE, POLISH_SEQ_LEN, PB_ERR_CAPACITY)
 from .synth import ReadBatch, RegionTable
 from .variant import VariantEncoder, VariantNet, _bind as _bind_variant
 from .polish import PolishEncoder, PolishNet, _bind as _bind_polish
@@ -64,6 +64,15 @@ def _bind_calls(L):
                                          C.POINTER(PbVariantParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp,
                                          C.POINTER(C.c_int64), vp]
     L.pb_variant_call_timings.argtypes = [vp, vp]
+    L.pb_variant_stream_begin.argtypes = [vp, vp, C.POINTER(PbVariantParams), C.c_int64, vp, vp]
+    L.pb_variant_stream_stage_host.argtypes = [vp, C.POINTER(PbReads), C.POINTER(PbRegion), C.c_int64, C.c_int64, vp, C.c_int32]
+    L.pb_variant_stream_stage_device.argtypes = [vp, C.POINTER(PbReads), C.POINTER(PbRegion), C.c_int64, C.c_int64, vp, C.c_int32]
+    L.pb_variant_stream_run.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int64)]
+    L.pb_variant_stream_sync.argtypes = [vp]
+    L.pb_variant_stream_end.argtypes = [vp, vp, C.POINTER(C.c_int64)]
+    L.pb_variant_stream_stats.argtypes = [vp, vp, vp, C.POINTER(C.c_int64)]
+    L.pb_variant_stream_columns.argtypes = [vp, C.POINTER(PbCandidateColumns), C.POINTER(vp), C.POINTER(vp)]
+    L.pb_variant_stream_fetch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pb_polish_call_host.argtypes = [vp, vp, C.POINTER(PbReads), C.POINTER(PbRegion), C.c_int64, C.c_int64, vp, vp, vp, vp,
                                       vp, vp, C.POINTER(C.c_int64), vp]
     L.pb_polish_call_device.argtypes = [vp, vp, C.POINTER(PbReads), vp, C.c_int64, C.POINTER(PbRegion), C.c_int64, vp, vp,
@@ -181,6 +190,73 @@ class VariantCaller:
         d = dict(encode_ms=float(ms[0]), network_ms=float(ms[1]))
         d.update({"enc_" + k: v for k, v in self.enc.timings().items()})
         return d
+
+    def stream(self, params: dict, capacity: int, d_records: int = 0, stream: int = 0) -> "VariantStream":
+        """Streaming session over region groups (pb_variant_stream_*): see VariantStream."""
+        return VariantStream(self, params, capacity, d_records, stream)
+
+
+class VariantStream:
+    """One streaming session of a VariantCaller: region GROUPS are staged and run one after the other, the candidates
+    accumulate on the device, the network runs over whole 9,472-candidate chunks as they fill.
+
+        s = caller.stream(params, capacity, d_records=ptr)      # ptr: optional device buffer for 84-byte records
+        s.stage_host(hr, regs, g0, g1, h_ref, region_id0)       # or stage_device(dreads, g0, g1, region_id0)
+        while ...:
+            s.run(last)                                         # kernels queued
+            s.stage_host(...)                                   # next group's copies overlap them
+            s.sync()
+        n = s.end()
+    """
+
+    def __init__(self, caller: VariantCaller, params: dict, capacity: int, d_records: int = 0, stream: int = 0):
+        self.c, self.L = caller, caller.L
+        self.p = variant_params(**params)
+        self.capacity = int(capacity)
+        self._keep = []
+        _lib.check(self.L.pb_variant_stream_begin(caller.enc.h, caller.net.h, C.byref(self.p), self.capacity,
+                                                  C.c_void_p(d_records or None), C.c_void_p(stream)), "pb_variant_stream_begin")
+
+    def stage_host(self, hr: HostReads, regs, g0: int, g1: int, h_ref: np.ndarray, region_id0: int = 0):
+        """`regs` = ctypes array from abi.regions_array (the FULL table the group indices refer to)."""
+        _lib.check(self.L.pb_variant_stream_stage_host(self.c.enc.h, C.byref(hr.struct), regs, g0, g1, h_ref.ctypes.data, region_id0),
+                   "pb_variant_stream_stage_host")
+
+    def stage_device(self, dreads: "DeviceReads", g0: int, g1: int, region_id0: int = 0):
+        _lib.check(self.L.pb_variant_stream_stage_device(self.c.enc.h, C.byref(dreads.struct), dreads.h_regions, g0, g1,
+                                                         C.c_void_p(dreads.d_ref), region_id0), "pb_variant_stream_stage_device")
+
+    def run(self, flush: bool = False) -> int:
+        n = C.c_int64(0)
+        rc = self.L.pb_variant_stream_run(self.c.enc.h, self.c.net.h, int(flush), C.byref(n))
+        if rc == PB_ERR_CAPACITY:
+            raise _lib.PepperB200Error("stream capacity %d too small (need >= %d so far)" % (self.capacity, n.value), rc)
+        _lib.check(rc, "pb_variant_stream_run")
+        return int(n.value)
+
+    def sync(self):
+        _lib.check(self.L.pb_variant_stream_sync(self.c.enc.h), "pb_variant_stream_sync")
+
+    def end(self) -> int:
+        n = C.c_int64(0)
+        _lib.check(self.L.pb_variant_stream_end(self.c.enc.h, self.c.net.h, C.byref(n)), "pb_variant_stream_end")
+        return int(n.value)
+
+    def stats(self) -> dict:
+        ms = (C.c_float * 5)(); nl = (C.c_int64 * 2)(); g = C.c_int64(0)
+        _lib.check(self.L.pb_variant_stream_stats(self.c.enc.h, ms, nl, C.byref(g)), "pb_variant_stream_stats")
+        d = dict(zip(("enc_prefix", "enc_count", "enc_sites", "enc_alleles", "enc_windows"), [float(x) for x in ms]))
+        d.update(encoder_launches=int(nl[0]), network_launches=int(nl[1]), groups=int(g.value))
+        return d
+
+    def fetch(self, n: int, want_images: bool = False, stream: int = 0) -> VariantCalls:
+        img = np.empty((n, WINDOW, FEATURES), np.int8) if want_images else None
+        pos = np.empty(n, np.int64); dep = np.empty(n, np.uint8); frq = np.empty(n, np.uint8)
+        keys = np.empty((n, ALLELE_STRIDE), np.uint8); rof = np.empty(n, np.int32); probs = np.empty((n, 3), np.float32)
+        _lib.check(self.L.pb_variant_stream_fetch(self.c.enc.h, n, img.ctypes.data if want_images else None, pos.ctypes.data,
+                                                  dep.ctypes.data, frq.ctypes.data, keys.ctypes.data, rof.ctypes.data,
+                                                  probs.ctypes.data, C.c_void_p(stream)), "pb_variant_stream_fetch")
+        return VariantCalls(pos, dep, frq, keys, rof, probs, img)
 
 
 class PolishCaller:

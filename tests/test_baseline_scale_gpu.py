@@ -44,7 +44,7 @@ def test_full_size_regions_vs_reference(oracle_built, platform, params, cov, see
     calls = caller.call(reads, regions, params, want_images=True)
     want = oracle_built.variant_encode(reads, regions, params, _impl(oracle_built))
     _same_candidates(calls, want, oracle_built)
-    assert len(calls) > 1000
+    assert len(calls) > (1000 if platform is synth.ONT else 100)
     probs = nets.variant_predict(state, calls.images, threads=16)
     assert np.abs(probs - calls.probs).max() < TOL, np.abs(probs - calls.probs).max()
     srt = np.sort(probs, axis=1)
