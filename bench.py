@@ -285,7 +285,13 @@ def run_variant(args, cfg):
     # bytes over PCIe per step, whole job: every group's reads go up once; the writer rank reads all records
     h2d = int((hr.nbytes + regions.table.nbytes + regions.ref.nbytes) * replicas)
     d2h = int(n_job * RECORD_BYTES + dvc.buffer.meta.numel() * 8)
+    l2_mb = dreads.nbytes / 1e6
 
+    registered = bool(dvc.buffer.registered)
+    meta_bytes = int(dvc.buffer.meta.numel() * 8)
+    if records is not None:
+        records = records.copy()
+    dvc.close()                                             # releases the NCCL-registered buffer before the process group
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -324,9 +330,9 @@ def run_variant(args, cfg):
                    "job_candidates": n_job, "schedule": schedule, "group_regions": args.group_regions,
                    "parallelism": f"region groups handed out ({schedule}) over {world} GPU(s); head kernel writes 84 B records into the "
                                   f"gather buffer; 1 all-gather of records (+1 of counts) per step",
-                   "l2": "inputs larger than L2 (%.0f MB of reads resident per GPU)" % (dreads.nbytes / 1e6),
+                   "l2": "inputs larger than L2 (%.0f MB of reads resident per GPU)" % l2_mb,
                    "weights": "seeded random (no trained checkpoint offline)", "generated_block_regions": block, "gen_seconds": round(gen_s, 1),
-                   "nccl_registered_buffer": bool(dvc.buffer.registered)},
+                   "nccl_registered_buffer": registered},
         "clocks": clocks,
         "e2e": {"value": job_bases / (e2e_ms / 1e3), "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "steps": e2e_steps,

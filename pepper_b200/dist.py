@@ -92,6 +92,7 @@ class GatherBuffer:
         self.registered = False
         nbytes = world * self.capacity * RECORD_BYTES
         dev = device if device is not None else torch.device("cpu")
+        self._dev = dev
         self.records = None
         if getattr(dev, "type", "cpu") == "cuda" and world > 1:
             try:
@@ -161,32 +162,66 @@ class GatherBuffer:
         self.gather_records(group)
 
     def to_host(self, order: bool = True) -> np.ndarray:
-        """The valid records of every rank (one host sync: the meta table), rank-major; `order` restores genomic order — by
-        copying whole group segments when the ranks reported them, else by a stable sort on the region ids."""
+        """The valid records of every rank on the host (one small host sync for the meta table, then asynchronous D2H copies
+        straight into their FINAL place in one page-locked buffer — rank-major, or group by group in genomic order when the
+        ranks reported their group segments — so no host-side re-ordering pass is needed).  The returned array is a view of
+        that buffer (valid until the next to_host)."""
+        import torch
         meta = self.meta.cpu().numpy()
-        parts, segs = [], []
-        base = 0
+        counts = [int(meta[r, 0]) for r in range(self.world)]
+        total = sum(counts)
+        segs = []                                              # (group id, source record index in the gather buffer, count)
         for r in range(self.world):
-            c = int(meta[r, 0])
-            a = self.records[r * self.slice_bytes: r * self.slice_bytes + c * RECORD_BYTES].cpu().numpy()
-            parts.append(a.view(PRED_RECORD))
-            off = base
+            off = r * self.capacity
             for i in range(self.max_groups):
                 g, k = int(meta[r, 1 + 2 * i]), int(meta[r, 2 + 2 * i])
                 if g < 0:
                     break
                 segs.append((g, off, k))
                 off += k
-            base += c
-        rec = np.concatenate(parts) if parts else np.zeros(0, PRED_RECORD)
-        if not order:
-            return rec
-        if segs and sum(k for _, _, k in segs) == rec.shape[0]:
+        by_segment = order and bool(segs) and sum(k for _, _, k in segs) == total
+        if by_segment:
             segs.sort()
-            if all(segs[i][1] + segs[i][2] == segs[i + 1][1] for i in range(len(segs) - 1)):
-                return rec                                     # already in group order (static schedule)
-            return np.concatenate([rec[o:o + k] for _, o, k in segs]) if segs else rec
-        return order_records(rec)
+            # merge neighbours that are contiguous in the source (a static schedule collapses to one copy per rank)
+            plan = []
+            for g, o, k in segs:
+                if plan and plan[-1][0] + plan[-1][1] == o:
+                    plan[-1][1] += k
+                else:
+                    plan.append([o, k])
+        else:
+            plan = [[r * self.capacity, counts[r]] for r in range(self.world)]
+        cuda = self.records.is_cuda
+        need = max(total, 1) * RECORD_BYTES
+        if getattr(self, "_host", None) is None or self._host.numel() < need:
+            self._host = torch.empty(need + need // 8, dtype=torch.uint8)
+            if cuda:
+                self._host = self._host.pin_memory()
+        dst = 0
+        for o, k in plan:
+            if k:
+                self._host[dst * RECORD_BYTES:(dst + k) * RECORD_BYTES].copy_(self.records[o * RECORD_BYTES:(o + k) * RECORD_BYTES], non_blocking=True)
+                dst += k
+        if cuda:
+            torch.cuda.current_stream(self.records.device).synchronize()
+        rec = self._host.numpy()[:total * RECORD_BYTES].view(PRED_RECORD)
+        return order_records(rec) if (order and not by_segment) else rec
+
+    def release(self):
+        """Drops the NCCL-registered pool BEFORE the process group goes away (a registered MemPool destroyed after
+        destroy_process_group aborts the process)."""
+        self.records = None
+        self.meta = None
+        pool = getattr(self, "_pool", None)
+        if pool is not None:
+            try:
+                import torch.distributed as dist
+                backend = dist.distributed_c10d._get_default_group()._get_backend(self._dev)
+                backend.deregister_mem_pool(pool)
+            except Exception:
+                pass
+            self._pool = None
+            del pool
 
 
 def order_records(rec: np.ndarray) -> np.ndarray:
@@ -233,6 +268,10 @@ class DistributedVariantCaller:
         self.groups_done = 0
 
     def close(self):
+        """Call before destroy_process_group()."""
+        if self.buffer is not None:
+            self.buffer.release()
+            self.buffer = None
         self.caller.close()
 
     def run(self, source, regions, params: dict, seq_off: np.ndarray | None = None, replicas: int = 1) -> int:

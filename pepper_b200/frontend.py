@@ -112,13 +112,24 @@ class VariantFromFiles(_FromFiles):
         return VariantCalls(h["positions"], h["depths"], h["freqs"], h["keys"], h["region_of"], h["probs"], h.get("images")), fetched_table(fetched, regions)
 
 
-    def find_candidates(self, contig: str, intervals: list[tuple[int, int]], params: dict, options: dict | None = None, **kw):
+    def find_candidate_tuples(self, contig: str, intervals: list[tuple[int, int]], params: dict, options: dict | None = None, **kw):
         """make_images + run_inference + the per-record candidate selection of find_candidates (CandidateFinder.py:356-530):
-        returns (margin_records, deepvariant_records) in the tuple layouts VcfWriter consumes."""
+        returns (margin_records, deepvariant_records) in the tuple layouts the reference's VcfWriter consumes."""
         from .candidates import find_candidates, ONT_OPTIONS
         calls, table = self.call(contig, intervals, params, want_images=False, **kw)
         return find_candidates(contig, calls.positions, calls.region_of, calls.depths, calls.freqs, calls.keys_raw, calls.probs, table,
                                options or ONT_OPTIONS)
+
+    def find_candidates(self, contig: str, intervals: list[tuple[int, int]], params: dict, options: dict | None = None,
+                        vcf_options: dict | None = None, **kw) -> list[dict]:
+        """The whole `pepper_variant find_candidates` step for one contig: make_images + run_inference, the per-record selection
+        (CUDA kernel), the (contig, position) merge with (ref, alt) de-duplication (CandidateFinder.py:547-581) and the per-site VCF
+        record assembly (VcfWriter.py:48-218).  Returns one dict per VCF record (pysam `new_record` keywords + `files`)."""
+        from .candidates import ONT_OPTIONS
+        from .vcf import find_site_records
+        calls, table = self.call(contig, intervals, params, want_images=False, **kw)
+        return find_site_records(contig, calls.positions, calls.region_of, calls.depths, calls.freqs, calls.keys_raw, calls.probs, table,
+                                 options or ONT_OPTIONS, vcf_options)
 
     def call_batches(self, contig: str, intervals: list[tuple[int, int]], params: dict, batch: int = 32, **kw):
         """Streaming form: yields (VariantCalls, RegionTable) per batch of `batch` intervals while a helper thread inflates the next

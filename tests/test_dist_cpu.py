@@ -90,8 +90,8 @@ def _worker(rank, world, port, q):
     rec["key"] = b"2AC"
     buf.my_slice()[:n * PRED_RECORD.itemsize] = torch.from_numpy(rec.view(np.uint8))
     buf.gather(n)
-    out = buf.to_host()
-    raw = buf.to_host(order=False)
+    out = buf.to_host().copy()
+    raw = buf.to_host(order=False).copy()
     q.put((rank, mine, out, raw, buf.counts.tolist()))
     dist.destroy_process_group()
 

@@ -89,7 +89,7 @@ def _rank_main(rank, world, port, q):
         for src_name in ("host", "device"):
             src = HostReads(reads, pin=True) if src_name == "host" else DeviceReads(reads, regions, device=rank)
             n = dvc.run(src, regions, params, seq_off=reads.seq_off)
-            out[(schedule, src_name)] = (dvc.buffer.to_host(), n, dict(dvc.phase_ms), dvc.buffer.registered)
+            out[(schedule, src_name)] = (dvc.buffer.to_host().copy(), n, dict(dvc.phase_ms), dvc.buffer.registered)
         dvc.close()
     q.put((rank, out))
     dist.destroy_process_group()

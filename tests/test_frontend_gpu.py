@@ -130,10 +130,19 @@ def test_variant_files_to_vcf_records(oracle_built, files):
     iv = variant_intervals(2000, 24000, 8000)
     vf = VariantFromFiles(files["bam"], files["fa"], nets.make_variant_weights(2))
     opts = dict(ONT_OPTIONS); opts["report_indel_above_freq"] = 0.5
-    m, d = vf.find_candidates("ctg", iv, params, opts)
+    m, d = vf.find_candidate_tuples("ctg", iv, params, opts)
     calls, _ = vf.call("ctg", iv, params, want_images=False)
     gs = files["genome"].tobytes().decode()
     wm, wd = ofc.select(opts, "ctg", calls.positions, calls.depths, calls.keys, calls.freqs, calls.probs, lambda c, a, b: gs[max(0, a):max(0, b)])
     assert [_norm(r) for r in m] == [_norm(r) for r in wm]
     assert [_norm(r) for r in d] == [_norm(r) for r in wd]
     assert len(d) > 10
+    # the per-site records (site merge across the shared interval boundaries, dedup, QUAL, GT): oracle restatement of the
+    # reference's merge + VCFWriter on the oracle's tuples
+    from oracle import vcf_records as ovr
+    from pepper_b200.vcf import VCF_OPTIONS_ONT
+    from tests.test_vcf_records import _norm as _n2
+    recs = vf.find_candidates("ctg", iv, params, opts)
+    contigs, sites = ovr.merge_sites(wd)
+    want = ovr.vcf_records(sites, VCF_OPTIONS_ONT)
+    assert [_n2(r) for r in recs] == [_n2(r) for r in want] and len(recs) > 10
