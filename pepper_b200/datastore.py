@@ -5,9 +5,14 @@
     polish images        pepper/modules/python/DataStore.py:53-67                 PolishImageStore.write_summary
     polish predictions   pepper/modules/python/DataStorePredict.py:49-76          PolishPredictionStore.write_prediction
 
-Group / dataset names, dtypes and shapes are the reference's.  h5py / libhdf5 are not part of the build image, so the
-backend is chosen at run time: h5py when importable (the files are then readable by the reference's own readers),
-otherwise a single-file ``.npz`` container whose keys are the HDF5 paths (same logical layout, used by the tests).
+Group / dataset names, dtypes and shapes are the reference's.  h5py / libhdf5 are not part of the build image (nor of the GPU
+box), so the backend is chosen at run time: h5py when importable, otherwise a single-file ``.npz`` container whose keys are the
+HDF5 paths.  String datasets follow the reference exactly: `candidates` is variable-length `str` (h5py.special_dtype(vlen=str),
+DataStore.py:60 / DataStorePredict.py:60 — its readers parse ``str(candidates[i])``, CandidateFinder.py:374-381), the polish
+`contig` is a `str` scalar (pepper DataStore.py:62); in the npz container those are unicode arrays, which read back as `str`
+objects just like h5py 2.10 (requirements.txt:1) returned them.  tests/test_datastore_reference_readers.py runs the
+reference's OWN reader code (both dataloader_predict.py, CandidateFinder.small_chunk_stitch, Stitch.small_chunk_stitch) over
+stores written here, through an h5py stand-in backed by the npz container.
 Deviations forced by modern numpy, all value-preserving: ``np.float`` -> ``np.float64`` (removed alias,
 DataStorePredict.py:62); int8 images are passed as int8 already (the reference casts a list of Python ints).
 """
@@ -49,6 +54,23 @@ class _Store:
         else:
             self.data[path] = np.asarray(data)
 
+    def put_vlen_str(self, path: str, rows):
+        """`rows`: list of lists of str (one list per candidate) -> variable-length string dataset [n][len(row)]."""
+        if self.backend == "h5py":
+            if path in self.f:
+                del self.f[path]
+            self.f.create_dataset(path, data=np.array(rows, dtype=h5py.special_dtype(vlen=str)))      # DataStore.py:60,67
+        else:
+            self.data[path] = np.array(rows, dtype="U")          # reads back as str objects, like a vlen-str dataset under h5py 2.10
+
+    def put_str(self, path: str, value: str):
+        if self.backend == "h5py":
+            if path in self.f:
+                del self.f[path]
+            self.f[path] = value                                  # pepper DataStore.py:62 assigns the Python str
+        else:
+            self.data[path] = np.array(value, dtype="U")
+
     def keys(self, prefix: str):
         if self.backend == "h5py":
             return list(self.f[prefix].keys()) if prefix in self.f else []
@@ -80,7 +102,7 @@ class VariantImageStore(_Store):
         self.put(g + "contigs", np.array([contig.encode()] * n, dtype="S"))
         self.put(g + "positions", np.asarray(positions, dtype=np.int32))                 # DataStore.py:64
         self.put(g + "depths", np.asarray(depths, dtype=np.uint8))
-        self.put(g + "candidates", np.array([[k.encode()] for k in keys], dtype="S64").reshape(n, 1))
+        self.put_vlen_str(g + "candidates", [[str(k)] for k in keys])                   # DataStore.py:60,67: vlen str [n][1]
         self.put(g + "candidate_frequency", np.asarray(freqs, dtype=np.uint8).reshape(n, 1))
         self.put(g + "images", np.asarray(images, dtype=np.int8).reshape(n, 33, 26))     # DataStore.py:68
 
@@ -94,7 +116,7 @@ class VariantPredictionStore(_Store):
         self.put(g + "contigs", np.array([c.encode() if isinstance(c, str) else c for c in contigs], dtype="S"))
         self.put(g + "positions", np.asarray(positions, dtype=np.int32))
         self.put(g + "depths", np.asarray(depths, dtype=np.uint8))
-        self.put(g + "candidates", np.array([[k.encode()] for k in keys], dtype="S64").reshape(n, 1))
+        self.put_vlen_str(g + "candidates", [[str(k)] for k in keys])                   # DataStorePredict.py:60,65
         self.put(g + "candidate_frequency", np.asarray(freqs, dtype=np.uint8).reshape(n, 1))
         self.put(g + "base_prediction", np.asarray(probs, dtype=np.float64).reshape(n, 3))  # np.float in the reference
 
@@ -108,7 +130,7 @@ class PolishImageStore(_Store):
         self.put(g + "label", np.zeros(1000, dtype=np.uint8) if label is None else np.asarray(label, dtype=np.uint8))
         self.put(g + "position", np.asarray(position, dtype=np.int64))
         self.put(g + "index", np.asarray(index, dtype=np.int64))
-        self.put(g + "contig", np.array(contig.encode(), dtype="S"))
+        self.put_str(g + "contig", contig)
         self.put(g + "region_start", np.int64(region_start))
         self.put(g + "region_end", np.int64(region_end))
         self.put(g + "chunk_id", np.int64(chunk_id))

@@ -15,7 +15,7 @@ def test_variant_stores_roundtrip(tmp_path):
     assert r.keys("summaries") == ["chr20_1000_2000"]
     assert r.get(g + "positions").dtype == np.int32 and r.get(g + "depths").dtype == np.uint8
     assert r.get(g + "images").dtype == np.int8 and r.get(g + "images").shape == (2, 33, 26)
-    assert r.get(g + "candidates").shape == (2, 1) and r.get(g + "candidates")[1, 0] == b"2ACG"
+    assert r.get(g + "candidates").shape == (2, 1) and r.get(g + "candidates")[1, 0] == "2ACG"
     assert r.get(g + "candidate_frequency").shape == (2, 1)
     p = str(tmp_path / "pred")
     with ds.VariantPredictionStore(p, backend="npz") as s:

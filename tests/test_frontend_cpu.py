@@ -57,7 +57,7 @@ def test_prediction_store_writers(tmp_path):
     st = VariantPredictionStore(str(tmp_path / "v.hdf"), "r", backend="npz")
     assert st.keys("predictions") == ["batch_0", "batch_1", "batch_2"]
     assert st.get("predictions/batch_2/positions").tolist() == list(range(1024, 1030))
-    assert st.get("predictions/batch_0/base_prediction").shape == (512, 3) and st.get("predictions/batch_0/candidates")[0, 0] == b"1T"
+    assert st.get("predictions/batch_0/base_prediction").shape == (512, 3) and st.get("predictions/batch_0/candidates")[0, 0] == "1T"
     pc = PolishCalls(np.ones((3, 1000), np.uint8), np.full((3, 1000), 20, np.uint8), np.tile(np.arange(1000, dtype=np.int64), (3, 1)),
                      np.zeros((3, 1000), np.int32), np.array([0, 0, 1], np.int32), np.array([0, 1, 0], np.int32))
     with PolishPredictionStore(str(tmp_path / "p.hdf"), "w", backend="npz") as st:
