@@ -213,7 +213,7 @@ def run_variant(args, cfg):
     schedule = args.schedule or ("dynamic" if world > 1 else "static")
     # per-rank record capacity: the even share of the job + head room for a rank that claims more groups than its share
     est = max(4096, int(regions.genomic_bases() * replicas / world / (45 if cfg["platform"] == "ONT" else 250)))
-    cap = int(est * (1.25 if world > 1 else 1.0))
+    cap = int(est * (1.5 if world > 1 else 1.0))
     dvc = DistributedVariantCaller(weights.random_variant_state(0), local, capacity=cap, schedule=schedule, group_regions=args.group_regions)
     dreads = DeviceReads(reads, regions, device=local)
 
@@ -261,6 +261,7 @@ def run_variant(args, cfg):
     # ---- end-to-end leg: pinned host reads -> H2D -> kernels -> gather -> D2H of the job's records on the writer rank
     hr = HostReads(reads, pin=True)
     e2e_steps = max(1, args.e2e_steps)
+    barrier()                                               # page-locking 4 GB takes a different time on every rank
     step(hr)                                                # warm-up of the staging buffers
     if rank == 0:
         dvc.buffer.to_host()

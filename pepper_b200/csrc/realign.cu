@@ -33,7 +33,8 @@ constexpr int GO = 8, GE = 2, MATCH = 4, MISM = 6, BIAS = 6;
 constexpr int NEG = -(1 << 28);
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int RMAX = 42;                      // rows per lane held in registers: reads up to 32 * 42 = 1344 bases
-constexpr int RBIG = 320;                     // fallback (local memory): reads up to 10240 bases
+constexpr int RDYN = 0;                       // fallback for longer reads (e.g. a soft clip of tens of kb ending inside the region): rows in a
+                                              // global scratch slab [row][lane], any length — the reference's SSW has no limit either
 
 struct Task {                                 // one read against the region reference from its own start
     int64_t q_off;                            // offset of the read's codes in `codes`
@@ -89,20 +90,28 @@ struct SwBest { int score, ref, read; };
 // 1 descending over [0, refLen).  lanesL = 16 (byte mode) / 8 (word mode).
 template <int R>
 __device__ __noinline__ SwBest sw_pass(const int8_t *__restrict__ codes, int64_t qbase, int qstep, int readLen, const int8_t *__restrict__ ref,
-                                       int refLen, int ref_dir, int lanesL, bool byte_mode, int terminate, int lane) {
+                                       int refLen, int ref_dir, int lanesL, bool byte_mode, int terminate, int lane, int *__restrict__ gHE = nullptr) {
+    constexpr bool DYN = R == RDYN;                           // rows in the global slab gHE: H at [2r][lane], E at [2r+1][lane]
+    constexpr int RA = DYN ? 1 : R;
     const int Rl = (readLen + 31) >> 5;
     const int S = (readLen + lanesL - 1) / lanesL;
     const int p0 = lane * Rl;
     const int cnt = max(0, min(Rl, readLen - p0));
-    constexpr int UNR = R <= 64 ? R : 1;                      // the big-read fallback keeps its rows in local memory
-    int H[R], E[R];
-    uint32_t qc[(R + 7) / 8];
+    constexpr int UNR = DYN ? 1 : R;
+    int Hreg[RA], Ereg[RA];
+    uint32_t qc[(RA + 7) / 8];
+    auto Hr = [&](int r) -> int & { if constexpr (DYN) return gHE[((int64_t) 2 * r) * 32 + lane]; else return Hreg[r]; };
+    auto Er = [&](int r) -> int & { if constexpr (DYN) return gHE[((int64_t) 2 * r + 1) * 32 + lane]; else return Ereg[r]; };
+    auto Qr = [&](int r) -> int {
+        if constexpr (DYN) return (int) (codes[qbase + (int64_t) qstep * (p0 + r)] & 15);
+        else return (int) ((qc[r >> 3] >> (4 * (r & 7))) & 15);
+    };
 #pragma unroll UNR
-    for (int k = 0; k < (R + 7) / 8; k++) qc[k] = 0;
+    for (int k = 0; k < (RA + 7) / 8; k++) qc[k] = 0;
 #pragma unroll UNR
-    for (int r = 0; r < R; r++) {
-        H[r] = 0; E[r] = 0;
-        if (r < cnt) qc[r >> 3] |= (uint32_t) (codes[qbase + (int64_t) qstep * (p0 + r)] & 15) << (4 * (r & 7));
+    for (int r = 0; r < (DYN ? cnt : R); r++) {
+        Hr(r) = 0; Er(r) = 0;
+        if constexpr (!DYN) { if (r < cnt) qc[r >> 3] |= (uint32_t) (codes[qbase + (int64_t) qstep * (p0 + r)] & 15) << (4 * (r & 7)); }
     }
     int reset_r = (S - p0 % S) % S;                           // row of this block that starts a stripe segment
     if (reset_r >= cnt) reset_r = -1;
@@ -117,21 +126,21 @@ __device__ __noinline__ SwBest sw_pass(const int8_t *__restrict__ codes, int64_t
         if (lane == 0) up = 0;
         // pass 1 (descending): H[r] <- max(diag + s, E, 0) using the previous column's H
 #pragma unroll UNR
-        for (int r = (R <= 64 ? R : cnt) - 1; r >= 0; r--) {
+        for (int r = (DYN ? cnt : R) - 1; r >= 0; r--) {
             if (r < cnt) {
-                const int code = (int) ((qc[r >> 3] >> (4 * (r & 7))) & 15);
+                const int code = Qr(r);
                 const int s = (code == rc && rc < 4) ? MATCH : -MISM;
-                const int diag = (r == 0 ? up : H[r - 1]) + s;
-                H[r] = max(max(diag, E[r]), 0);
+                const int diag = (r == 0 ? up : Hr(r - 1)) + s;
+                Hr(r) = max(max(diag, Er(r)), 0);
             }
         }
         // block transfer of the two F chains: F_out = max(F_in + d, A)
         int aloc = 0, afull = 0;
 #pragma unroll UNR
-        for (int r = 0; r < (R <= 64 ? R : cnt); r++) {
+        for (int r = 0; r < (DYN ? cnt : R); r++) {
             if (r < cnt) {
                 if (r == reset_r) aloc = 0;
-                const int open = max(H[r] - GO, 0);
+                const int open = max(Hr(r) - GO, 0);
                 aloc = max(aloc - GE, open);
                 afull = max(afull - GE, open);
             }
@@ -157,16 +166,16 @@ __device__ __noinline__ SwBest sw_pass(const int8_t *__restrict__ codes, int64_t
         // pass 2 (ascending): finish H / E / F, lane-local best in (column, row) order
         int cm = 0;
 #pragma unroll UNR
-        for (int r = 0; r < (R <= 64 ? R : cnt); r++) {
+        for (int r = 0; r < (DYN ? cnt : R); r++) {
             if (r < cnt) {
                 if (r == reset_r) floc = 0;
-                const int hm = max(H[r], floc);
+                const int hm = max(Hr(r), floc);
                 const int open = max(hm - GO, 0);
-                E[r] = max(E[r] - GE, open);
+                Er(r) = max(Er(r) - GE, open);
                 floc = max(floc - GE, open);
                 const int hf = max(hm, ffull);
                 ffull = max(ffull - GE, open);
-                H[r] = hf;
+                Hr(r) = hf;
                 cm = max(cm, hf);
                 if (hf > lbest) { lbest = hf; lcol = c; lrow = p0 + r; }
                 if (r == cnt - 1) hlast = hf;
@@ -193,22 +202,24 @@ __device__ __noinline__ SwBest sw_pass(const int8_t *__restrict__ codes, int64_t
 // ssw_align steps 1-2 (ssw.c:801-866): score / end (byte then word), begin by the reverse pass
 template <int R>
 __global__ void __launch_bounds__(128) k_sw(const Task *__restrict__ tasks, const int32_t *__restrict__ order, int64_t n, const int8_t *__restrict__ codes,
-                                            const int8_t *__restrict__ rcodes, Aln *__restrict__ out) {
+                                            const int8_t *__restrict__ rcodes, Aln *__restrict__ out, int *__restrict__ slab = nullptr,
+                                            const int64_t *__restrict__ slab_off = nullptr) {
     const int64_t w = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n) return;
     const int64_t a = order[w];
     const Task t = tasks[a];
+    int *gHE = (R == RDYN) ? slab + slab_off[w] : nullptr;      // this warp's [2 * rows][32] slab
     Aln res = {0, -1, 0, -1, 0, 0};
     if (t.q_len > 0 && t.r_len > 0) {
         const int8_t *ref = rcodes + t.r_off;
         bool word = false;
-        SwBest b = sw_pass<R>(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 16, true, 255, lane);
-        if (b.score == 255) { b = sw_pass<R>(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 8, false, 65535, lane); word = true; }
+        SwBest b = sw_pass<R>(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 16, true, 255, lane, gHE);
+        if (b.score == 255) { b = sw_pass<R>(codes, t.q_off, 1, t.q_len, ref, t.r_len, 0, 8, false, 65535, lane, gHE); word = true; }
         res.score = b.score; res.ref_end = b.ref; res.read_end = b.read;
         if (b.score > 1 && b.ref >= 0) {                       // results with score <= 1 are never used (simple_aligner.cpp:84)
-            const SwBest rb = word ? sw_pass<R>(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 8, false, b.score, lane)
-                                   : sw_pass<R>(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 16, true, b.score, lane);
+            const SwBest rb = word ? sw_pass<R>(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 8, false, b.score, lane, gHE)
+                                   : sw_pass<R>(codes, t.q_off + b.read, -1, b.read + 1, ref, b.ref + 1, 1, 16, true, b.score, lane, gHE);
             res.ref_begin = rb.ref; res.read_begin = b.read - rb.read;
             res.status = 1;
         }
@@ -637,7 +648,8 @@ struct pb_realigner {
     int device = 0;
     int sms = 148;
     DevBuf codes, rcodes, tasks, region_of, err, alns, order, list, scratch, pool, pool_used, cig_off, cig_len, out_nc;
-    DevBuf o_pos, o_cigar_off, o_cigar, scal;
+    DevBuf o_pos, o_cigar_off, o_cigar, scal, slab, slab_off;
+    int64_t n_long = 0;                          // reads that took the global-slab kernel in the last call
     DevBuf h_pos, h_seq_off, h_cigar_off, h_flags, h_mapq, h_seq, h_qual, h_cigar, h_regions, h_ref;
     pb_reads_t in{};
     int64_t out_cigar = 0;
@@ -667,7 +679,7 @@ extern "C" int pb_realigner_create(pb_realigner_t **out, int device) {
 extern "C" int pb_realigner_destroy(pb_realigner_t *t) {
     if (!t) return PB_OK;
     DevBuf *bufs[] = {&t->codes, &t->rcodes, &t->tasks, &t->region_of, &t->err, &t->alns, &t->order, &t->list, &t->scratch, &t->pool,
-                      &t->pool_used, &t->cig_off, &t->cig_len, &t->out_nc, &t->o_pos, &t->o_cigar_off, &t->o_cigar, &t->scal, &t->h_pos,
+                      &t->pool_used, &t->cig_off, &t->cig_len, &t->out_nc, &t->o_pos, &t->o_cigar_off, &t->o_cigar, &t->scal, &t->slab, &t->slab_off, &t->h_pos,
                       &t->h_seq_off, &t->h_cigar_off, &t->h_flags, &t->h_mapq, &t->h_seq, &t->h_qual, &t->h_cigar, &t->h_regions, &t->h_ref};
     for (auto *b : bufs) b->release();
     for (auto &e : t->evt) if (e) cudaEventDestroy(e);
@@ -684,7 +696,7 @@ extern "C" int pb_realign_device(pb_realigner_t *t, const pb_reads_t *dr, const 
     const int64_t n = dr->n_reads;
     t->in = *dr;
     *out = *dr;
-    t->out_cigar = 0; t->n_realigned = 0; t->n_sw = 0;
+    t->out_cigar = 0; t->n_realigned = 0; t->n_sw = 0; t->n_long = 0;
     if (n == 0) return PB_OK;
     std::vector<int64_t> so(n + 1), co2(2);
     PB_CUDA(cudaMemcpyAsync(so.data(), dr->seq_off, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, st));
@@ -693,7 +705,6 @@ extern "C" int pb_realign_device(pb_realigner_t *t, const pb_reads_t *dr, const 
     const int64_t nb = so[n], nc_in = co2[0];
     int64_t max_len = 0;
     for (int64_t r = 0; r < n; r++) max_len = std::max(max_len, so[r + 1] - so[r]);
-    if (max_len > 32 * RBIG) { set_error("read of %lld bases exceeds the realigner's limit (%d)", (long long) max_len, 32 * RBIG); return PB_ERR_ARG; }
     int64_t max_ref = 0;
     for (int64_t g = 0; g < n_regions; g++) max_ref = std::max(max_ref, h_regions[g].ref_len);
     PB_CUDA(cudaEventRecord(t->evt[0], st));
@@ -722,8 +733,19 @@ extern "C" int pb_realign_device(pb_realigner_t *t, const pb_reads_t *dr, const 
     int64_t n_big = 0;
     while (n_big < n && so[order[n_big] + 1] - so[order[n_big]] > 32 * RMAX) n_big++;
     PB_TRY(upload(t->order, order.data(), sizeof(int32_t) * n, st));
-    if (n_big) k_sw<RBIG><<<(unsigned) ceil_div(n_big * 32, 128), 128, 0, st>>>(t->tasks.as<Task>(), t->order.as<int32_t>(), n_big, t->codes.as<int8_t>(),
-                                                                               t->rcodes.as<int8_t>(), t->alns.as<Aln>());
+    if (n_big) {
+        // reads beyond the register kernels (no upper bound on the length): one slab of 2 x ceil(len / 32) rows x 32 lanes per read
+        std::vector<int64_t> slab_off((size_t) n_big + 1, 0);
+        for (int64_t i = 0; i < n_big; i++) {
+            const int64_t len = so[order[i] + 1] - so[order[i]];
+            slab_off[i + 1] = slab_off[i] + 2 * ((len + 31) / 32) * 32;
+        }
+        PB_TRY(t->slab.reserve(sizeof(int32_t) * (size_t) slab_off[n_big]));
+        PB_TRY(upload(t->slab_off, slab_off.data(), sizeof(int64_t) * (n_big + 1), st));
+        k_sw<RDYN><<<(unsigned) ceil_div(n_big * 32, 128), 128, 0, st>>>(t->tasks.as<Task>(), t->order.as<int32_t>(), n_big, t->codes.as<int8_t>(),
+                                                                        t->rcodes.as<int8_t>(), t->alns.as<Aln>(), t->slab.as<int>(), t->slab_off.as<int64_t>());
+        t->n_long = n_big;
+    }
     if (n - n_big) {
         static const bool force_i32 = getenv("PB_REALIGN_I32") && atoi(getenv("PB_REALIGN_I32")) != 0;     // debug: int32 kernel for every read
         if (force_i32) {

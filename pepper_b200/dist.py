@@ -79,6 +79,12 @@ class GroupClaimer:
         g = int(self.store.add(self.key, 1)) - 1
         return g if g < self.n else None
 
+    def exhausted(self) -> bool:
+        """Dynamic schedule: has every group been claimed?  (a rank that stopped claiming for lack of room checks this)"""
+        if self._it is not None:
+            return True
+        return int(self.store.add(self.key, 0)) >= self.n
+
 
 class GatherBuffer:
     """[world][capacity] prediction records + [world] counts.  On NCCL the record tensor is allocated from NCCL's own
@@ -309,10 +315,16 @@ class DistributedVariantCaller:
         if cur is not None:
             stage(cur)
         segments, seen = [], 0
+        # a rank stops claiming when its slice of the gather buffer could not hold two more groups (the one in flight and the
+        # one it would claim): under the dynamic schedule a rank that started early may otherwise take more than its capacity;
+        # what it leaves is claimed by the others
+        worst = max(1, self.buffer.capacity // max(4, 2 * n_job // max(1, self.world)))
         while cur is not None:
-            nxt = claimer.next()                  # claimed one ahead, so that its copies overlap this group's kernels
+            room = self.buffer.capacity - seen
+            nxt = claimer.next() if room >= 2.2 * worst else None     # claimed one ahead: its copies overlap this group's kernels
             tot = s.run(flush=False)
             segments.append((cur, tot - seen))
+            worst = max(worst, tot - seen)
             seen = tot
             if nxt is not None:
                 stage(nxt)
@@ -331,4 +343,9 @@ class DistributedVariantCaller:
         torch.cuda.synchronize(self.device)
         self.phase_ms = dict(encoder_ms=t["encode_ms"], network_ms=t["network_ms"], wait_ms=self._ev[0].elapsed_time(self._ev[1]),
                              gather_ms=self._ev[1].elapsed_time(self._ev[2]), groups=len(segments))
+        if self.schedule == "dynamic" and self.world > 1:
+            done = int((self.buffer.meta[:, 1::2] >= 0).sum().item())
+            if done != n_job:
+                raise RuntimeError("only %d of %d groups were run: every rank's record capacity (%d) is exhausted — raise `capacity`"
+                                   % (done, n_job, self.buffer.capacity))
         return n

@@ -118,10 +118,11 @@ def test_two_rank_gather_equals_one_rank():
     for p in procs:
         p.join(timeout=120)
     for key in res[0]:
-        n_tot = 0
+        n_tot, g_tot = 0, 0
         for rank in range(world):
             rec, n, phases, registered = res[rank][key]
             assert np.array_equal(rec, want), (key, rank)
             n_tot += n
-            assert phases["network_ms"] > 0 and phases["groups"] > 0
-        assert n_tot == want.shape[0]
+            g_tot += phases["groups"]
+            assert (phases["network_ms"] > 0) == (n > 0)           # under the dynamic schedule a rank may end up with no group at all
+        assert n_tot == want.shape[0] and g_tot == 15                # 72 regions in groups of 5, each group run exactly once

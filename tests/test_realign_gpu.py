@@ -108,6 +108,30 @@ def test_realign_long_reads_fallback_kernel(oracle_built):
     ra.close()
 
 
+def test_realign_read_with_soft_clip_over_10kb(oracle_built):
+    """a read that ends inside a ~1.2 kb polish region but carries a soft clip of > 10 kb (get_reads keeps trailing
+    soft clips, bam_handler.cpp:240-266) used to abort the whole batch (32 x 320 = 10,240-base limit).  The global-slab kernel has
+    no length limit, like the reference's SSW: the 13 kb read aligns, the others are unaffected."""
+    from pepper_b200.realign import Realigner
+    rng = np.random.default_rng(18)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 1300))
+    junk = "".join("ACGT"[i] for i in rng.integers(0, 4, 12500))
+    long_q = ref[300:1100] + junk                                 # 800 aligned bases + a 12.5 kb tail that matches nothing
+    recs = [dict(pos=100, seq=ref[100:900], cigar=[(0, 800)]),
+            dict(pos=300, seq=long_q, cigar=[(0, 800), (4, len(junk))]),
+            dict(pos=400, seq=ref[400:1000].replace("C", "G", 3), cigar=[(0, 600)])]
+    reads = synth.make_batch(recs)
+    tab = np.array([[0, 1280, 0, 1280, 0, 1300, 0, 3]], dtype=np.int64)
+    regions = synth.RegionTable(tab, np.frombuffer(ref.encode(), dtype=np.uint8))
+    want_pos, want_off, want_cig = oracle_realign(oracle_built, reads, regions)
+    ra = Realigner(0)
+    got = ra.realign(reads, regions)
+    assert np.array_equal(got.pos, want_pos) and np.array_equal(got.cigar_off, want_off) and np.array_equal(got.cigar, want_cig)
+    a, b = int(got.cigar_off[1]), int(got.cigar_off[2])
+    assert int(got.cigar[b - 1]) & 15 == 4 and int(got.cigar[b - 1]) >> 4 >= 12000      # the tail comes back as one soft clip
+    ra.close()
+
+
 def test_realign_properties_large_batch():
     """Properties at a size the oracle is not run at: sequences untouched, CIGAR read-consumption equals the read length, positions
     only move right, the realigned span stays inside the region reference, and the result is deterministic."""
