@@ -200,6 +200,18 @@ const char *pb_bam_header_text(pb_bam_t *b, int64_t *len);     /* get_sample_nam
 int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_records_t *h_view);
 int pb_bam_io_stats(pb_bam_t *b, int64_t *compressed_bytes, int64_t *inflated_bytes);
 
+/* GPU fetch: the same records as pb_bam_fetch, but only the COMPRESSED BGZF blocks are copied to the
+ * device; DEFLATE inflate (one warp per BGZF block), the record-chain walk (one thread per BAI linear-index window start), the
+ * record parse and the scatter into the structure-of-arrays are kernels.  `view` receives DEVICE pointers owned by the
+ * reader (valid until its next pb_bam_fetch_device) — the input of pb_get_reads_plan_device.  Replaces bgzf_read / bam_read1 /
+ * sam_itr_next under BAM_handler::get_reads (bam_handler.cpp:115-135).                                                        */
+int pb_bam_fetch_device(pb_bam_t *bam, int tid, int64_t beg, int64_t end, int device, pb_records_t *view, void *stream);
+/* device time (ms) of the last pb_bam_fetch_device: [H2D + inflate, record chains + parse, scatter] */
+int pb_bam_fetch_device_timings(pb_bam_t *bam, float *ms3);
+/* diagnostics: raw DEFLATE streams inflated by the GPU kernel (outputs concatenated; h_status[i] != 0 = rejected stream) */
+int pb_inflate_blocks_host(const uint8_t *h_comp, int64_t comp_bytes, const int64_t *h_in_off, const int32_t *h_in_len,
+                           const int32_t *h_out_len, int64_t n_blocks, uint8_t *h_out, int32_t *h_status, void *stream);
+
 typedef struct pb_fasta pb_fasta_t;
 int pb_fasta_open(pb_fasta_t **out, const char *path);          /* FASTA_handler(path): path + ".fai" must exist       */
 int pb_fasta_close(pb_fasta_t *f);

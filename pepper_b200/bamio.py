@@ -26,6 +26,9 @@ def _bind(L):
     L.pb_bam_header_text.restype = C.c_void_p
     L.pb_bam_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(PbRecords)]
     L.pb_bam_io_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.pb_bam_fetch_device.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.POINTER(PbRecords), C.c_void_p]
+    L.pb_bam_fetch_device_timings.argtypes = [C.c_void_p, C.c_void_p]
+    L.pb_inflate_blocks_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pb_fasta_open.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
     L.pb_fasta_close.argtypes = [C.c_void_p]
     L.pb_fasta_n_contigs.argtypes = [C.c_void_p]
@@ -62,6 +65,59 @@ class HostRecordsView:
         nb, nc = int(seq_off[-1]), int(cigar_off[-1])
         return RecordBatch(arr(s.pos, n, np.int64), seq_off, cigar_off, arr(s.flag, n, np.uint16), arr(s.mapq, n, np.uint8),
                            arr(s.seq, (nb + 1) // 2, np.uint8), arr(s.qual, nb, np.uint8), arr(s.cigar, nc, np.uint32))
+
+
+class DeviceRecordsView:
+    """pb_records_t whose pointers are reader-owned DEVICE buffers (valid until the reader's next fetch_device): what
+    ReadTrimmer.get_reads takes through pb_get_reads_plan_device."""
+    on_host = False
+
+    def __init__(self, struct: PbRecords, owner, device: int):
+        self.struct = struct
+        self._owner = owner
+        self.device = device
+
+    @property
+    def n_records(self) -> int:
+        return int(self.struct.n_records)
+
+    def to_batch(self) -> RecordBatch:
+        """Copy to the host (tests)."""
+        import torch
+        s = self.struct
+        n = int(s.n_records)
+
+        def arr(ptr, count, dtype):
+            if count == 0 or not ptr:
+                return np.zeros(0, dtype=dtype)
+            out = np.empty(count, dtype=dtype)
+            rc = torch.cuda.cudart().cudaMemcpy(out.ctypes.data, ptr, out.nbytes, 2)      # cudaMemcpyDeviceToHost
+            if int(rc) != 0:
+                raise _lib.PepperB200Error("cudaMemcpy D2H failed (%s)" % rc)
+            return out
+        seq_off = arr(s.seq_off, n + 1, np.int64)
+        cigar_off = arr(s.cigar_off, n + 1, np.int64)
+        nb, nc = int(seq_off[-1]), int(cigar_off[-1])
+        return RecordBatch(arr(s.pos, n, np.int64), seq_off, cigar_off, arr(s.flag, n, np.uint16), arr(s.mapq, n, np.uint8),
+                           arr(s.seq, (nb + 1) // 2, np.uint8), arr(s.qual, nb, np.uint8), arr(s.cigar, nc, np.uint32))
+
+
+def inflate_blocks(streams: list[bytes], sizes: list[int]):
+    """Raw DEFLATE streams through the GPU kernel (diagnostics / tests): returns (list of outputs, status array)."""
+    _lib.require_gpu()
+    L = _lib.lib()
+    _bind(L)
+    n = len(streams)
+    comp = np.frombuffer(b"".join(streams) + b"\0" * 16, dtype=np.uint8).copy()
+    lens = np.array([len(s) for s in streams], dtype=np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.int64) if n else np.zeros(0, np.int64)
+    outl = np.array(sizes, dtype=np.int32)
+    out = np.zeros(int(outl.sum()) + 1, dtype=np.uint8)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    _lib.check(L.pb_inflate_blocks_host(comp.ctypes.data, int(lens.sum()), offs.ctypes.data, lens.ctypes.data, outl.ctypes.data, n,
+                                        out.ctypes.data, status.ctypes.data, None), "pb_inflate_blocks_host")
+    cuts = np.concatenate([[0], np.cumsum(outl)]).astype(np.int64)
+    return [bytes(out[cuts[i]:cuts[i + 1]]) for i in range(n)], status[:n]
 
 
 class BamReader:
@@ -115,6 +171,20 @@ class BamReader:
         view = PbRecords()
         _lib.check(self.L.pb_bam_fetch(self.h, tid, beg, end, C.byref(view)), "pb_bam_fetch")
         return HostRecordsView(view, self)
+
+    def fetch_device(self, contig: str, beg: int, end: int, device: int = 0, stream: int = 0) -> DeviceRecordsView:
+        """The records of fetch(), produced on the GPU: only the compressed BGZF blocks cross PCIe (pb_bam_fetch_device)."""
+        tid = self.L.pb_bam_contig_id(self.h, contig.encode())
+        if tid < 0:
+            raise _lib.PepperB200Error(f"contig {contig!r} is not in {self.path}")
+        view = PbRecords()
+        _lib.check(self.L.pb_bam_fetch_device(self.h, tid, beg, end, device, C.byref(view), C.c_void_p(stream)), "pb_bam_fetch_device")
+        return DeviceRecordsView(view, self, device)
+
+    def fetch_device_timings(self) -> dict:
+        ms = (C.c_float * 3)()
+        self.L.pb_bam_fetch_device_timings(self.h, ms)
+        return dict(inflate_ms=float(ms[0]), chain_parse_ms=float(ms[1]), scatter_ms=float(ms[2]))
 
     def io_stats(self) -> tuple[int, int]:
         a, b = C.c_int64(0), C.c_int64(0)

@@ -7,8 +7,11 @@
 // pos < end && pos + max(rlen, n_cigar ? 0 : 1) > beg - as a pb_records_t in (page-locked when a GPU is present) host
 // memory, ready for pb_get_reads_plan_host / one cudaMemcpy.  BGZF blocks of a fetch are inflated by a thread pool and
 // the records are scattered into the SoA arrays in parallel; the trim itself runs on the GPU (get_reads.cu).
-// This file contains no device code; it is host plumbing, not a compute fallback.
+// pb_bam_fetch is host plumbing (thread-pool zlib inflate); pb_bam_fetch_device is the GPU path: the host only selects the BGZF
+// blocks (index arithmetic + block headers) and copies their COMPRESSED bytes; inflate, record walk, parse and the SoA
+// scatter are kernels (bgzf_inflate.cuh) and the records never visit host memory.
 #include "common.cuh"
+#include "bgzf_inflate.cuh"
 #include <zlib.h>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -202,6 +205,13 @@ struct pb_bam {
     } ubuf;
     HostBuf o_pos, o_seq_off, o_cigar_off, o_flag, o_mapq, o_seq, o_qual, o_cigar;
     int64_t n_compressed = 0, n_inflated = 0;
+    // device path (pb_bam_fetch_device)
+    int device = -1;
+    HostBuf c_host;                     // page-locked staging of the compressed blocks
+    pb::DevBuf d_comp, d_blocks, d_status, d_ubuf, d_starts, d_stops, d_counts, d_base, d_rec_off, d_info, d_keep32, d_lseq32, d_ncig32,
+        d_keep_off, d_so, d_co, d_scal, d_pos, d_seq_off, d_cigar_off, d_flag, d_mapq, d_seq, d_qual, d_cigar;
+    float dev_ms[3] = {0, 0, 0};        // inflate, chain + parse, scatter
+    cudaEvent_t dev_evt[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct pb_fasta {
@@ -220,8 +230,9 @@ int inflate_range(pb_bam *b, size_t c0, size_t c1_block, std::vector<Block> &blo
     while (off <= c1_block && off < b->f.n) {
         size_t data_off;
         const size_t bs = bgzf_block_size(b->f.p, b->f.n, off, &data_off);
-        if (!bs) { set_error("corrupt BGZF block at offset %zu", off); return PB_ERR_ARG; }
+        if (!bs || bs < data_off + 8) { set_error("corrupt BGZF block at offset %zu", off); return PB_ERR_ARG; }       // header + CRC32 + ISIZE must fit
         const uint32_t isize = rd32(b->f.p + off + bs - 4);
+        if (isize > 65536) { set_error("BGZF block at offset %zu claims %u inflated bytes (limit 65536)", off, isize); return PB_ERR_ARG; }
         blocks.push_back({off, data_off, bs, isize, utotal});
         utotal += isize;
         off += bs;
@@ -359,6 +370,11 @@ extern "C" int pb_bam_close(pb_bam_t *b) {
     if (!b) return PB_OK;
     HostBuf *bufs[] = {&b->o_pos, &b->o_seq_off, &b->o_cigar_off, &b->o_flag, &b->o_mapq, &b->o_seq, &b->o_qual, &b->o_cigar};
     for (auto *x : bufs) x->release();
+    b->c_host.release();
+    pb::DevBuf *dbufs[] = {&b->d_comp, &b->d_blocks, &b->d_status, &b->d_ubuf, &b->d_starts, &b->d_stops, &b->d_counts, &b->d_base, &b->d_rec_off, &b->d_info,
+                           &b->d_keep32, &b->d_lseq32, &b->d_ncig32, &b->d_keep_off, &b->d_so, &b->d_co, &b->d_scal, &b->d_pos, &b->d_seq_off, &b->d_cigar_off,
+                           &b->d_flag, &b->d_mapq, &b->d_seq, &b->d_qual, &b->d_cigar};
+    if (b->device >= 0) { cudaSetDevice(b->device); for (auto *x : dbufs) x->release(); for (auto &e : b->dev_evt) if (e) cudaEventDestroy(e); }
     b->f.close();
     delete b->pool;
     delete b;
@@ -451,8 +467,13 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
                     const size_t pe = std::min(upos_of(blocks, merged[ci].end, utotal), utotal);
                     while (p + 4 <= pe) {
                         const uint32_t bs = rd32(u.data() + p);
-                        if (p + 4 + bs > utotal) { set_error("BAM record runs past its chunk"); return PB_ERR_ARG; }
+                        if (bs < 32 || p + 4 + (size_t) bs > utotal) { set_error("BAM record runs past its chunk"); return PB_ERR_ARG; }
                         const uint8_t *r = u.data() + p + 4;
+                        // fixed fields + name + cigar + sequence + qualities must fit in the record (a corrupt record would otherwise be
+                        // read out of bounds by the parse / scatter passes)
+                        if (32ull + r[8] + 4ull * rd16(r + 12) + ((uint64_t) rd32(r + 16) + 1) / 2 + rd32(r + 16) > bs) {
+                            set_error("malformed BAM record at inflated offset %zu", p); return PB_ERR_ARG;
+                        }
                         const int32_t rtid = rdi32(r), pos = rdi32(r + 4);
                         if (rtid != tid || pos >= end) { if (rtid > tid || (rtid == tid && pos >= end)) { done = true; break; } p += 4 + bs; continue; }
                         cand.push_back(p);
@@ -489,7 +510,7 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
                                     const char st = (char) a[0];
                                     const uint32_t cnt = rd32(a + 1);
                                     const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
-                                    if (t0 == 'C' && t1 == 'G' && st == 'I') { n_cigar = cnt; cigar = a + 5; }
+                                    if (t0 == 'C' && t1 == 'G' && st == 'I' && a + 5 + 4ull * cnt <= ae) { n_cigar = cnt; cigar = a + 5; }
                                     sz = 5 + es * cnt;
                                 } else break;
                                 a += sz;
@@ -575,6 +596,264 @@ extern "C" int pb_bam_fetch(pb_bam_t *b, int tid, int64_t beg, int64_t end, pb_r
     view->pos = o_pos; view->seq_off = b->o_seq_off.as<int64_t>(); view->cigar_off = b->o_cigar_off.as<int64_t>();
     view->flag = o_flag; view->mapq = o_mapq; view->seq = o_seq; view->qual = o_qual; view->cigar = o_cigar;
     return PB_OK;
+}
+
+
+namespace {
+
+// chunks of (tid, [beg, end)) from the bin index, clipped by the linear index, sorted and merged (SAMv1 5.1.1) — the same selection
+// pb_bam_fetch makes
+void select_chunks(const RefIndex &ri, int64_t beg, int64_t end, std::vector<Chunk> &merged) {
+    std::vector<uint32_t> bins;
+    reg2bins(beg, end, bins);
+    uint64_t min_off = 0;
+    if (!ri.linear.empty()) {
+        const size_t w = (size_t) (beg >> 14);
+        min_off = ri.linear[std::min(w, ri.linear.size() - 1)];
+        if (w >= ri.linear.size()) min_off = ri.linear.back();
+    }
+    std::vector<Chunk> chunks;
+    for (uint32_t bin : bins) {
+        auto it = ri.bins.find(bin);
+        if (it == ri.bins.end()) continue;
+        for (const Chunk &c : it->second) if (c.end > min_off) chunks.push_back(c);
+    }
+    std::sort(chunks.begin(), chunks.end(), [](const Chunk &a, const Chunk &c) { return a.beg < c.beg; });
+    merged.clear();
+    for (const Chunk &c : chunks) {
+        if (!merged.empty() && c.beg <= merged.back().end) merged.back().end = std::max(merged.back().end, c.end);
+        else merged.push_back(c);
+    }
+}
+
+}  // namespace
+
+// GPU fetch: same records as pb_bam_fetch (file order, htslib overlap rule), delivered as a pb_records_t whose pointers are DEVICE
+// pointers owned by the reader (valid until its next pb_bam_fetch_device), ready for pb_get_reads_plan_device.
+extern "C" int pb_bam_fetch_device(pb_bam_t *b, int tid, int64_t beg, int64_t end, int device, pb_records_t *view, void *stream_) {
+    using namespace pb::bgzf;
+    if (!b || !view) { set_error("null argument"); return PB_ERR_ARG; }
+    memset(view, 0, sizeof(*view));
+    if (tid < 0 || tid >= (int) b->names.size()) { set_error("contig id %d out of range", tid); return PB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t) stream_;
+    PB_CUDA(cudaSetDevice(device));
+    if (b->device != device) { b->device = device; }
+    for (auto &e : b->dev_evt) if (!e) PB_CUDA(cudaEventCreate(&e));
+    if (beg < 0) beg = 0;
+    if (end > (1ll << 29)) end = 1ll << 29;
+    std::vector<Chunk> merged;
+    if (end > beg && tid < (int) b->index.size()) select_chunks(b->index[tid], beg, end, merged);
+    // ---- block list of every chunk group (groups = chunks whose block ranges touch), compressed bytes into one pinned buffer
+    struct Group { size_t c0, c1_end; size_t first_block, n_blocks; uint64_t vbeg, vend; size_t chunk0, chunk1; };
+    std::vector<Group> groups;
+    std::vector<Block> blocks;                                  // coff = file offset, uoff = offset in the inflated buffer (all groups)
+    std::vector<size_t> block_in_off;                           // offset of the block (header included) in the staging buffer
+    size_t ctotal = 0, utotal = 0;
+    for (size_t gi = 0; gi < merged.size();) {
+        size_t gj = gi;
+        uint64_t gend = merged[gi].end;
+        while (gj + 1 < merged.size() && (merged[gj + 1].beg >> 16) <= (gend >> 16)) { gj++; gend = std::max(gend, merged[gj].end); }
+        const size_t c0 = (size_t) (merged[gi].beg >> 16);
+        size_t c1 = (size_t) (gend >> 16);
+        if ((gend & 0xffff) == 0 && c1 > c0) c1 -= 1;
+        Group G;
+        G.c0 = c0; G.first_block = blocks.size(); G.vbeg = merged[gi].beg; G.vend = gend; G.chunk0 = gi; G.chunk1 = gj;
+        size_t off = c0;
+        while (off <= c1 && off < b->f.n) {
+            size_t data_off;
+            const size_t bs = bgzf_block_size(b->f.p, b->f.n, off, &data_off);
+            if (!bs || bs < data_off + 8) { set_error("corrupt BGZF block at offset %zu", off); return PB_ERR_ARG; }
+            const uint32_t isize = rd32(b->f.p + off + bs - 4);
+            if (isize > 65536) { set_error("BGZF block at offset %zu claims %u bytes", off, isize); return PB_ERR_ARG; }
+            blocks.push_back({off, data_off, bs, isize, utotal});
+            block_in_off.push_back(ctotal + (off - c0));
+            utotal += isize;
+            off += bs;
+        }
+        G.c1_end = off; G.n_blocks = blocks.size() - G.first_block;
+        ctotal += off - c0;
+        groups.push_back(G);
+        gi = gj + 1;
+    }
+    const int64_t n_blocks = (int64_t) blocks.size();
+    if (n_blocks == 0) {
+        PB_TRY(b->d_seq_off.reserve(16)); PB_TRY(b->d_cigar_off.reserve(16));
+        PB_CUDA(cudaMemsetAsync(b->d_seq_off.p, 0, 8, st)); PB_CUDA(cudaMemsetAsync(b->d_cigar_off.p, 0, 8, st));
+        view->seq_off = b->d_seq_off.as<int64_t>(); view->cigar_off = b->d_cigar_off.as<int64_t>();
+        PB_CUDA(cudaStreamSynchronize(st));
+        return PB_OK;
+    }
+    if (!b->c_host.reserve(ctotal + 64, true)) { set_error("out of host memory"); return PB_ERR_ARG; }
+    {   // parallel pread of the compressed ranges (1 MB slices)
+        struct Slice { size_t file_off, dst_off, len; };
+        std::vector<Slice> slices;
+        size_t dst = 0;
+        for (const Group &G : groups) {
+            for (size_t o = G.c0; o < G.c1_end; o += (1u << 20)) slices.push_back({o, dst + (o - G.c0), std::min<size_t>(1u << 20, G.c1_end - o)});
+            dst += G.c1_end - G.c0;
+        }
+        uint8_t *cb = b->c_host.as<uint8_t>();
+        b->pool->run(slices.size(), [&](size_t i) {
+            const Slice &S = slices[i];
+            const ssize_t got = pread(b->f.fd, cb + S.dst_off, S.len, (off_t) S.file_off);
+            if (got != (ssize_t) S.len) memcpy(cb + S.dst_off, b->f.p + S.file_off, S.len);
+        });
+    }
+    // ---- known record starts: chunk begins + the linear-index entries of the windows the query touches
+    auto upos = [&](uint64_t voff) -> int64_t {
+        const size_t coff = (size_t) (voff >> 16);
+        auto it = std::lower_bound(blocks.begin(), blocks.end(), coff, [](const Block &k, size_t c) { return k.coff < c; });
+        if (it == blocks.end() || it->coff != coff) return -1;
+        if ((voff & 0xffff) > it->isize) return -1;
+        return (int64_t) (it->uoff + (size_t) (voff & 0xffff));
+    };
+    std::vector<int64_t> starts, stops;
+    const RefIndex &ri = b->index[tid];
+    for (const Group &G : groups) {
+        const Block &lastb = blocks[G.first_block + G.n_blocks - 1];
+        int64_t limit = upos(G.vend);
+        if (limit < 0) limit = (int64_t) (lastb.uoff + lastb.isize);              // chunk end beyond the last needed block
+        std::vector<int64_t> s;
+        for (size_t ci = G.chunk0; ci <= G.chunk1; ci++) { const int64_t u0 = upos(merged[ci].beg); if (u0 >= 0 && u0 < limit) s.push_back(u0); }
+        if (!ri.linear.empty()) {
+            const size_t w0 = (size_t) (beg >> 14), w1 = std::min((size_t) ((end - 1) >> 14), ri.linear.size() - 1);
+            for (size_t w = w0; w <= w1 && w < ri.linear.size(); w++) {
+                const uint64_t v = ri.linear[w];
+                if (v < G.vbeg || v >= G.vend) continue;
+                const int64_t u0 = upos(v);
+                if (u0 >= 0 && u0 < limit) s.push_back(u0);
+            }
+        }
+        std::sort(s.begin(), s.end());
+        s.erase(std::unique(s.begin(), s.end()), s.end());
+        for (size_t i = 0; i < s.size(); i++) { starts.push_back(s[i]); stops.push_back(i + 1 < s.size() ? s[i + 1] : limit); }
+    }
+    const int n_starts = (int) starts.size();
+    // ---- device: copy, inflate
+    std::vector<BlockDesc> desc((size_t) n_blocks);
+    for (int64_t i = 0; i < n_blocks; i++) {
+        const Block &k = blocks[i];
+        desc[i] = {(int64_t) (block_in_off[i] + k.data_off), (int32_t) (k.bsize - k.data_off - 8), (int32_t) k.isize, (int64_t) k.uoff};
+        b->n_compressed += (int64_t) k.bsize; b->n_inflated += k.isize;
+    }
+    PB_CUDA(cudaEventRecord(b->dev_evt[0], st));
+    PB_TRY(upload(b->d_comp, b->c_host.p, ctotal + 16, st));
+    PB_TRY(upload(b->d_blocks, desc.data(), sizeof(BlockDesc) * n_blocks, st));
+    PB_TRY(b->d_status.reserve(sizeof(int) * (n_blocks + 4)));
+    PB_TRY(b->d_ubuf.reserve(utotal + 64));
+    PB_TRY(b->d_scal.reserve(sizeof(int64_t) * 8));
+    PB_CUDA(cudaMemsetAsync(b->d_scal.p, 0, sizeof(int64_t) * 8, st));
+    int64_t *sc = b->d_scal.as<int64_t>();                      // [0] n_rec [1] n_keep [2] n_bases [3] n_cigar [4] err (int)
+    int *d_err = reinterpret_cast<int *>(sc + 4);
+    k_bgzf_inflate<<<(unsigned) ceil_div(n_blocks, WARPS_PER_CTA), 32 * WARPS_PER_CTA, 0, st>>>(b->d_comp.as<uint8_t>(), b->d_blocks.as<BlockDesc>(), (int) n_blocks,
+                                                                                                 b->d_ubuf.as<uint8_t>(), b->d_status.as<int>());
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaEventRecord(b->dev_evt[1], st));
+    // ---- record chains
+    int64_t n_rec = 0;
+    if (n_starts > 0) {
+        PB_TRY(upload(b->d_starts, starts.data(), sizeof(int64_t) * n_starts, st));
+        PB_TRY(upload(b->d_stops, stops.data(), sizeof(int64_t) * n_starts, st));
+        PB_TRY(b->d_counts.reserve(sizeof(int32_t) * (n_starts + 1)));
+        PB_TRY(b->d_base.reserve(sizeof(int64_t) * (n_starts + 2)));
+        k_chain<0><<<(unsigned) ceil_div(n_starts, 128), 128, 0, st>>>(b->d_ubuf.as<uint8_t>(), b->d_starts.as<int64_t>(), b->d_stops.as<int64_t>(), n_starts,
+                                                                       b->d_counts.as<int32_t>(), nullptr, nullptr, d_err);
+        k_scan_excl<<<1, 1024, 0, st>>>(b->d_counts.as<int32_t>(), b->d_base.as<int64_t>(), n_starts, sc + 0);
+    }
+    std::vector<int> h_status((size_t) n_blocks);
+    int64_t h_sc[5] = {0, 0, 0, 0, 0};
+    PB_CUDA(cudaMemcpyAsync(h_status.data(), b->d_status.p, sizeof(int) * n_blocks, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n_blocks; i++)
+        if (h_status[i]) { set_error("BGZF inflate failed on the GPU: block at file offset %zu, status %d", blocks[i].coff, h_status[i]); return PB_ERR_ARG; }
+    if ((int) h_sc[4]) { set_error("BAM record chain is inconsistent with the index (code %d)", (int) h_sc[4]); return PB_ERR_ARG; }
+    n_rec = h_sc[0];
+    int64_t n_keep = 0, nb = 0, nc = 0;
+    if (n_rec > 0) {
+        PB_TRY(b->d_rec_off.reserve(sizeof(int64_t) * n_rec));
+        PB_TRY(b->d_info.reserve(sizeof(RecInfo) * n_rec));
+        PB_TRY(b->d_keep32.reserve(sizeof(int32_t) * n_rec)); PB_TRY(b->d_lseq32.reserve(sizeof(int32_t) * n_rec)); PB_TRY(b->d_ncig32.reserve(sizeof(int32_t) * n_rec));
+        PB_TRY(b->d_keep_off.reserve(sizeof(int64_t) * (n_rec + 1))); PB_TRY(b->d_so.reserve(sizeof(int64_t) * (n_rec + 1))); PB_TRY(b->d_co.reserve(sizeof(int64_t) * (n_rec + 1)));
+        k_chain<1><<<(unsigned) ceil_div(n_starts, 128), 128, 0, st>>>(b->d_ubuf.as<uint8_t>(), b->d_starts.as<int64_t>(), b->d_stops.as<int64_t>(), n_starts, nullptr,
+                                                                       b->d_base.as<int64_t>(), b->d_rec_off.as<int64_t>(), d_err);
+        k_rec_parse<<<(unsigned) ceil_div(n_rec, 128), 128, 0, st>>>(b->d_ubuf.as<uint8_t>(), b->d_rec_off.as<int64_t>(), n_rec, tid, beg, end, b->d_info.as<RecInfo>(),
+                                                                     b->d_keep32.as<int32_t>(), b->d_lseq32.as<int32_t>(), b->d_ncig32.as<int32_t>(), d_err);
+        k_scan_excl<<<1, 1024, 0, st>>>(b->d_keep32.as<int32_t>(), b->d_keep_off.as<int64_t>(), n_rec, sc + 1);
+        k_scan_excl<<<1, 1024, 0, st>>>(b->d_lseq32.as<int32_t>(), b->d_so.as<int64_t>(), n_rec, sc + 2);
+        k_scan_excl<<<1, 1024, 0, st>>>(b->d_ncig32.as<int32_t>(), b->d_co.as<int64_t>(), n_rec, sc + 3);
+        PB_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        if ((int) h_sc[4]) { set_error("malformed BAM record (code %d)", (int) h_sc[4]); return PB_ERR_ARG; }
+        n_keep = h_sc[1]; nb = h_sc[2]; nc = h_sc[3];
+    }
+    PB_CUDA(cudaEventRecord(b->dev_evt[2], st));
+    PB_TRY(b->d_pos.reserve(sizeof(int64_t) * (n_keep + 1))); PB_TRY(b->d_seq_off.reserve(sizeof(int64_t) * (n_keep + 2)));
+    PB_TRY(b->d_cigar_off.reserve(sizeof(int64_t) * (n_keep + 2))); PB_TRY(b->d_flag.reserve(sizeof(uint16_t) * (n_keep + 1)));
+    PB_TRY(b->d_mapq.reserve(n_keep + 1)); PB_TRY(b->d_seq.reserve((size_t) nb / 2 + 16)); PB_TRY(b->d_qual.reserve((size_t) nb + 16));
+    PB_TRY(b->d_cigar.reserve(sizeof(uint32_t) * (nc + 4)));
+    if (n_rec > 0 && n_keep > 0) {
+        k_rec_scatter<<<(unsigned) ceil_div(n_rec * 32, 256), 256, 0, st>>>(b->d_ubuf.as<uint8_t>(), b->d_rec_off.as<int64_t>(), b->d_info.as<RecInfo>(),
+                                                                           b->d_keep_off.as<int64_t>(), b->d_so.as<int64_t>(), b->d_co.as<int64_t>(), n_rec,
+                                                                           b->d_pos.as<int64_t>(), b->d_seq_off.as<int64_t>(), b->d_cigar_off.as<int64_t>(),
+                                                                           b->d_flag.as<uint16_t>(), b->d_mapq.as<uint8_t>(), b->d_seq.as<uint8_t>(),
+                                                                           b->d_qual.as<uint8_t>(), b->d_cigar.as<uint32_t>());
+        k_rec_tail<<<1, 32, 0, st>>>(b->d_ubuf.as<uint8_t>(), b->d_rec_off.as<int64_t>(), b->d_info.as<RecInfo>(), n_rec, nb, b->d_seq.as<uint8_t>());
+    }
+    // closing offsets seq_off[n_keep] = nb, cigar_off[n_keep] = nc
+    const int64_t tails[2] = {nb, nc};
+    PB_CUDA(cudaMemcpyAsync(b->d_seq_off.as<int64_t>() + n_keep, &tails[0], sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(b->d_cigar_off.as<int64_t>() + n_keep, &tails[1], sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaEventRecord(b->dev_evt[3], st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 3; i++) cudaEventElapsedTime(&b->dev_ms[i], b->dev_evt[i], b->dev_evt[i + 1]);
+    view->n_records = n_keep;
+    view->pos = b->d_pos.as<int64_t>(); view->seq_off = b->d_seq_off.as<int64_t>(); view->cigar_off = b->d_cigar_off.as<int64_t>();
+    view->flag = b->d_flag.as<uint16_t>(); view->mapq = b->d_mapq.as<uint8_t>(); view->seq = b->d_seq.as<uint8_t>();
+    view->qual = b->d_qual.as<uint8_t>(); view->cigar = b->d_cigar.as<uint32_t>();
+    return PB_OK;
+}
+
+// device time (ms) of the last pb_bam_fetch_device: [H2D + inflate, record chains + parse, scatter]
+extern "C" int pb_bam_fetch_device_timings(pb_bam_t *b, float *ms3) {
+    if (!b || !ms3) return PB_ERR_ARG;
+    for (int i = 0; i < 3; i++) ms3[i] = b->dev_ms[i];
+    return PB_OK;
+}
+
+// diagnostics / tests: inflate `n_blocks` raw DEFLATE streams on the GPU (h_in_off / h_in_len / h_out_len per stream, outputs
+// concatenated in order); h_status[i] != 0 marks a stream the kernel rejected
+extern "C" int pb_inflate_blocks_host(const uint8_t *h_comp, int64_t comp_bytes, const int64_t *h_in_off, const int32_t *h_in_len, const int32_t *h_out_len,
+                                      int64_t n_blocks, uint8_t *h_out, int32_t *h_status, void *stream_) {
+    using namespace pb::bgzf;
+    if (!h_comp || !h_in_off || !h_in_len || !h_out_len || !h_out || !h_status) { set_error("null argument"); return PB_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { set_error("no CUDA device: libpepper_b200 has no CPU fallback"); return PB_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t) stream_;
+    std::vector<BlockDesc> desc((size_t) n_blocks);
+    int64_t utotal = 0;
+    for (int64_t i = 0; i < n_blocks; i++) {
+        if (h_in_off[i] < 0 || h_in_off[i] + h_in_len[i] > comp_bytes || h_out_len[i] < 0) { set_error("stream %lld out of bounds", (long long) i); return PB_ERR_ARG; }
+        desc[i] = {h_in_off[i], h_in_len[i], h_out_len[i], utotal};
+        utotal += h_out_len[i];
+    }
+    DevBuf dc, db, ds, du;
+    int rc = PB_OK;
+    do {
+        if ((rc = upload(dc, h_comp, (size_t) comp_bytes, st)) != PB_OK) break;
+        if ((rc = upload(db, desc.data(), sizeof(BlockDesc) * n_blocks, st)) != PB_OK) break;
+        if ((rc = ds.reserve(sizeof(int) * (n_blocks + 1))) != PB_OK) break;
+        if ((rc = du.reserve((size_t) utotal + 64)) != PB_OK) break;
+        if (n_blocks) k_bgzf_inflate<<<(unsigned) ceil_div(n_blocks, WARPS_PER_CTA), 32 * WARPS_PER_CTA, 0, st>>>(dc.as<uint8_t>(), db.as<BlockDesc>(), (int) n_blocks,
+                                                                                                                  du.as<uint8_t>(), ds.as<int>());
+        if (cudaGetLastError() != cudaSuccess) { set_error("k_bgzf_inflate launch failed"); rc = PB_ERR_CUDA; break; }
+        cudaMemcpyAsync(h_status, ds.p, sizeof(int) * n_blocks, cudaMemcpyDeviceToHost, st);
+        if (utotal) cudaMemcpyAsync(h_out, du.p, (size_t) utotal, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("inflate kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = PB_ERR_CUDA; }
+    } while (0);
+    dc.release(); db.release(); ds.release(); du.release();
+    return rc;
 }
 
 // ----------------------------------------------------------------------------------------------------------- FASTA
