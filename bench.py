@@ -351,9 +351,66 @@ def run_variant(args, cfg):
         line["verified"], base = verify_variant(args, cfg, reads, regions, records, replicas)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = base
+    if world == 1 and not args.no_files:
+        try:
+            line["e2e_files"] = files_leg(args, cfg, local)
+        except Exception as ex:                                 # the headline numbers above stand on their own
+            line["e2e_files"] = {"error": repr(ex)[:300]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def files_leg(args, cfg, local):
+    """north_star's input: a synthetic coordinate-sorted .bam + .bai + .fa of the SAME scale on disk -> predictions through
+    VariantFromFiles.call_stream.  Inside the timed region: pread of the compressed BGZF blocks, H2D of those blocks, GPU
+    inflate + record walk + parse, get_reads (trim), encoder, network, D2H of the prediction columns.  Not in it: writing the
+    files (a fork pool of zlib compressors) and page-cache warm-up (one pass over the file)."""
+    import shutil
+    import tempfile
+    import torch
+    from pepper_b200 import synth, synth_files, weights
+    from pepper_b200.frontend import VariantFromFiles, variant_intervals
+    plat, params = platform_of(cfg)
+    n_regions = args.files_regions or args.regions
+    span = args.block * args.region_size
+    times = -(-(n_regions * args.region_size + 200) // span)
+    t0 = time.time()
+    rec, genome = synth.simulate_contig_records(span, args.coverage, plat, args.seed + 7)
+    d = tempfile.mkdtemp(prefix="pb_bench_files_")
+    try:
+        bam, fa = os.path.join(d, "s.bam"), os.path.join(d, "s.fa")
+        L = synth_files.write_bam_tiled(bam, "chr20s", rec, span, times)
+        synth_files.write_fasta(fa, [("chr20s", np.tile(genome[:span], times))])
+        gen_s = time.time() - t0
+        iv = variant_intervals(100, min(L - 100, 100 + n_regions * args.region_size), args.region_size)
+        genomic = sum(e - s for s, e in iv)
+        vf = VariantFromFiles(bam, fa, weights.random_variant_state(0), device=local, gpu_inflate=not args.host_inflate)
+        cap = int(genomic // (40 if cfg["platform"] == "ONT" else 250)) + 65536
+        vf.call_stream("chr20s", iv[:64], params, batch=args.group_regions, capacity=cap)        # warm-up (allocations, page cache of the head)
+        with open(bam, "rb") as f:                               # page cache: the file was just written, read it once anyway
+            while f.read(1 << 26):
+                pass
+        torch.cuda.synchronize()
+        steps = max(1, args.files_steps)
+        t0 = time.perf_counter()
+        n_cand = 0
+        for _ in range(steps):
+            calls = vf.call_stream("chr20s", iv, params, batch=args.group_regions, capacity=cap)
+            n_cand = len(calls)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        comp, infl = vf.bam.io_stats()
+        ft = vf.bam.fetch_device_timings() if not args.host_inflate else {}
+        vf.close()
+        return {"value": genomic / dt, "unit": "bases/s", "ms_per_step": dt * 1e3, "steps": steps, "regions": len(iv), "genomic_bases": genomic,
+                "candidates": n_cand, "bam_bytes": os.path.getsize(bam), "records_per_block": rec.n_records, "batch_regions": args.group_regions,
+                "inflate": "host zlib thread pool" if args.host_inflate else "GPU (k_bgzf_inflate, warp per BGZF block)",
+                "last_batch_fetch_ms": ft, "h2d_bytes_per_step": int(os.path.getsize(bam)), "d2h_bytes_per_step": int(n_cand * 90),
+                "gen_seconds": round(gen_s, 1),
+                "api": "pepper_b200.frontend.VariantFromFiles.call_stream -> pb_bam_fetch_device + pb_get_reads_* + pb_variant_stream_*"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 # figures carried over from the ncu --set full captures under profiles/ (per candidate / per algorithmic byte)
@@ -698,6 +755,10 @@ def main():
     ap.add_argument("--verify-regions", type=int, default=2)
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the from-files leg (writes a chr20-scale BAM to a temp dir)")
+    ap.add_argument("--files-regions", type=int, default=0, help="regions of the from-files leg (default: --regions)")
+    ap.add_argument("--files-steps", type=int, default=2)
+    ap.add_argument("--host-inflate", action="store_true", help="from-files leg with the host zlib pool instead of the GPU inflate")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.regions is None:

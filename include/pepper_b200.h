@@ -92,6 +92,8 @@ const char *pb_last_error(void);
 int  pb_version(void);
 /* number of CUDA devices visible (0 on a CPU box); never fails */
 int  pb_device_count(void);
+/* synchronous device -> host copy of a library-owned device buffer (read-backs of device views, tests) */
+int  pb_memcpy_to_host(void *h_dst, const void *d_src, int64_t bytes);
 
 /* ------------------------------------------------------------------------
  * Region read fetch + trim.  Replaces the per-record body of

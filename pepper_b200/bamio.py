@@ -83,17 +83,16 @@ class DeviceRecordsView:
 
     def to_batch(self) -> RecordBatch:
         """Copy to the host (tests)."""
-        import torch
         s = self.struct
         n = int(s.n_records)
+        L = _lib.lib()
+        L.pb_memcpy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
 
         def arr(ptr, count, dtype):
             if count == 0 or not ptr:
                 return np.zeros(0, dtype=dtype)
             out = np.empty(count, dtype=dtype)
-            rc = torch.cuda.cudart().cudaMemcpy(out.ctypes.data, ptr, out.nbytes, 2)      # cudaMemcpyDeviceToHost
-            if int(rc) != 0:
-                raise _lib.PepperB200Error("cudaMemcpy D2H failed (%s)" % rc)
+            _lib.check(L.pb_memcpy_to_host(out.ctypes.data, C.c_void_p(ptr), out.nbytes), "pb_memcpy_to_host")
             return out
         seq_off = arr(s.seq_off, n + 1, np.int64)
         cigar_off = arr(s.cigar_off, n + 1, np.int64)

@@ -19,3 +19,10 @@ extern "C" int pb_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+
+// device -> host copy of a library-owned buffer (tests / read-backs of views such as pb_bam_fetch_device's)
+extern "C" int pb_memcpy_to_host(void *h_dst, const void *d_src, int64_t bytes) {
+    if (bytes < 0 || (bytes && (!h_dst || !d_src))) { pb::set_error("pb_memcpy_to_host: bad argument"); return PB_ERR_ARG; }
+    if (bytes) PB_CUDA(cudaMemcpy(h_dst, d_src, (size_t) bytes, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}

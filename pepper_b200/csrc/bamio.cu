@@ -210,6 +210,7 @@ struct pb_bam {
     HostBuf c_host;                     // page-locked staging of the compressed blocks
     pb::DevBuf d_comp, d_blocks, d_status, d_ubuf, d_starts, d_stops, d_counts, d_base, d_rec_off, d_info, d_keep32, d_lseq32, d_ncig32,
         d_keep_off, d_so, d_co, d_scal, d_pos, d_seq_off, d_cigar_off, d_flag, d_mapq, d_seq, d_qual, d_cigar;
+    cudaStream_t own_stream = nullptr;
     float dev_ms[3] = {0, 0, 0};        // inflate, chain + parse, scatter
     cudaEvent_t dev_evt[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -374,7 +375,7 @@ extern "C" int pb_bam_close(pb_bam_t *b) {
     pb::DevBuf *dbufs[] = {&b->d_comp, &b->d_blocks, &b->d_status, &b->d_ubuf, &b->d_starts, &b->d_stops, &b->d_counts, &b->d_base, &b->d_rec_off, &b->d_info,
                            &b->d_keep32, &b->d_lseq32, &b->d_ncig32, &b->d_keep_off, &b->d_so, &b->d_co, &b->d_scal, &b->d_pos, &b->d_seq_off, &b->d_cigar_off,
                            &b->d_flag, &b->d_mapq, &b->d_seq, &b->d_qual, &b->d_cigar};
-    if (b->device >= 0) { cudaSetDevice(b->device); for (auto *x : dbufs) x->release(); for (auto &e : b->dev_evt) if (e) cudaEventDestroy(e); }
+    if (b->device >= 0) { cudaSetDevice(b->device); for (auto *x : dbufs) x->release(); for (auto &e : b->dev_evt) if (e) cudaEventDestroy(e); if (b->own_stream) cudaStreamDestroy(b->own_stream); }
     b->f.close();
     delete b->pool;
     delete b;
@@ -635,9 +636,12 @@ extern "C" int pb_bam_fetch_device(pb_bam_t *b, int tid, int64_t beg, int64_t en
     if (!b || !view) { set_error("null argument"); return PB_ERR_ARG; }
     memset(view, 0, sizeof(*view));
     if (tid < 0 || tid >= (int) b->names.size()) { set_error("contig id %d out of range", tid); return PB_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t) stream_;
     PB_CUDA(cudaSetDevice(device));
     if (b->device != device) { b->device = device; }
+    // stream == NULL: the reader's own NON-BLOCKING stream, so that a prefetch thread's inflate overlaps the kernels the caller
+    // queued on the default stream (this function synchronises its stream before it returns: the records are complete)
+    if (!stream_ && !b->own_stream) PB_CUDA(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    cudaStream_t st = stream_ ? (cudaStream_t) stream_ : b->own_stream;
     for (auto &e : b->dev_evt) if (!e) PB_CUDA(cudaEventCreate(&e));
     if (beg < 0) beg = 0;
     if (end > (1ll << 29)) end = 1ll << 29;

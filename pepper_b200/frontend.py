@@ -35,7 +35,11 @@ def variant_intervals(interval_start: int, interval_end: int, region_size: int =
 
 
 class _FromFiles:
-    def __init__(self, bam_path: str, fasta_path: str, device: int = 0, threads: int = 0):
+    """`gpu_inflate` (default): BGZF inflate, record walk and parse run on the GPU (pb_bam_fetch_device; only compressed blocks
+    cross PCIe); False = the host thread-pool zlib path (pb_bam_fetch)."""
+
+    def __init__(self, bam_path: str, fasta_path: str, device: int = 0, threads: int = 0, gpu_inflate: bool = True):
+        self.gpu_inflate = gpu_inflate
         self.bam = BamReader(bam_path, threads)
         self.fasta = FastaReader(fasta_path)
         self.trimmer = ReadTrimmer(device)
@@ -59,6 +63,9 @@ class _FromFiles:
     def __exit__(self, *a):
         self.close()
 
+    def _fetch(self, reader, contig: str, beg: int, end: int):
+        return reader.fetch_device(contig, beg, end, self.device) if self.gpu_inflate else reader.fetch(contig, beg, end)
+
     def _ref_table(self, contig: str, rows: list[list[int]], spans: list[tuple[int, int]]) -> RegionTable:
         """Region table + reference strings: ONE faidx fetch of the covering span, the (overlapping) per-region strings are
         offsets into it (get_reference_sequence clamps at the contig end; so do the lengths here)."""
@@ -73,8 +80,8 @@ class _FromFiles:
 class VariantFromFiles(_FromFiles):
     """call_variant's make_images + run_inference for a list of intervals of one contig."""
 
-    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0):
-        super().__init__(bam_path, fasta_path, device, threads)
+    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0, gpu_inflate: bool = True):
+        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate)
         self.caller = VariantCaller(state, device)
 
     def call(self, contig: str, intervals: list[tuple[int, int]], params: dict, include_supplementary: bool = False,
@@ -90,7 +97,7 @@ class VariantFromFiles(_FromFiles):
             rows.append([rs, re_, s, e, 0, 0, 0, 0])
             spans.append((rs, re_ + 1))                                             # get_reference_sequence(.., region_end + 1)
         regions = self._ref_table(contig, rows, spans)
-        view = _view if _view is not None else self.bam.fetch(contig, min(q[0] for q in queries), max(q[1] for q in queries))
+        view = _view if _view is not None else self._fetch(self.bam, contig, min(q[0] for q in queries), max(q[1] for q in queries))
         got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
                                      max_reads=max_reads, downsample_rate=downsample_rate)
         fetched = FetchedReads(got, regions, self.device)
@@ -144,7 +151,7 @@ class VariantFromFiles(_FromFiles):
             return max(0, min(s for s, _ in g) - REGION_SAFE_BASES), max(e for _, e in g) + REGION_SAFE_BASES
 
         def prefetch(k):
-            return readers[k & 1].fetch(contig, *span(groups[k]))
+            return self._fetch(readers[k & 1], contig, *span(groups[k]))
         # a Future re-raises the worker's exception (bad contig, corrupt BGZF block) in the consumer
         with ThreadPoolExecutor(max_workers=1) as pool:
             fut = pool.submit(prefetch, 0)
@@ -155,11 +162,62 @@ class VariantFromFiles(_FromFiles):
                 yield self.call(contig, g, params, _view=view, **kw)
 
 
+    def call_stream(self, contig: str, intervals: list[tuple[int, int]], params: dict, batch: int = 32, capacity: int | None = None,
+                    include_supplementary: bool = False, min_mapq: int = 0, downsample_rate: float = 1.0,
+                    max_reads: int = VARIANT_MAX_READS, want_images: bool = False) -> VariantCalls:
+        """The whole interval list as ONE streaming session (pipeline.VariantStream): batch k+1's BGZF blocks are read, copied and
+        inflated (helper thread, second reader, its own CUDA stream) while batch k's get_reads / encoder / network kernels run;
+        candidates accumulate on the device and the network runs over whole 9,472-candidate chunks across batch boundaries.
+        `region_of` counts intervals from the start of the list."""
+        from concurrent.futures import ThreadPoolExecutor
+        if not intervals:
+            raise ValueError("no intervals")
+        if self._bam2 is None:
+            self._bam2 = BamReader(self.bam.path, 0)
+        readers = [self.bam, self._bam2]
+        groups = [intervals[i:i + batch] for i in range(0, len(intervals), batch)]
+
+        def span(g):
+            return max(0, min(s for s, _ in g) - REGION_SAFE_BASES), max(e for _, e in g) + REGION_SAFE_BASES
+
+        def prefetch(k):
+            return self._fetch(readers[k & 1], contig, *span(groups[k]))
+        cap = capacity or max(4096, int(sum(e - s + 1 for s, e in intervals)) // 30)
+        while True:
+            s = self.caller.stream(params, cap)
+            try:
+                with ThreadPoolExecutor(max_workers=1) as pool:
+                    fut = pool.submit(prefetch, 0)
+                    done = 0
+                    for k, g in enumerate(groups):
+                        view = fut.result()
+                        if k + 1 < len(groups):
+                            fut = pool.submit(prefetch, k + 1)
+                        rows, queries, spans = [], [], []
+                        for (a, b) in g:
+                            rs, re_ = max(0, a - REGION_SAFE_BASES), b + REGION_SAFE_BASES
+                            queries.append((rs, re_)); rows.append([rs, re_, a, b, 0, 0, 0, 0]); spans.append((rs, re_ + 1))
+                        regions = self._ref_table(contig, rows, spans)
+                        got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
+                                                     max_reads=max_reads, downsample_rate=downsample_rate)
+                        fetched = FetchedReads(got, regions, self.device)
+                        s.stage_device(fetched, 0, len(g), done)
+                        s.run(flush=False)
+                        s.sync()
+                        done += len(g)
+                n = s.end()
+                return s.fetch(n, want_images=want_images)
+            except PepperB200Error as ex:
+                if ex.rc != PB_ERR_CAPACITY:
+                    raise
+                cap *= 2
+
+
 class PolishFromFiles(_FromFiles):
     """polish's make_images (with read realignment) + call_consensus for a list of regions of one contig."""
 
-    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0):
-        super().__init__(bam_path, fasta_path, device, threads)
+    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0, gpu_inflate: bool = True):
+        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate)
         self.caller = PolishCaller(state, device)
         self.realigner = Realigner(device)
 
@@ -173,7 +231,7 @@ class PolishFromFiles(_FromFiles):
             rows.append([rs, re_, rs, re_, 0, 0, 0, 0])
             spans.append((rs, re_ + ALIGNMENT_SAFE_BASES))                         # AlignmentSummarizer.py:164-170
         regions = self._ref_table(contig, rows, spans)
-        view = self.bam.fetch(contig, min(r[0] for r in regions_se), max(r[1] for r in regions_se))
+        view = self._fetch(self.bam, contig, min(r[0] for r in regions_se), max(r[1] for r in regions_se))
         got = self.trimmer.get_reads(view, regions_se, False, 0, 0, max_reads=max_reads, downsample_rate=1.0)   # :300-325
         fetched = FetchedReads(got, regions, self.device)
         if realign:

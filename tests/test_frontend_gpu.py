@@ -105,6 +105,25 @@ def test_variant_batches_equal_single_call(files):
     assert np.abs(np.concatenate([p[0].probs for p in parts]) - whole.probs).max() < 1e-5
 
 
+def test_variant_stream_equals_single_call(files):
+    """call_stream (one streaming session over batches, GPU inflate prefetched by a helper thread) == one call, for the GPU
+    and the host inflate paths."""
+    from pepper_b200 import weights
+    from pepper_b200.frontend import VariantFromFiles, variant_intervals
+    params = synth.ont_params()
+    iv = variant_intervals(1000, 25000, 3000)
+    for gpu_inflate in (True, False):
+        vf = VariantFromFiles(files["bam"], files["fa"], weights.random_variant_state(0), gpu_inflate=gpu_inflate)
+        whole, _ = vf.call("ctg", iv, params)
+        got = vf.call_stream("ctg", iv, params, batch=3, want_images=True)
+        assert np.array_equal(got.positions, whole.positions) and got.keys == whole.keys
+        assert np.array_equal(got.region_of, whole.region_of) and np.array_equal(got.images, whole.images)
+        assert np.array_equal(got.probs, whole.probs)
+        small = vf.call_stream("ctg", iv, params, batch=3, capacity=10)          # capacity retry restarts the session
+        assert np.array_equal(small.probs, whole.probs)
+        vf.close()
+
+
 def test_polish_contig_from_files_to_consensus(files):
     """files -> tiling -> get_reads -> realign -> encoder -> GRU -> stitch, in batches, equals the oracle stitch of the same calls
     and does not depend on the batch size."""
