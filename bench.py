@@ -402,11 +402,12 @@ def files_leg(args, cfg, local):
         dt = (time.perf_counter() - t0) / steps
         comp, infl = vf.bam.io_stats()
         ft = vf.bam.fetch_device_timings() if not args.host_inflate else {}
+        stage_prof = getattr(vf, "last_profile", None)
         vf.close()
         return {"value": genomic / dt, "unit": "bases/s", "ms_per_step": dt * 1e3, "steps": steps, "regions": len(iv), "genomic_bases": genomic,
                 "candidates": n_cand, "bam_bytes": os.path.getsize(bam), "records_per_block": rec.n_records, "batch_regions": args.group_regions,
                 "inflate": "host zlib thread pool" if args.host_inflate else "GPU (k_bgzf_inflate, warp per BGZF block)",
-                "last_batch_fetch_ms": ft, "h2d_bytes_per_step": int(os.path.getsize(bam)), "d2h_bytes_per_step": int(n_cand * 90),
+                "last_batch_fetch_ms": ft, "host_stage_ms": stage_prof, "h2d_bytes_per_step": int(os.path.getsize(bam)), "d2h_bytes_per_step": int(n_cand * 90),
                 "gen_seconds": round(gen_s, 1),
                 "api": "pepper_b200.frontend.VariantFromFiles.call_stream -> pb_bam_fetch_device + pb_get_reads_* + pb_variant_stream_*"}
     finally:

@@ -396,7 +396,7 @@ int pb_polish_net_launches(pb_polish_net_t *net, int64_t *n_launches);
 /* 0 = fp32 FFMA GEMMs, 1 = tcgen05 bf16x3 GEMMs (fp32-equivalent) */
 int pb_polish_net_set_mode(pb_polish_net_t *net, int mode);
 
-/* diagnostics: C[M][N] = A[M][K] W[N][K]^T + bias through the tcgen05 kernel (N % 128 == 0, K % 32 == 0) */
+/* diagnostics: C[M][N] = A[M][K] W[N][K]^T + bias through the tcgen05 kernel (N % 256 == 0, K % 32 == 0) */
 int pb_test_tc_gemm(int M, int N, int K, const float *h_A, const float *h_W, const float *h_bias, float *h_out);
 
 /* ------------------------------------------------------------------------

@@ -97,18 +97,6 @@ static int launch_tc(const Args &A, int mt, int nt128, int ndir, cudaStream_t st
     tc::k_tc_gemm_p<EPI><<<(unsigned) std::min(tiles, g_num_sms), tc::PG_THREADS, tc::PSMEM_BYTES, st>>>(A, mt, nt, ndir);
     return PB_OK;
 }
-// one 128x128 tile per CTA, two CTAs per SM (first tcgen05 version; kept for N %% 256 != 0 and as a cross-check)
-template <int EPI>
-static int launch_tc128(const Args &A, int mt, int nt, int ndir, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(tc::k_tc_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        attr_set = true;
-    }
-    tc::k_tc_gemm<EPI><<<dim3((unsigned) mt, (unsigned) nt, (unsigned) ndir), tc::THREADS, tc::SMEM_BYTES, st>>>(A);
-    return PB_OK;
-}
-
 static Dir empty_dir() {
     Dir D;
     memset(&D, 0, sizeof(D));
@@ -304,25 +292,19 @@ __global__ void __launch_bounds__(128) k_polish_dense_tiles(const bf16 *__restri
     for (int c = 0; c < 5; c++) dst[c] += e[c] / sum;
 }
 
-// one bidirectional GRU layer over the 100 steps of a window: ONE cooperative launch of k_gru_window.
+// one bidirectional GRU layer over the 100 steps of a window: ONE launch of k_gru_layer (or the k_gru_cluster fallback).
 //   x operand: [mt][100][xkt] tiles (hi, lo or hi only); h0: the fwd state at time 99 / bwd state at time 0 of another
 //   sequence operand (h0_is_seq) or the zero operand.
 static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi, const bf16 *x_lo, int xkt, const bf16 *h0_hi,
                         const bf16 *h0_lo, bool h0_is_seq, bf16 *y_hi, bf16 *y_lo, int64_t B, cudaStream_t st) {
     static bool attr_set = false;
-    static int use_cluster = 1;       // PB_GRU_CLUSTER=0 selects the HBM-flag kernel (cooperative launch, <= 37 row tiles)
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(tc::k_gru_window, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSMEM_BYTES));
         PB_CUDA(cudaFuncSetAttribute(tc::k_gru_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CSMEM_BYTES));
-        const char *e = getenv("PB_GRU_CLUSTER");
-        use_cluster = (e && e[0] == '0') ? 0 : 1;
         attr_set = true;
     }
     TcPolish &T = *N->tc;
     const int64_t Mt = ceil_div(B, 128);
     const int64_t ystride = (int64_t) PWIN * 8 * TILE_ELEMS;
-    PB_TRY(T.flags.reserve(sizeof(int) * 2 * Mt));
-    PB_CUDA(cudaMemsetAsync(T.flags.p, 0, sizeof(int) * 2 * Mt, st));
     tc::GruWin G;
     G.x_hi = x_hi; G.x_lo = x_lo; G.x_kt = xkt;
     for (int d = 0; d < 2; d++) {
@@ -333,7 +315,7 @@ static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi
         G.bias[d] = Wb[d].bias.as<float>();
     }
     G.h0_mt_stride = h0_is_seq ? ystride : 0;
-    G.y_hi = y_hi; G.y_lo = y_lo; G.flags = T.flags.as<int>();
+    G.y_hi = y_hi; G.y_lo = y_lo; G.flags = nullptr;
     G.M = (int) B; G.n_mt = (int) Mt; G.T = PWIN;
     if (W[0].nkt_x != xkt || W[0].nkt_h != 4) { set_error("gru_layer_tc: weight / operand k-tile mismatch"); return PB_ERR_STATE; }
     static const bool use_layer = !(getenv("PB_GRU_LAYER") && atoi(getenv("PB_GRU_LAYER")) == 0);
@@ -342,12 +324,9 @@ static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi
         if (!la) { PB_CUDA(cudaFuncSetAttribute(tc::k_gru_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSMEM_BYTES)); la = true; }
         tc::k_gru_layer<<<(unsigned) (2 * Mt), tc::PG_THREADS, tc::PSMEM_BYTES, st>>>(G);    // one CTA per (direction, row tile), no h exchange
         PB_CUDA(cudaGetLastError());
-    } else if (use_cluster) {
-        tc::k_gru_cluster<<<(unsigned) (4 * Mt), tc::THREADS, tc::CSMEM_BYTES, st>>>(G);      // clusters of 2 CTAs (__cluster_dims__)
-        PB_CUDA(cudaGetLastError());
     } else {
-        void *args[] = {&G};
-        PB_CUDA(cudaLaunchCooperativeKernel((void *) tc::k_gru_window, dim3((unsigned) (4 * Mt)), dim3(tc::THREADS), args, tc::PSMEM_BYTES, st));
+        tc::k_gru_cluster<<<(unsigned) (4 * Mt), tc::THREADS, tc::CSMEM_BYTES, st>>>(G);      // A/B fallback (PB_GRU_LAYER=0): clusters of 2 CTAs
+        PB_CUDA(cudaGetLastError());
     }
     N->launches++;
     return PB_OK;
@@ -389,16 +368,15 @@ int polish_forward_tc(pb_polish_net *N, const uint8_t *d_images, int64_t B, int6
 }  // namespace pb
 
 // ------------------------------------------------------------------------------------------------- self test
-// C[M][N] = A[M][K] W[N][K]^T + bias through the tcgen05 kernel (EPI_BIAS, fp32 output).  N % 128 == 0, K % 32 == 0.
+// C[M][N] = A[M][K] W[N][K]^T + bias through the tcgen05 kernel (EPI_BIAS, fp32 output).  N % 256 == 0, K % 32 == 0.
 extern "C" int pb_test_tc_gemm(int M, int N, int K, const float *h_A, const float *h_W, const float *h_bias, float *h_out) {
-    if (N % 128 || K % 32 || M <= 0) { set_error("pb_test_tc_gemm: N %% 128 and K %% 32 must be 0"); return PB_ERR_ARG; }
+    if (N % 256 || K % 32 || M <= 0) { set_error("pb_test_tc_gemm: N %% 256 and K %% 32 must be 0"); return PB_ERR_ARG; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { set_error("no CUDA device: libpepper_b200 has no CPU fallback"); return PB_ERR_CUDA; }
     const int64_t Mt = ceil_div(M, 128);
     std::vector<uint16_t> ahi, alo, whi, wlo;
-    const bool big = (N % 256) == 0;
     tile_matrix(h_A, M, K, Mt * 128, K, ahi, alo);
-    tile_matrix(h_W, N, K, N, K, whi, wlo, big ? 256 : 128);
+    tile_matrix(h_W, N, K, N, K, whi, wlo, 256);
     DevBuf dahi, dalo, dwhi, dwlo, dbias, dout;
     PB_TRY(upload_tiles(dahi, dalo, ahi, alo));
     PB_TRY(upload_tiles(dwhi, dwlo, whi, wlo));
@@ -413,8 +391,7 @@ extern "C" int pb_test_tc_gemm(int M, int N, int K, const float *h_A, const floa
     D.bias = dbias.as<float>();
     D.y_f32 = dout.as<float>(); D.ldy = N;
     A.d[0] = D; A.d[1] = D;
-    if (big) PB_TRY(launch_tc<tc::EPI_BIAS>(A, (int) Mt, N / 128, 1, 0));
-    else PB_TRY(launch_tc128<tc::EPI_BIAS>(A, (int) Mt, N / 128, 1, 0));
+    PB_TRY(launch_tc<tc::EPI_BIAS>(A, (int) Mt, N / 128, 1, 0));
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaDeviceSynchronize());
     PB_CUDA(cudaMemcpy(h_out, dout.p, sizeof(float) * (size_t) M * N, cudaMemcpyDeviceToHost));

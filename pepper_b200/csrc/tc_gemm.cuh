@@ -134,179 +134,6 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(THREADS, 2) k_tc_gemm(Args G) {
-    static_assert(THREADS == 64 + 8 * 32, "warp roles");
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES), bar_acc = smem_u32(bars + 2 * STAGES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
-    const uint32_t smem_base = smem_u32(smem);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Dir &D = G.d[blockIdx.z];
-    const int mt = blockIdx.x, nt = blockIdx.y;
-    const int nkt0 = D.seg[0].nkt, nkt = nkt0 + D.seg[1].nkt;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_acc, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kt = 0; kt < nkt; kt++) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (uint32_t) ((kt / STAGES) & 1);
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                const Seg &S = (kt < nkt0) ? D.seg[0] : D.seg[1];
-                const int64_t off = (int64_t) mt * S.mt_stride + (int64_t) ((kt < nkt0) ? kt : kt - nkt0) * TILE_ELEMS;
-                const uint32_t st = smem_base + s * STAGE_BYTES;
-                mbar_expect_tx(bar_full + 8 * s, (S.lo ? 4u : 3u) * TILE_BYTES);
-                bulk_g2s(st, S.hi + off, TILE_BYTES, bar_full + 8 * s);
-                if (S.lo) bulk_g2s(st + TILE_BYTES, S.lo + off, TILE_BYTES, bar_full + 8 * s);
-                const int64_t woff = ((int64_t) nt * D.w_nkt + kt) * TILE_ELEMS;
-                bulk_g2s(st + 2 * TILE_BYTES, D.w_hi + woff, TILE_BYTES, bar_full + 8 * s);
-                bulk_g2s(st + 3 * TILE_BYTES, D.w_lo + woff, TILE_BYTES, bar_full + 8 * s);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            for (int kt = 0; kt < nkt; kt++) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (uint32_t) ((kt / STAGES) & 1);
-                mbar_wait(bar_full + 8 * s, ph);
-                tc_fence_after();
-                const bool has_lo = ((kt < nkt0) ? D.seg[0].lo : D.seg[1].lo) != nullptr;
-                const uint32_t st = smem_base + s * STAGE_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < BK / 16; ks++) {
-                    const uint64_t a_hi = smem_desc(st + ks * 4096), a_lo = smem_desc(st + TILE_BYTES + ks * 4096);
-                    const uint64_t b_hi = smem_desc(st + 2 * TILE_BYTES + ks * 4096), b_lo = smem_desc(st + 3 * TILE_BYTES + ks * 4096);
-                    tc_mma(tmem_base, a_hi, b_hi, IDESC, (kt > 0 || ks > 0) ? 1u : 0u);
-                    tc_mma(tmem_base, a_hi, b_lo, IDESC, 1u);
-                    if (has_lo) tc_mma(tmem_base, a_lo, b_hi, IDESC, 1u);
-                }
-                tc_commit(bar_empty + 8 * s);          // frees the stage when these MMAs have read it
-            }
-            tc_commit(bar_acc);                         // accumulator complete
-        }
-    } else {
-        const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;               // which half of the 128 accumulator columns
-        const int row = mt * BM + q * 32 + lane;
-        const bool valid = row < G.M;
-        const int r128 = q * 32 + lane;
-        // state that does not depend on the accumulator is fetched while the main loop runs:
-        // LSTM cell state c / GRU previous hidden state of this row's 32 units
-        float st[EPI_COLS / 4];
-        const int ubase = nt * (BN / 4) + half * (EPI_COLS / 4);       // first hidden unit of this warp
-        if (EPI == EPI_LSTM) {
-#pragma unroll
-            for (int u = 0; u < EPI_COLS / 4; u++) st[u] = valid ? D.c[(int64_t) (ubase + u) * G.c_ld + row] : 0.f;
-        } else if (EPI == EPI_GRU) {
-#pragma unroll
-            for (int u8 = 0; u8 < EPI_COLS / 32; u8++) {
-                uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
-                if (valid && D.hp_hi) {
-                    const int j0 = ubase + u8 * 8;
-                    const int64_t o = (int64_t) mt * D.hp_mt_stride + (int64_t) (j0 >> 5) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
-                    h = *reinterpret_cast<const uint4 *>(D.hp_hi + o);
-                    l = *reinterpret_cast<const uint4 *>(D.hp_lo + o);
-                }
-                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-                for (int e = 0; e < 8; e++)
-                    st[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
-            }
-        }
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
-#pragma unroll
-        for (int cl = 0; cl < EPI_COLS / 32; cl++) {
-            const int cc = half * (EPI_COLS / 32) + cl;
-            uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
-            const int col0 = nt * BN + cc * 32;
-            if (EPI == EPI_BIAS || EPI == EPI_SELU) {
-#pragma unroll
-                for (int g8 = 0; g8 < 4; g8++) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float x = __uint_as_float(acc[g8 * 8 + i]) + __ldg(D.bias + col0 + g8 * 8 + i);
-                        v[i] = (EPI == EPI_SELU) ? selu(x) : x;
-                    }
-                    if (valid) {
-                        if (D.y_hi) {
-                            uint4 hi, lo;
-                            split8(v, hi, lo);
-                            const int64_t o = (int64_t) mt * D.y_mt_stride + (int64_t) (D.y_kt0 + col0 / 32) * TILE_ELEMS + g8 * 1024 + r128 * 8;
-                            *reinterpret_cast<uint4 *>(D.y_hi + o) = hi;
-                            *reinterpret_cast<uint4 *>(D.y_lo + o) = lo;
-                        }
-                        if (D.y_f32) {
-                            float4 *dst = reinterpret_cast<float4 *>(D.y_f32 + (int64_t) row * D.ldy + col0 + g8 * 8);
-                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                        }
-                    }
-                }
-            } else {
-                // 32 columns = 8 hidden units x 4 gate columns
-                const int j0 = col0 >> 2;
-                float hn[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const float4 bz = __ldg(reinterpret_cast<const float4 *>(D.bias + col0 + 4 * u));
-                    const float v0 = __uint_as_float(acc[4 * u + 0]) + bz.x, v1 = __uint_as_float(acc[4 * u + 1]) + bz.y;
-                    const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
-                    if (EPI == EPI_LSTM) {
-                        const float ig = sigm(v0), fg = sigm(v1), gg = tanh_fast(v2), og = sigm(v3);
-                        const float cn = fg * st[cl * 8 + u] + ig * gg;
-                        st[cl * 8 + u] = cn;
-                        hn[u] = og * tanh_fast(cn);
-                    } else {
-                        const float r = sigm(v0), z = sigm(v1);
-                        const float n = tanh_fast(v2 + r * v3);
-                        hn[u] = (1.0f - z) * n + z * st[cl * 8 + u];
-                    }
-                }
-                if (valid) {
-                    uint4 hi, lo;
-                    split8(hn, hi, lo);
-                    const int64_t o = (int64_t) mt * D.y_mt_stride + (int64_t) (D.y_kt0 + (j0 >> 5)) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
-                    *reinterpret_cast<uint4 *>(D.y_hi + o) = hi;
-                    *reinterpret_cast<uint4 *>(D.y_lo + o) = lo;
-                    if (D.y_f32) {
-                        float4 *dst = reinterpret_cast<float4 *>(D.y_f32 + (int64_t) row * D.ldy + j0);
-                        dst[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                        dst[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
-                    }
-                }
-            }
-        }
-        if (EPI == EPI_LSTM && valid) {
-#pragma unroll
-            for (int u = 0; u < EPI_COLS / 4; u++) D.c[(int64_t) (ubase + u) * G.c_ld + row] = st[u];
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) TMEM_COLS) : "memory");
-    }
-}
-
 // ---------------------------------------------------------------- persistent variant
 // One CTA per SM loops over output tiles (static round-robin).  The accumulator is double buffered in TMEM (2 x 128
 // columns) and the shared-memory ring is shared by consecutive tiles, so the MMA warp starts tile i+1 while the eight
@@ -739,14 +566,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_lstm_layer(LstmLayer G) {
     }
 }
 
-// ---------------------------------------------------------------- persistent GRU window kernel (polish)
-// All 100 time steps of one bidirectional GRU layer of one window in ONE launch.  CTA b owns tile
-// (dir, row tile mt, gate-column half nt) for every step; its sibling (same dir / mt, other half) produces the other 64
-// hidden units, so the only cross-CTA dependency per step is the sibling pair: after the epilogue of step t both CTAs
-// bump flag[pair]; the producer warp streams the x / W tiles of step t+1 ahead of time and waits for flag >= 2(t+1) only
-// before the four h k-tiles.  The accumulator is double buffered in TMEM across steps, the x-part MMAs of step t+1 overlap
-// the epilogue of step t, and each thread keeps "its" previous hidden values in registers.  Launched cooperatively
-// (all CTAs resident: grid = 4 * row tiles <= number of SMs).
+// ---------------------------------------------------------------- GRU window layers (polish)
+// All 100 time steps of one bidirectional GRU layer of one window in ONE launch (k_gru_layer below; k_gru_cluster is the A/B
+// fallback that splits the hidden units over a 2-CTA cluster).  The first persistent version, k_gru_window (sibling CTAs
+// exchanging h through HBM flags under a cooperative launch), was removed in round 2: superseded twice.
 struct GruWin {
     const __nv_bfloat16 *x_hi, *x_lo;      // input sequence operand [mt][100][x_kt] tiles (x_lo == nullptr: exact input)
     int x_kt;
@@ -755,181 +578,9 @@ struct GruWin {
     const __nv_bfloat16 *w_hi[2], *w_lo[2];     // per direction: [nt(2)][x_kt + 4][WTILE_ELEMS]
     const float *bias[2];
     __nv_bfloat16 *y_hi, *y_lo;            // output sequence operand [mt][100][8] tiles
-    int *flags;                            // [2 * n_mt] zero initialised
+    int *flags;                            // unused (kept for layout stability of the host code)
     int M, n_mt, T;
 };
-
-__device__ __forceinline__ int ld_acquire(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(THREADS, 1) k_gru_window(GruWin G) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PSTAGES * PSTAGE_BYTES);
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + PSTAGES);
-    const uint32_t bar_accf = smem_u32(bars + 2 * PSTAGES), bar_acce = smem_u32(bars + 2 * PSTAGES + 2);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * PSTAGES + 4);
-    const uint32_t smem_base = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nt = blockIdx.x & 1, pair = blockIdx.x >> 1;
-    const int mt = pair % G.n_mt, dir = pair / G.n_mt;
-    const int nkt = G.x_kt + 4;
-    const int64_t seq_stride = (int64_t) G.T * 8 * TILE_ELEMS;              // y operand: elements per row tile
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < PSTAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 8); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) PTMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int t = 0; t < G.T; t++) {
-                const int tt = dir == 0 ? t : G.T - 1 - t;
-                const int tp = dir == 0 ? tt - 1 : tt + 1;
-                for (int kt = 0; kt < nkt; kt++, g++) {
-                    const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                    const uint32_t st = smem_base + s * PSTAGE_BYTES;
-                    const __nv_bfloat16 *a_hi, *a_lo;
-                    if (kt < G.x_kt) {
-                        const int64_t off = ((int64_t) (mt * G.T + tt) * G.x_kt + kt) * TILE_ELEMS;
-                        a_hi = G.x_hi + off; a_lo = G.x_lo ? G.x_lo + off : nullptr;
-                    } else {
-                        const int kk = kt - G.x_kt;
-                        if (t == 0) {
-                            const int64_t off = (int64_t) mt * G.h0_mt_stride + (int64_t) kk * TILE_ELEMS;
-                            a_hi = G.h0_hi[dir] + off; a_lo = G.h0_lo[dir] + off;
-                        } else {
-                            if (kk == 0) {
-                                // both halves of h_{t-1} of this row tile are in HBM once the pair has finished step t-1
-                                while (ld_acquire(G.flags + pair) < 2 * t) { }
-                                asm volatile("fence.proxy.async;" ::: "memory");
-                            }
-                            const int64_t off = (int64_t) mt * seq_stride + ((int64_t) tp * 8 + dir * 4 + kk) * TILE_ELEMS;
-                            a_hi = G.y_hi + off; a_lo = G.y_lo + off;
-                        }
-                    }
-                    mbar_expect_tx(bar_full + 8 * s, (a_lo ? 2u : 1u) * TILE_BYTES + 2u * WTILE_BYTES);
-                    bulk_g2s(st, a_hi, TILE_BYTES, bar_full + 8 * s);
-                    if (a_lo) bulk_g2s(st + TILE_BYTES, a_lo, TILE_BYTES, bar_full + 8 * s);
-                    const int64_t woff = ((int64_t) nt * nkt + kt) * WTILE_ELEMS;
-                    bulk_g2s(st + 2 * TILE_BYTES, G.w_hi[dir] + woff, WTILE_BYTES, bar_full + 8 * s);
-                    bulk_g2s(st + 2 * TILE_BYTES + WTILE_BYTES, G.w_lo[dir] + woff, WTILE_BYTES, bar_full + 8 * s);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int t = 0; t < G.T; t++) {
-                const uint32_t buf = (uint32_t) t & 1u, use = (uint32_t) t >> 1;
-                mbar_wait(bar_acce + 8 * buf, (use & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + buf * PBN;
-                for (int kt = 0; kt < nkt; kt++, g++) {
-                    const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
-                    mbar_wait(bar_full + 8 * s, ph);
-                    tc_fence_after();
-                    const bool has_lo = (kt >= G.x_kt) || (G.x_lo != nullptr);
-                    const uint32_t st = smem_base + s * PSTAGE_BYTES;
-#pragma unroll
-                    for (int ks = 0; ks < BK / 16; ks++) {
-                        const uint64_t a_hi = smem_desc_lbo(st + ks * 4096, 2048), a_lo = smem_desc_lbo(st + TILE_BYTES + ks * 4096, 2048);
-                        const uint64_t b_hi = smem_desc_lbo(st + 2 * TILE_BYTES + ks * 8192, 4096);
-                        const uint64_t b_lo = smem_desc_lbo(st + 2 * TILE_BYTES + WTILE_BYTES + ks * 8192, 4096);
-                        tc_mma(tacc, a_hi, b_hi, IDESC256, (kt > 0 || ks > 0) ? 1u : 0u);
-                        tc_mma(tacc, a_hi, b_lo, IDESC256, 1u);
-                        if (has_lo) tc_mma(tacc, a_lo, b_hi, IDESC256, 1u);
-                    }
-                    tc_commit(bar_empty + 8 * s);
-                }
-                tc_commit(bar_accf + 8 * buf);
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int r128 = q * 32 + lane;
-        const int row = mt * BM + r128;
-        const bool valid = row < G.M;
-        const int ubase = nt * (PBN / 4) + half * (PEPI_COLS / 4);          // first hidden unit (0..127) of this thread's 32
-        const float *bias = G.bias[dir];
-        // previous hidden state of this thread's units: from the initial-state tiles, then kept in registers
-        float hp[PEPI_COLS / 4];
-#pragma unroll
-        for (int u8 = 0; u8 < PEPI_COLS / 32; u8++) {
-            uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
-            if (valid) {
-                const int j0 = ubase + u8 * 8;
-                const int64_t o = (int64_t) mt * G.h0_mt_stride + (int64_t) (j0 >> 5) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
-                h = *reinterpret_cast<const uint4 *>(G.h0_hi[dir] + o);
-                l = *reinterpret_cast<const uint4 *>(G.h0_lo[dir] + o);
-            }
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-            for (int e = 0; e < 8; e++)
-                hp[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
-        }
-        for (int t = 0; t < G.T; t++) {
-            const int tt = dir == 0 ? t : G.T - 1 - t;
-            const uint32_t buf = (uint32_t) t & 1u, use = (uint32_t) t >> 1;
-            mbar_wait(bar_accf + 8 * buf, use & 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int cl = 0; cl < PEPI_COLS / 32; cl++) {
-                const int cc = half * (PEPI_COLS / 32) + cl;
-                const int col0 = nt * PBN + cc * 32;
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + buf * PBN + ((uint32_t) (q * 32) << 16) + (uint32_t) (cc * 32), acc);
-                if (cl == PEPI_COLS / 32 - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
-                }
-                const int j0 = col0 >> 2;
-                float hn[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias + col0 + 4 * u));
-                    const float v0 = __uint_as_float(acc[4 * u + 0]) + bz.x, v1 = __uint_as_float(acc[4 * u + 1]) + bz.y;
-                    const float v2 = __uint_as_float(acc[4 * u + 2]) + bz.z, v3 = __uint_as_float(acc[4 * u + 3]) + bz.w;
-                    const float r = sigm(v0), z = sigm(v1);
-                    const float n = tanh_fast(v2 + r * v3);
-                    hn[u] = (1.0f - z) * n + z * hp[cl * 8 + u];
-                    hp[cl * 8 + u] = hn[u];
-                }
-                if (valid) {
-                    uint4 hi, lo;
-                    split8(hn, hi, lo);
-                    const int64_t o = (int64_t) mt * seq_stride + ((int64_t) tt * 8 + dir * 4 + (j0 >> 5)) * TILE_ELEMS + ((j0 & 31) >> 3) * 1024 + r128 * 8;
-                    *reinterpret_cast<uint4 *>(G.y_hi + o) = hi;
-                    *reinterpret_cast<uint4 *>(G.y_lo + o) = lo;
-                }
-            }
-            // publish h_t: every epilogue thread fences its stores, the 256 of them meet, one bumps the pair flag
-            __threadfence();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 64) atomicAdd(G.flags + pair, 1);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) PTMEM_COLS) : "memory");
-    }
-}
 
 // ---------------------------------------------------------------- cluster-resident GRU window kernel (polish)
 // Same work split as k_gru_window, but the two CTAs that own the two halves of a (direction, row tile) form a thread-block

@@ -182,31 +182,52 @@ class VariantFromFiles(_FromFiles):
 
         def prefetch(k):
             return self._fetch(readers[k & 1], contig, *span(groups[k]))
+        import time
         cap = capacity or max(4096, int(sum(e - s + 1 for s, e in intervals)) // 30)
+        prof = dict(wait_fetch=0.0, ref_table=0.0, get_reads=0.0, stage=0.0, run=0.0, sync=0.0, end_fetch=0.0, fetch_thread=0.0)
+
+        def timed_prefetch(k):
+            t0 = time.perf_counter()
+            v = prefetch(k)
+            prof["fetch_thread"] += time.perf_counter() - t0
+            return v
         while True:
             s = self.caller.stream(params, cap)
             try:
                 with ThreadPoolExecutor(max_workers=1) as pool:
-                    fut = pool.submit(prefetch, 0)
+                    fut = pool.submit(timed_prefetch, 0)
                     done = 0
                     for k, g in enumerate(groups):
+                        t0 = time.perf_counter()
                         view = fut.result()
                         if k + 1 < len(groups):
-                            fut = pool.submit(prefetch, k + 1)
+                            fut = pool.submit(timed_prefetch, k + 1)
+                        t1 = time.perf_counter()
                         rows, queries, spans = [], [], []
                         for (a, b) in g:
                             rs, re_ = max(0, a - REGION_SAFE_BASES), b + REGION_SAFE_BASES
                             queries.append((rs, re_)); rows.append([rs, re_, a, b, 0, 0, 0, 0]); spans.append((rs, re_ + 1))
                         regions = self._ref_table(contig, rows, spans)
+                        t2 = time.perf_counter()
                         got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
                                                      max_reads=max_reads, downsample_rate=downsample_rate)
+                        t3 = time.perf_counter()
                         fetched = FetchedReads(got, regions, self.device)
                         s.stage_device(fetched, 0, len(g), done)
+                        t4 = time.perf_counter()
                         s.run(flush=False)
+                        t5 = time.perf_counter()
                         s.sync()
+                        t6 = time.perf_counter()
                         done += len(g)
+                        for key, dt in zip(("wait_fetch", "ref_table", "get_reads", "stage", "run", "sync"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5)):
+                            prof[key] += dt
+                t0 = time.perf_counter()
                 n = s.end()
-                return s.fetch(n, want_images=want_images)
+                out = s.fetch(n, want_images=want_images)
+                prof["end_fetch"] = time.perf_counter() - t0
+                self.last_profile = {k: round(v * 1e3, 2) for k, v in prof.items()}      # host wall time (ms) per stage of the last call
+                return out
             except PepperB200Error as ex:
                 if ex.rc != PB_ERR_CAPACITY:
                     raise
