@@ -393,6 +393,12 @@ int pb_polish_net_forward_host(pb_polish_net_t *net, const uint8_t *h_images,
                                int64_t n, uint8_t *h_bases, uint8_t *h_phred,
                                float *h_hidden_dbg, float *h_acc_dbg, void *stream);
 int pb_polish_net_launches(pb_polish_net_t *net, int64_t *n_launches);
+/* Precision experiments on the tcgen05 path: every GEMM runs as a_hi*w_hi + a_hi*w_lo (+ a_lo*w_hi); the mask says which GEMMs keep
+ * the third product (default: all = fp32-equivalent).  variant bits: 0 encoder h, 1 decoder x, 2 decoder h, 3 linear_1,
+ * 4 linear_2-5; polish bits: 0 encoder h, 1 decoder x, 2 decoder h.  Two-product GEMMs miss the argmax-outside-1e-4 gate
+ * (DESIGN.md), so this is not a supported operating mode.                                                                   */
+int pb_variant_net_set_lo_mask(pb_variant_net_t *net, int mask);
+int pb_polish_net_set_lo_mask(pb_polish_net_t *net, int mask);
 /* 0 = fp32 FFMA GEMMs, 1 = tcgen05 bf16x3 GEMMs (fp32-equivalent) */
 int pb_polish_net_set_mode(pb_polish_net_t *net, int mode);
 

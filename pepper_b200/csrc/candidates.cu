@@ -48,7 +48,10 @@ __global__ void k_find_candidates(const int64_t *__restrict__ positions, const i
     if (ref_ok && valid) {
         if (t == '1' && g != 0) f |= 1;                                            // Margin: SNPs with a non-ref genotype
         const double na = (double) fmaxf(p1, p2);
-        const double vaf = (double) freqs[i] / (double) depths[i];
+        // depth 0 cannot come out of the encoder (a candidate needs support >= 2); the reference would raise ZeroDivisionError
+        // (:456) — here such a record is simply never selected by the frequency rule.  freqs / depths are the encoder's uint8
+        // values, saturated at 125 like the reference's stores (region_summary.cpp:857, DataStore.py:66).
+        const double vaf = depths[i] ? (double) freqs[i] / (double) depths[i] : -1.0;
         const double pthr = t == '1' ? (in_repeat ? O.snp_p_value_in_lc : O.snp_p_value)
                           : t == '2' ? (in_repeat ? O.insert_p_value_in_lc : O.insert_p_value)
                                      : (in_repeat ? O.delete_p_value_in_lc : O.delete_p_value);

@@ -14,10 +14,14 @@ struct TcVariant {
     TcRnn enc[2], dec[2];
     TcLin lin[5];
     DevBuf img_op, yenc_hi, yenc_lo, ydec_hi, ydec_lo, c, act_hi[2], act_lo[2], final_f32;
+    // which GEMMs execute the third (a_lo x w_hi) product: bit 0 encoder h-part, 1 decoder x-part, 2 decoder h-part, 3 linear_1,
+    // 4 linear_2..5.  0x1f = fp32-equivalent everywhere (default); clearing a bit runs that GEMM with two products.
+    int lo_mask = 0x1f;
 };
 struct TcPolish {
     TcRnn enc[2], dec[2];
     DevBuf img_op, yenc_hi, yenc_lo, ydec_hi, ydec_lo, zero, flags;
+    int lo_mask = 0x7;      // bit 0 encoder h-part, 1 decoder x-part, 2 decoder h-part
 };
 // optional record sink of the variant head kernel: the encoder's columns of the candidates of this forward call + output records
 struct OutSink {

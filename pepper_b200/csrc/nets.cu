@@ -430,6 +430,17 @@ extern "C" int pb_variant_net_set_mode(pb_variant_net_t *N, int mode) {
     N->mode = mode;
     return PB_OK;
 }
+// experiments (DESIGN.md "two-product variant"): which GEMMs keep the third tensor-core product
+extern "C" int pb_variant_net_set_lo_mask(pb_variant_net_t *N, int mask) {
+    if (!N || !N->tc) { set_error("no tcgen05 state"); return PB_ERR_ARG; }
+    N->tc->lo_mask = mask & 0x1f;
+    return PB_OK;
+}
+extern "C" int pb_polish_net_set_lo_mask(pb_polish_net_t *N, int mask) {
+    if (!N || !N->tc) { set_error("no tcgen05 state"); return PB_ERR_ARG; }
+    N->tc->lo_mask = mask & 0x7;
+    return PB_OK;
+}
 extern "C" int pb_variant_net_launches(pb_variant_net_t *N, int64_t *n) {
     if (!N || !n) return PB_ERR_ARG;
     *n = N->launches;

@@ -11,23 +11,12 @@ using tc::Args;
 using tc::Dir;
 using tc::Seg;
 using tc::TILE_ELEMS;
-typedef __nv_bfloat16 bf16;
+typedef pb::tc::op_t bf16;      // 16-bit operand element (fp16 by default, bf16 with -DPB_OPERAND_BF16)
 
 namespace pb {
 
-static inline uint16_t f2bf(float f) {           // round to nearest even
-    uint32_t x;
-    memcpy(&x, &f, 4);
-    const uint32_t lsb = (x >> 16) & 1u;
-    x += 0x7FFFu + lsb;
-    return (uint16_t) (x >> 16);
-}
-static inline float bf2f(uint16_t h) {
-    uint32_t x = (uint32_t) h << 16;
-    float f;
-    memcpy(&f, &x, 4);
-    return f;
-}
+static inline uint16_t f2bf(float f) { return tc::op_bits(f); }      // round to nearest even into the operand type
+static inline float bf2f(uint16_t h) { return tc::op_val(h); }
 
 // row-major [rows][K] fp32 (rows % 128 == 0 after padding, K % 32 == 0 after padding) -> hi / lo tiles [rt][kt][4][128][8]
 static void tile_matrix(const float *src, int64_t rows, int64_t K, int64_t rows_p, int64_t Kp, std::vector<uint16_t> &hi, std::vector<uint16_t> &lo,
@@ -148,6 +137,8 @@ int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, flo
             L.y_hi = y_hi; L.y_lo = y_lo; L.y_mt_stride = (int64_t) VT * 16 * TILE_ELEMS;
             if (layer == 1 && d_hidden_dbg) { L.y_f32 = d_hidden_dbg; L.ldy = (int64_t) VT * 512; }
             L.M = (int) B; L.n_mt = (int) Mt; L.T = VT; L.c_ld = Bp;
+            L.lo_x = layer == 0 ? 1 : ((T.lo_mask >> 1) & 1);       // encoder x-part: int8 images are exact (no lo operand at all)
+            L.lo_h = layer == 0 ? (T.lo_mask & 1) : ((T.lo_mask >> 2) & 1);
             static bool attr_set = false;
             if (!attr_set) {
                 PB_CUDA(cudaFuncSetAttribute(tc::k_lstm_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSMEM_BYTES));
@@ -193,10 +184,10 @@ int variant_forward_tc(pb_variant_net *N, const int8_t *d_images, int64_t B, flo
         A.M = (int) B; A.N = 512; A.c_ld = 0;
         Dir D = empty_dir();
         if (i == 0) {
-            D.seg[0].hi = T.ydec_hi.as<bf16>(); D.seg[0].lo = T.ydec_lo.as<bf16>();
+            D.seg[0].hi = T.ydec_hi.as<bf16>(); D.seg[0].lo = ((T.lo_mask >> 3) & 1) ? T.ydec_lo.as<bf16>() : nullptr;
             D.seg[0].mt_stride = (int64_t) VT * 16 * TILE_ELEMS; D.seg[0].nkt = VT * 16;
         } else {
-            D.seg[0].hi = T.act_hi[(i - 1) & 1].as<bf16>(); D.seg[0].lo = T.act_lo[(i - 1) & 1].as<bf16>();
+            D.seg[0].hi = T.act_hi[(i - 1) & 1].as<bf16>(); D.seg[0].lo = ((T.lo_mask >> 4) & 1) ? T.act_lo[(i - 1) & 1].as<bf16>() : nullptr;
             D.seg[0].mt_stride = (int64_t) 16 * TILE_ELEMS; D.seg[0].nkt = 16;
         }
         D.w_hi = T.lin[i].w_hi.as<bf16>(); D.w_lo = T.lin[i].w_lo.as<bf16>(); D.w_nkt = T.lin[i].nkt;
@@ -231,7 +222,7 @@ __global__ void k_tc_pack_polish(const uint8_t *__restrict__ img /* [B][1000][10
         for (int e = 0; e < 8; e++) {
             const int k = kc * 8 + e;
             const float v = (k < 10) ? (float) img[(row * 1000 + win_start + t) * 10 + k] : 0.f;
-            w[e >> 1] |= (uint32_t) __bfloat16_as_ushort(__float2bfloat16_rn(v)) << (16 * (e & 1));
+            w[e >> 1] |= (uint32_t) tc::op_bits(v) << (16 * (e & 1));
         }
     }
     const int64_t o = ((row >> 7) * PWIN + t) * TILE_ELEMS + kc * 1024 + (row & 127) * 8;
@@ -247,7 +238,7 @@ __global__ void k_tc_unpack_hidden(const bf16 *__restrict__ y_hi, const bf16 *__
     const int64_t b = i / (2 * PH);
     const int tt = d == 0 ? PWIN - 1 : 0;
     const int64_t o = (((b >> 7) * PWIN + tt) * 8 + d * 4 + (j >> 5)) * TILE_ELEMS + ((j & 31) >> 3) * 1024 + (b & 127) * 8 + (j & 7);
-    out[i] = __bfloat162float(y_hi[o]) + __bfloat162float(y_lo[o]);
+    out[i] = tc::op_val(reinterpret_cast<const uint16_t *>(y_hi)[o]) + tc::op_val(reinterpret_cast<const uint16_t *>(y_lo)[o]);
 }
 // dense1 (256 -> 5) + softmax + window accumulate straight from the decoder's tiled output operand
 // (predict_distributed_cpu.py:62-81): one thread per (image row, time step); lanes = consecutive rows of a row tile, so
@@ -274,7 +265,7 @@ __global__ void __launch_bounds__(128) k_polish_dense_tiles(const bf16 *__restri
             const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                const float v = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+                const float v = tc::op_val(hw[e >> 1] >> (16 * (e & 1))) + tc::op_val(lw[e >> 1] >> (16 * (e & 1)));
                 const int f = kt * 32 + kc * 8 + e;
 #pragma unroll
                 for (int c = 0; c < 5; c++) s[c] = fmaf(v, sW[c * 256 + f], s[c]);
@@ -317,6 +308,8 @@ static int gru_layer_tc(pb_polish_net *N, TcRnn *W, DevRnn *Wb, const bf16 *x_hi
     G.h0_mt_stride = h0_is_seq ? ystride : 0;
     G.y_hi = y_hi; G.y_lo = y_lo; G.flags = nullptr;
     G.M = (int) B; G.n_mt = (int) Mt; G.T = PWIN;
+    G.lo_x = xkt == 1 ? 1 : ((T.lo_mask >> 1) & 1);                  // encoder x-part: uint8 images are exact
+    G.lo_h = xkt == 1 ? (T.lo_mask & 1) : ((T.lo_mask >> 2) & 1);
     if (W[0].nkt_x != xkt || W[0].nkt_h != 4) { set_error("gru_layer_tc: weight / operand k-tile mismatch"); return PB_ERR_STATE; }
     static const bool use_layer = !(getenv("PB_GRU_LAYER") && atoi(getenv("PB_GRU_LAYER")) == 0);
     if (use_layer) {

@@ -16,9 +16,26 @@
 #pragma once
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace pb {
 namespace tc {
+
+// 16-bit operand type of the hi / lo split.  Round 2: fp16 (11 + 11 significant bits: a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi is
+// good to ~2^-22 relative, 10-50 x closer to the fp32 reference than the bf16 split at the same three products per k-tile —
+// scripts/sim_precision.py).  Activations are clamped to +-65504 (recurrent states are in [-1, 1]; MLP
+// activations of O(1..10)); -DPB_OPERAND_BF16 restores the round-1 bf16 split (8 + 8 bits, no range limit).
+#ifdef PB_OPERAND_BF16
+typedef __nv_bfloat16 op_t;
+constexpr uint32_t OP_FMT = 1u;                      // tcgen05 kind::f16 a_format / b_format: 1 = BF16
+__host__ __device__ __forceinline__ uint16_t op_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__host__ __device__ __forceinline__ float op_val(uint32_t b) { return __bfloat162float(__ushort_as_bfloat16((unsigned short) (b & 0xffffu))); }
+#else
+typedef __half op_t;
+constexpr uint32_t OP_FMT = 0u;                      // 0 = F16
+__host__ __device__ __forceinline__ uint16_t op_bits(float v) { return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f))); }
+__host__ __device__ __forceinline__ float op_val(uint32_t b) { return __half2float(__ushort_as_half((unsigned short) (b & 0xffffu))); }
+#endif
 
 constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int TILE_ELEMS = 128 * BK;                 // 4096 bf16
@@ -32,19 +49,19 @@ constexpr int TMEM_COLS = 128;
 enum { EPI_BIAS = 0, EPI_SELU = 1, EPI_LSTM = 2, EPI_GRU = 3 };
 
 struct Seg {                       // one K-segment of the A operand
-    const __nv_bfloat16 *hi, *lo;  // lo == nullptr: exactly representable operand (int8 images), a_lo*w_hi product skipped
+    const op_t *hi, *lo;  // lo == nullptr: exactly representable operand (int8 images), a_lo*w_hi product skipped
     int64_t mt_stride;             // elements between consecutive row tiles
     int nkt;                       // k-tiles in this segment
 };
 struct Dir {
     Seg seg[2];
-    const __nv_bfloat16 *w_hi, *w_lo;   // [n_tile][w_nkt][TILE_ELEMS]
+    const op_t *w_hi, *w_lo;   // [n_tile][w_nkt][TILE_ELEMS]
     int w_nkt;                          // k-tiles per n-tile of the packed weight (>= k-tiles of this launch)
     const float *bias;                  // [N]
     float *c;                           // LSTM cell state [H][c_ld]
-    const __nv_bfloat16 *hp_hi, *hp_lo; // GRU: previous hidden state as a tiled operand (k-tile = unit/32)
+    const op_t *hp_hi, *hp_lo; // GRU: previous hidden state as a tiled operand (k-tile = unit/32)
     int64_t hp_mt_stride;
-    __nv_bfloat16 *y_hi, *y_lo;         // output operand tiles: tile (mt, y_kt0 + col/32)
+    op_t *y_hi, *y_lo;         // output operand tiles: tile (mt, y_kt0 + col/32)
     int64_t y_mt_stride;
     int y_kt0;
     float *y_f32; int64_t ldy;          // optional fp32 copy  y_f32[row*ldy + col]
@@ -95,7 +112,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return d;
 }
 // kind::f16, A = B = BF16, D = F32, both K-major, M = 128, N = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | (OP_FMT << 7) | (OP_FMT << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -119,16 +136,15 @@ __device__ __forceinline__ float selu(float x) {
     const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
     return x > 0.f ? scale * x : scale * alpha * (__expf(x) - 1.0f);
 }
-// 8 fp32 -> 8 bf16 hi + 8 bf16 lo, 16 B each
+// 8 fp32 -> 8 hi + 8 lo 16-bit operands, 16 B each
 __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-        h[i] = (uint32_t) __bfloat16_as_ushort(h0) | ((uint32_t) __bfloat16_as_ushort(h1) << 16);
-        l[i] = (uint32_t) __bfloat16_as_ushort(l0) | ((uint32_t) __bfloat16_as_ushort(l1) << 16);
+        const uint16_t h0 = op_bits(v[2 * i]), h1 = op_bits(v[2 * i + 1]);
+        const uint16_t l0 = op_bits(v[2 * i] - op_val(h0)), l1 = op_bits(v[2 * i + 1] - op_val(h1));
+        h[i] = (uint32_t) h0 | ((uint32_t) h1 << 16);
+        l[i] = (uint32_t) l0 | ((uint32_t) l1 << 16);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -154,7 +170,7 @@ constexpr int PEPI_COLS = PBN / 2;                    // columns per epilogue wa
 constexpr int PG_EPI_WARPS = PB_PG_EPI_WARPS;         // epilogue warps of k_tc_gemm_p: 4 TMEM lane quarters x column groups
 constexpr int PG_COLS = PBN / (PG_EPI_WARPS / 4);     // columns per epilogue warp
 constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS;
-constexpr uint32_t IDESC256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (PBN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+constexpr uint32_t IDESC256 = (1u << 4) | (OP_FMT << 7) | (OP_FMT << 10) | ((uint32_t) (PBN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
 __device__ __forceinline__ uint64_t smem_desc_lbo(uint32_t addr, uint32_t lbo) {
     uint64_t d = 0;
     d |= (uint64_t) ((addr >> 4) & 0x3FFF);
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_tc_gemm_p(Args G, int n_mt, i
                     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
                     for (int e = 0; e < 8; e++)
-                        st[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+                        st[u8 * 8 + e] = op_val(hw[e >> 1] >> (16 * (e & 1))) + op_val(lw[e >> 1] >> (16 * (e & 1)));
                 }
             }
             mbar_wait(bar_accf + 8 * buf, use & 1u);
@@ -383,18 +399,19 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_tc_gemm_p(Args G, int n_mt, i
 // tiles and steps.  One chunk of 9,472 candidates = 74 row tiles x 2 directions = 148 CTAs = one per SM; 33 x fewer
 // launches, prologues and tails than the per-step kernel above (kept as the cross-check path).
 struct LstmLayer {
-    const __nv_bfloat16 *x_hi, *x_lo;           // input sequence operand: tile (mt, t, kt) at mt * x_mt_stride + (t * x_nkt + kt) * TILE_ELEMS
+    const op_t *x_hi, *x_lo;           // input sequence operand: tile (mt, t, kt) at mt * x_mt_stride + (t * x_nkt + kt) * TILE_ELEMS
     int64_t x_mt_stride;
     int x_nkt;
-    const __nv_bfloat16 *w_hi[2], *w_lo[2];     // per direction: [4 n-tiles][x_nkt + 8][WTILE_ELEMS]
+    const op_t *w_hi[2], *w_lo[2];     // per direction: [4 n-tiles][x_nkt + 8][WTILE_ELEMS]
     const float *bias[2];
     float *c[2];                                // cell state per direction [256][c_ld], zero initialised
-    __nv_bfloat16 *y_hi, *y_lo;                 // output sequence operand [mt][T][16] tiles; (time tt, direction d) -> k-tiles tt * 16 + d * 8 ...
+    op_t *y_hi, *y_lo;                 // output sequence operand [mt][T][16] tiles; (time tt, direction d) -> k-tiles tt * 16 + d * 8 ...
     int64_t y_mt_stride;
     float *y_f32;                               // optional fp32 copy [row][T][512]
     int64_t ldy;
     int M, n_mt, T;
     int64_t c_ld;
+    int lo_x, lo_h;                             // 1: the a_lo x w_hi product of the x-part / h-part is executed (0: two products)
 };
 
 __global__ void __launch_bounds__(PG_THREADS, 1) k_lstm_layer(LstmLayer G) {
@@ -434,10 +451,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_lstm_layer(LstmLayer G) {
                     for (int kt = 0; kt < nkt; kt++, g++) {
                         const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
                         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                        const __nv_bfloat16 *a_hi, *a_lo;
+                        const op_t *a_hi, *a_lo;
                         if (kt < G.x_nkt) {
                             const int64_t off = (int64_t) mt * G.x_mt_stride + ((int64_t) tt * G.x_nkt + kt) * TILE_ELEMS;
-                            a_hi = G.x_hi + off; a_lo = G.x_lo ? G.x_lo + off : nullptr;
+                            a_hi = G.x_hi + off; a_lo = (G.x_lo && G.lo_x) ? G.x_lo + off : nullptr;
                         } else {
                             const int kk = kt - G.x_nkt;
                             if (kk == 0 && nt == 0) {
@@ -446,7 +463,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_lstm_layer(LstmLayer G) {
                                 asm volatile("fence.proxy.async;" ::: "memory");
                             }
                             const int64_t off = (int64_t) mt * G.y_mt_stride + ((int64_t) tp * 16 + dir * 8 + kk) * TILE_ELEMS;
-                            a_hi = G.y_hi + off; a_lo = G.y_lo + off;
+                            a_hi = G.y_hi + off; a_lo = G.lo_h ? G.y_lo + off : nullptr;
                         }
                         const uint32_t st = smem_base + s * PSTAGE_BYTES;
                         mbar_expect_tx(bar_full + 8 * s, (a_lo ? 2u : 1u) * TILE_BYTES + 2u * WTILE_BYTES);
@@ -473,7 +490,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_lstm_layer(LstmLayer G) {
                         const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
                         mbar_wait(bar_full + 8 * s, ph);
                         tc_fence_after();
-                        const bool has_lo = kt >= G.x_nkt || G.x_lo != nullptr;
+                        const bool has_lo = kt >= G.x_nkt ? (G.lo_h != 0) : (G.x_lo != nullptr && G.lo_x != 0);
                         const uint32_t st = smem_base + s * PSTAGE_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ks++) {
@@ -571,15 +588,16 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_lstm_layer(LstmLayer G) {
 // fallback that splits the hidden units over a 2-CTA cluster).  The first persistent version, k_gru_window (sibling CTAs
 // exchanging h through HBM flags under a cooperative launch), was removed in round 2: superseded twice.
 struct GruWin {
-    const __nv_bfloat16 *x_hi, *x_lo;      // input sequence operand [mt][100][x_kt] tiles (x_lo == nullptr: exact input)
+    const op_t *x_hi, *x_lo;      // input sequence operand [mt][100][x_kt] tiles (x_lo == nullptr: exact input)
     int x_kt;
-    const __nv_bfloat16 *h0_hi[2], *h0_lo[2];   // initial state tiles per direction (4 k-tiles per row tile)
+    const op_t *h0_hi[2], *h0_lo[2];   // initial state tiles per direction (4 k-tiles per row tile)
     int64_t h0_mt_stride;
-    const __nv_bfloat16 *w_hi[2], *w_lo[2];     // per direction: [nt(2)][x_kt + 4][WTILE_ELEMS]
+    const op_t *w_hi[2], *w_lo[2];     // per direction: [nt(2)][x_kt + 4][WTILE_ELEMS]
     const float *bias[2];
-    __nv_bfloat16 *y_hi, *y_lo;            // output sequence operand [mt][100][8] tiles
+    op_t *y_hi, *y_lo;            // output sequence operand [mt][100][8] tiles
     int *flags;                            // unused (kept for layout stability of the host code)
     int M, n_mt, T;
+    int lo_x, lo_h;                        // k_gru_layer: 1 = execute the a_lo x w_hi product of the x-part / h-part
 };
 
 // ---------------------------------------------------------------- cluster-resident GRU window kernel (polish)
@@ -716,7 +734,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_gru_cl
             const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
             for (int e = 0; e < 8; e++)
-                hp[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+                hp[u8 * 8 + e] = op_val(hw[e >> 1] >> (16 * (e & 1))) + op_val(lw[e >> 1] >> (16 * (e & 1)));
         }
         const uint32_t peer = (uint32_t) (nt ^ 1);
         for (int t = 0; t < G.T; t++) {
@@ -829,22 +847,22 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_gru_layer(GruWin G) {
                     for (int kt = 0; kt < nkt; kt++, g++) {
                         const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
                         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                        const __nv_bfloat16 *a_hi, *a_lo;
+                        const op_t *a_hi, *a_lo;
                         if (kt < G.x_kt) {
                             const int64_t off = ((int64_t) (mt * G.T + tt) * G.x_kt + kt) * TILE_ELEMS;
-                            a_hi = G.x_hi + off; a_lo = G.x_lo ? G.x_lo + off : nullptr;
+                            a_hi = G.x_hi + off; a_lo = (G.x_lo && G.lo_x) ? G.x_lo + off : nullptr;
                         } else {
                             const int kk = kt - G.x_kt;
                             if (t == 0) {
                                 const int64_t off = (int64_t) mt * G.h0_mt_stride + (int64_t) kk * TILE_ELEMS;
-                                a_hi = G.h0_hi[dir] + off; a_lo = G.h0_lo[dir] + off;
+                                a_hi = G.h0_hi[dir] + off; a_lo = G.lo_h ? G.h0_lo[dir] + off : nullptr;
                             } else {
                                 if (kk == 0 && nt == 0) {
                                     mbar_wait(bar_h, (uint32_t) (t - 1) & 1u);      // every epilogue warp has written its part of h_{t-1}
                                     asm volatile("fence.proxy.async;" ::: "memory");
                                 }
                                 const int64_t off = (int64_t) mt * seq_stride + ((int64_t) tp * 8 + dir * 4 + kk) * TILE_ELEMS;
-                                a_hi = G.y_hi + off; a_lo = G.y_lo + off;
+                                a_hi = G.y_hi + off; a_lo = G.lo_h ? G.y_lo + off : nullptr;
                             }
                         }
                         const uint32_t st = smem_base + s * PSTAGE_BYTES;
@@ -871,7 +889,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_gru_layer(GruWin G) {
                         const uint32_t s = g % PSTAGES, ph = (g / PSTAGES) & 1u;
                         mbar_wait(bar_full + 8 * s, ph);
                         tc_fence_after();
-                        const bool has_lo = kt >= G.x_kt || G.x_lo != nullptr;
+                        const bool has_lo = kt >= G.x_kt ? (G.lo_h != 0) : (G.x_lo != nullptr && G.lo_x != 0);
                         const uint32_t st = smem_base + s * PSTAGE_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ks++) {
@@ -916,7 +934,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_gru_layer(GruWin G) {
                     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
                     for (int e = 0; e < 8; e++)
-                        hp[u8 * 8 + e] = __uint_as_float((hw[e >> 1] >> (16 * (e & 1))) << 16) + __uint_as_float((lw[e >> 1] >> (16 * (e & 1))) << 16);
+                        hp[u8 * 8 + e] = op_val(hw[e >> 1] >> (16 * (e & 1))) + op_val(lw[e >> 1] >> (16 * (e & 1)));
                 }
                 mbar_wait(bar_accf + 8 * buf, use & 1u);
                 tc_fence_after();
@@ -967,7 +985,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) k_gru_layer(GruWin G) {
 
 // ---------------------------------------------------------------- operand preparation kernels
 // int8 images [B][T][F] -> tiled operand [mt][T][1 k-tile] (hi only; |v| <= 128 is exact in bf16)
-__global__ void k_tc_pack_images(const int8_t *__restrict__ img, __nv_bfloat16 *__restrict__ op, int64_t B, int T, int F) {
+__global__ void k_tc_pack_images(const int8_t *__restrict__ img, op_t *__restrict__ op, int64_t B, int T, int F) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;     // one thread per (row, t, kc)
     const int64_t total = ceil_div(B, 128) * 128 * T * 4;
     if (i >= total) return;
@@ -981,7 +999,7 @@ __global__ void k_tc_pack_images(const int8_t *__restrict__ img, __nv_bfloat16 *
         for (int e = 0; e < 8; e++) {
             const int k = kc * 8 + e;
             const float v = (k < F) ? (float) img[(row * T + t) * F + k] : 0.f;
-            w[e >> 1] |= (uint32_t) __bfloat16_as_ushort(__float2bfloat16_rn(v)) << (16 * (e & 1));
+            w[e >> 1] |= (uint32_t) op_bits(v) << (16 * (e & 1));
         }
     }
     const int64_t o = ((row >> 7) * T + t) * TILE_ELEMS + kc * 1024 + (row & 127) * 8;

@@ -170,6 +170,11 @@ class PolishNet:
         """0 = fp32 FFMA GEMMs, 1 = tcgen05 bf16x3 GEMMs (fp32-equivalent)."""
         _lib.check(self.L.pb_polish_net_set_mode(self.h, mode), "pb_polish_net_set_mode")
 
+    def set_lo_mask(self, mask: int) -> None:
+        """Experiments only: bit set = that GEMM keeps its third product; bits: 0 encoder h, 1 decoder x, 2 decoder h; default 7."""
+        self.L.pb_polish_net_set_lo_mask.argtypes = [C.c_void_p, C.c_int]
+        _lib.check(self.L.pb_polish_net_set_lo_mask(self.h, mask), "pb_polish_net_set_lo_mask")
+
     def launches(self) -> int:
         n = C.c_int64(0)
         _lib.check(self.L.pb_polish_net_launches(self.h, C.byref(n)), "launches")
