@@ -38,25 +38,40 @@ __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+// LSB-first bit reader over 32-bit ALIGNED loads (the payload may start at any byte: the first word is shifted).  Reads may run
+// up to 7 bytes past the payload into the next block's header / the buffer padding — consumed positions are checked, not loads.
 struct BitReader {
-    const uint8_t *p;
-    int64_t pos, end;
+    const uint8_t *p;          // payload start (any alignment)
+    const uint32_t *w;         // next aligned word to load
+    int64_t end;               // payload length in bytes
+    int64_t loaded;            // payload bytes loaded so far (may exceed `end`)
     uint64_t buf;
     int cnt;
-    __device__ __forceinline__ void init(const uint8_t *src, int64_t len) { p = src; pos = 0; end = len; buf = 0; cnt = 0; }
-    __device__ __forceinline__ void refill() {                 // at least 32 valid bits afterwards (zero padded past the end)
-        if (cnt <= 32) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) { const uint32_t b = (pos + k < end) ? p[pos + k] : 0u; w |= b << (8 * k); }
-            buf |= (uint64_t) w << cnt;
-            pos += 4; cnt += 32;
-        }
+    __device__ __forceinline__ void init(const uint8_t *src, int64_t len) {
+        p = src; end = len;
+        const int mis = (int) ((uintptr_t) src & 3);
+        w = reinterpret_cast<const uint32_t *>(src - mis);
+        buf = (uint64_t) (*w++ >> (8 * mis));
+        cnt = 32 - 8 * mis;
+        loaded = 4 - mis;
     }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t) (buf & ((1ull << n) - 1)); }
+    __device__ __forceinline__ void refill() {                 // more than 32 valid bits afterwards
+        if (cnt <= 32) { buf |= (uint64_t) (*w++) << cnt; cnt += 32; loaded += 4; }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t) buf & ((1u << n) - 1u); }
     __device__ __forceinline__ void skip(int n) { buf >>= n; cnt -= n; }
     __device__ __forceinline__ uint32_t get(int n) { refill(); const uint32_t v = peek(n); skip(n); return v; }
-    __device__ __forceinline__ bool overrun() const { return pos - (cnt >> 3) > end; }     // consumed bytes beyond the payload
+    __device__ __forceinline__ uint32_t get_nofill(int n) { const uint32_t v = peek(n); skip(n); return v; }     // caller guarantees n <= cnt
+    __device__ __forceinline__ int64_t consumed() const { return loaded - (cnt >> 3); }                           // whole bytes consumed
+    __device__ __forceinline__ bool overrun() const { return consumed() > end; }
+    __device__ __forceinline__ void seek(int64_t byte_pos) {                                                     // restart at a byte position
+        const uint8_t *q = p + byte_pos;
+        const int mis = (int) ((uintptr_t) q & 3);
+        w = reinterpret_cast<const uint32_t *>(q - mis);
+        buf = (uint64_t) (*w++ >> (8 * mis));
+        cnt = 32 - 8 * mis;
+        loaded = byte_pos + 4 - mis;
+    }
 };
 
 // Builds the primary table + the canonical (count, sorted symbols) arrays for `n` symbols with code lengths lens[0..n).
@@ -141,14 +156,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8
                 const uint32_t l = br.get(16), nl = br.get(16);
                 if ((l ^ 0xffffu) != nl) err = 1;
                 len = (int) l;
-                src = br.pos - (br.cnt >> 3);                         // byte position of the next unread input byte
+                src = br.consumed();                                  // byte position of the next unread input byte
             }
             err = __shfl_sync(0xffffffffu, err, 0); len = __shfl_sync(0xffffffffu, len, 0); src = __shfl_sync(0xffffffffu, src, 0);
             if (!err && (pos + len > D.out_len || src + len > D.in_len)) err = 4;
             if (err) break;
             for (int i = lane; i < len; i += 32) dst[pos + i] = br.p[src + i];
             pos += len;
-            if (lane == 0) { br.pos = src + len; br.buf = 0; br.cnt = 0; }
+            if (lane == 0) br.seek(src + len);
             __syncwarp();
             continue;
         }
@@ -199,36 +214,42 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8
         if (!build_table(T.lens, 288, T.lit, LIT_BITS, T.lit_cnt, T.lit_sym, T.code, lane)) { err = 2; break; }
         // an incomplete distance code is legal when only one distance code is used (zlib emits it): do not reject under-subscription
         if (!build_table(T.lens + 288, 30, T.dist, DIST_BITS, T.dist_cnt, T.dist_sym, T.code, lane)) { err = 2; break; }
-        // ---- symbols: lane 0 decodes (writing literals itself) up to the next match / end of block, the warp performs the copy
+        // ---- symbols: lane 0 decodes (writing literals itself) up to the next match / end of block, the warp performs the copy.
+        //      One packed broadcast per match: bits 0-15 distance (1..32768), 16-24 length, 28-30 error, bit 31 end of block.
         for (;;) {
-            int mlen = 0, mdist = 0;
+            uint32_t msg = 0;
             if (lane == 0) {
                 for (;;) {
-                    const int s = decode_sym(br, T.lit, LIT_BITS, T.lit_cnt, T.lit_sym);
+                    const int s = decode_sym(br, T.lit, LIT_BITS, T.lit_cnt, T.lit_sym);          // refills: > 32 bits before, >= 18 after
                     if (s < 256) {
                         if (s < 0) { err = 3; break; }
                         if (pos >= D.out_len) { err = 4; break; }
                         dst[pos++] = (uint8_t) s;
                         continue;
                     }
-                    if (s == 256) { mlen = -1; break; }
+                    if (s == 256) { msg = 0x80000000u; break; }
                     if (s > 285) { err = 3; break; }
                     const int li = s - 257;
-                    mlen = c_len_base[li] + (int) br.get(c_len_extra[li]);
-                    const int ds = decode_sym(br, T.dist, DIST_BITS, T.dist_cnt, T.dist_sym);
+                    const int mlen = c_len_base[li] + (int) br.get_nofill(c_len_extra[li]);       // <= 5 extra bits: still in the buffer
+                    const int ds = decode_sym(br, T.dist, DIST_BITS, T.dist_cnt, T.dist_sym);      // refills again: > 32 bits before
                     if (ds < 0 || ds > 29) { err = 3; break; }
-                    mdist = c_dist_base[ds] + (int) br.get(c_dist_extra[ds]);
+                    const int mdist = c_dist_base[ds] + (int) br.get_nofill(c_dist_extra[ds]);    // 15 + 13 bits <= 32
+                    msg = (uint32_t) (mdist & 0xffff) | ((uint32_t) mlen << 16);
                     break;
                 }
                 if (br.overrun()) err = 7;
+                msg |= (uint32_t) err << 28;
             }
-            err = __shfl_sync(0xffffffffu, err, 0);
+            msg = __shfl_sync(0xffffffffu, msg, 0);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            err = (int) ((msg >> 28) & 7u);
             if (err) break;
-            mlen = __shfl_sync(0xffffffffu, mlen, 0); mdist = __shfl_sync(0xffffffffu, mdist, 0); pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (mlen < 0) break;                                        // end of this deflate block
+            if (msg >> 31) break;                                       // end of this deflate block
+            const int mlen = (int) ((msg >> 16) & 0x1ffu);
+            const int mdist = (msg & 0xffffu) ? (int) (msg & 0xffffu) : 65536;     // 32768 fits; 0 cannot occur (bases start at 1)
             if (mdist > pos) { err = 5; break; }
             if (pos + mlen > D.out_len) { err = 4; break; }
-            __syncwarp();                                               // lane 0's literal stores are visible to the copying lanes
+            __syncwarp();                                               // earlier stores of this warp (literals, previous copy) are visible
             const uint8_t *src = dst + pos - mdist;
             if (mdist >= mlen) {
                 for (int i = lane; i < mlen; i += 32) dst[pos + i] = src[i];
@@ -236,7 +257,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8
                 for (int i = lane; i < mlen; i += 32) dst[pos + i] = src[i % mdist];
             }
             pos += mlen;
-            __syncwarp();
         }
     }
     if (!err && pos != D.out_len) err = 6;

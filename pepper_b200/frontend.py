@@ -191,37 +191,54 @@ class VariantFromFiles(_FromFiles):
             v = prefetch(k)
             prof["fetch_thread"] += time.perf_counter() - t0
             return v
+        import torch
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)        # get_reads of batch k+1 runs here, beside the network of batch k
+
+        def trim(view, g):
+            """reference strings + batched get_reads of one batch (side stream; synchronous for the host)."""
+            t1 = time.perf_counter()
+            rows, queries, spans = [], [], []
+            for (a, b) in g:
+                rs, re_ = max(0, a - REGION_SAFE_BASES), b + REGION_SAFE_BASES
+                queries.append((rs, re_)); rows.append([rs, re_, a, b, 0, 0, 0, 0]); spans.append((rs, re_ + 1))
+            regions = self._ref_table(contig, rows, spans)
+            t2 = time.perf_counter()
+            got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
+                                         max_reads=max_reads, downsample_rate=downsample_rate, stream=self._side.cuda_stream)
+            prof["ref_table"] += t2 - t1; prof["get_reads"] += time.perf_counter() - t2
+            return got, regions
         while True:
             s = self.caller.stream(params, cap)
             try:
                 with ThreadPoolExecutor(max_workers=1) as pool:
                     fut = pool.submit(timed_prefetch, 0)
+                    t0 = time.perf_counter()
+                    view = fut.result()
+                    prof["wait_fetch"] += time.perf_counter() - t0
+                    if len(groups) > 1:
+                        fut = pool.submit(timed_prefetch, 1)
+                    nxt = trim(view, groups[0])
                     done = 0
                     for k, g in enumerate(groups):
-                        t0 = time.perf_counter()
-                        view = fut.result()
-                        if k + 1 < len(groups):
-                            fut = pool.submit(timed_prefetch, k + 1)
-                        t1 = time.perf_counter()
-                        rows, queries, spans = [], [], []
-                        for (a, b) in g:
-                            rs, re_ = max(0, a - REGION_SAFE_BASES), b + REGION_SAFE_BASES
-                            queries.append((rs, re_)); rows.append([rs, re_, a, b, 0, 0, 0, 0]); spans.append((rs, re_ + 1))
-                        regions = self._ref_table(contig, rows, spans)
-                        t2 = time.perf_counter()
-                        got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
-                                                     max_reads=max_reads, downsample_rate=downsample_rate)
+                        got, regions = nxt
                         t3 = time.perf_counter()
                         fetched = FetchedReads(got, regions, self.device)
                         s.stage_device(fetched, 0, len(g), done)
                         t4 = time.perf_counter()
-                        s.run(flush=False)
+                        s.run(flush=False)                 # encoder done (host-synchronous), network of this batch queued
                         t5 = time.perf_counter()
+                        if k + 1 < len(groups):            # while that network runs: the next batch's records -> trimmed reads
+                            view = fut.result()
+                            t6 = time.perf_counter()
+                            prof["wait_fetch"] += t6 - t5
+                            if k + 2 < len(groups):
+                                fut = pool.submit(timed_prefetch, k + 2)
+                            nxt = trim(view, groups[k + 1])
+                        t7 = time.perf_counter()
                         s.sync()
-                        t6 = time.perf_counter()
+                        prof["stage"] += t4 - t3; prof["run"] += t5 - t4; prof["sync"] += time.perf_counter() - t7
                         done += len(g)
-                        for key, dt in zip(("wait_fetch", "ref_table", "get_reads", "stage", "run", "sync"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5)):
-                            prof[key] += dt
                 t0 = time.perf_counter()
                 n = s.end()
                 out = s.fetch(n, want_images=want_images)
