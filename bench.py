@@ -387,7 +387,7 @@ def files_leg(args, cfg, local):
         genomic = sum(e - s for s, e in iv)
         vf = VariantFromFiles(bam, fa, weights.random_variant_state(0), device=local, gpu_inflate=not args.host_inflate)
         cap = int(genomic // (40 if cfg["platform"] == "ONT" else 250)) + 65536
-        vf.call_stream("chr20s", iv[:64], params, batch=args.group_regions, capacity=cap)        # warm-up (allocations, page cache of the head)
+        vf.call_stream("chr20s", iv[:2 * args.files_batch], params, batch=args.files_batch, capacity=cap)   # warm-up (allocations, page cache of the head)
         with open(bam, "rb") as f:                               # page cache: the file was just written, read it once anyway
             while f.read(1 << 26):
                 pass
@@ -396,7 +396,7 @@ def files_leg(args, cfg, local):
         t0 = time.perf_counter()
         n_cand = 0
         for _ in range(steps):
-            calls = vf.call_stream("chr20s", iv, params, batch=args.group_regions, capacity=cap)
+            calls = vf.call_stream("chr20s", iv, params, batch=args.files_batch, capacity=cap)
             n_cand = len(calls)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
@@ -405,7 +405,7 @@ def files_leg(args, cfg, local):
         stage_prof = getattr(vf, "last_profile", None)
         vf.close()
         return {"value": genomic / dt, "unit": "bases/s", "ms_per_step": dt * 1e3, "steps": steps, "regions": len(iv), "genomic_bases": genomic,
-                "candidates": n_cand, "bam_bytes": os.path.getsize(bam), "records_per_block": rec.n_records, "batch_regions": args.group_regions,
+                "candidates": n_cand, "bam_bytes": os.path.getsize(bam), "records_per_block": rec.n_records, "batch_regions": args.files_batch,
                 "inflate": "host zlib thread pool" if args.host_inflate else "GPU (k_bgzf_inflate, warp per BGZF block)",
                 "last_batch_fetch_ms": ft, "host_stage_ms": stage_prof, "h2d_bytes_per_step": int(os.path.getsize(bam)), "d2h_bytes_per_step": int(n_cand * 90),
                 "gen_seconds": round(gen_s, 1),
@@ -416,7 +416,7 @@ def files_leg(args, cfg, local):
 
 # figures carried over from the ncu --set full captures under profiles/ (per candidate / per algorithmic byte)
 PRODUCTS = 3
-OPERAND = "bf16"
+OPERAND = "fp16"
 TRAFFIC_RATIO_COUNT = 1.30
 TRAFFIC_NOTE_COUNT = ("dram__bytes_read+write of k_tile_count = 1.30 x algorithmic bytes in the ncu --set full capture "
                       "(77.2 MB vs 59.4 MB at 8 regions, profiles/README.md); scaled to this step")
@@ -759,6 +759,7 @@ def main():
     ap.add_argument("--no-files", action="store_true", help="skip the from-files leg (writes a chr20-scale BAM to a temp dir)")
     ap.add_argument("--files-regions", type=int, default=0, help="regions of the from-files leg (default: --regions)")
     ap.add_argument("--files-steps", type=int, default=2)
+    ap.add_argument("--files-batch", type=int, default=64, help="regions per batch of the from-files streaming session")
     ap.add_argument("--host-inflate", action="store_true", help="from-files leg with the host zlib pool instead of the GPU inflate")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
