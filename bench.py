@@ -759,7 +759,7 @@ def main():
     ap.add_argument("--no-files", action="store_true", help="skip the from-files leg (writes a chr20-scale BAM to a temp dir)")
     ap.add_argument("--files-regions", type=int, default=0, help="regions of the from-files leg (default: --regions)")
     ap.add_argument("--files-steps", type=int, default=2)
-    ap.add_argument("--files-batch", type=int, default=64, help="regions per batch of the from-files streaming session")
+    ap.add_argument("--files-batch", type=int, default=32, help="regions per batch of the from-files streaming session")
     ap.add_argument("--host-inflate", action="store_true", help="from-files leg with the host zlib pool instead of the GPU inflate")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -164,7 +164,10 @@ struct VariantStream {
     int32_t region_id0[2] = {0, 0};
     bool staged[2] = {false, false}, from_host[2] = {false, false};
     int next_stage = 0, next_run = 0;
-    bool timing_pending = false;
+    // one event triple per group (encoder start, encoder end = network start, network end): read back at _sync / _end only, so
+    // that run(g+1) — whose host-side table building is not short — can start while the network of group g is still running
+    std::vector<cudaEvent_t> ev;
+    int64_t ev_done = 0;               // groups whose times have been added to enc_ms / net_ms
     float enc_ms = 0.f, net_ms = 0.f;
     float enc_phase_ms[5] = {0, 0, 0, 0, 0};        // prefix, count, sites, alleles, windows — summed over the groups
     int64_t enc_launches = 0, net_launches = 0, groups = 0;
@@ -200,7 +203,7 @@ extern "C" int pb_variant_stream_begin(pb_variant_encoder_t *e, pb_variant_net_t
     PB_TRY(e->p_probs.reserve(sizeof(float) * 3 * cap));
     S->active = true; S->params = *params; S->capacity = capacity; S->done = 0; S->net_done = 0; S->d_records = d_records;
     S->st = (cudaStream_t) stream_;
-    S->staged[0] = S->staged[1] = false; S->next_stage = 0; S->next_run = 0; S->timing_pending = false;
+    S->staged[0] = S->staged[1] = false; S->next_stage = 0; S->next_run = 0; S->ev_done = 0;
     S->enc_ms = S->net_ms = 0.f;
     for (int i = 0; i < 5; i++) S->enc_phase_ms[i] = 0.f;
     S->enc_launches = S->net_launches = S->groups = 0;
@@ -251,13 +254,24 @@ extern "C" int pb_variant_stream_stage_device(pb_variant_encoder_t *e, const pb_
     return PB_OK;
 }
 
-static void stream_collect_timing(pb_variant_encoder_t *e, VariantStream *S) {
-    if (!S->timing_pending) return;
-    float a = 0.f, b = 0.f;
-    cudaEventElapsedTime(&a, e->pevt[0], e->pevt[1]);
-    cudaEventElapsedTime(&b, e->pevt[1], e->pevt[2]);
-    S->enc_ms += a; S->net_ms += b;
-    S->timing_pending = false;
+// adds the times of every group whose events have completed (call after a stream synchronisation)
+static void stream_collect_timing(VariantStream *S) {
+    for (; S->ev_done < S->groups; S->ev_done++) {
+        float a = 0.f, b = 0.f;
+        cudaEvent_t *E = &S->ev[(size_t) 3 * S->ev_done];
+        cudaEventElapsedTime(&a, E[0], E[1]);
+        cudaEventElapsedTime(&b, E[1], E[2]);
+        S->enc_ms += a; S->net_ms += b;
+    }
+}
+static int stream_events(VariantStream *S, int64_t group, cudaEvent_t **E) {
+    while ((int64_t) S->ev.size() < 3 * (group + 1)) {
+        cudaEvent_t x;
+        PB_CUDA(cudaEventCreate(&x));
+        S->ev.push_back(x);
+    }
+    *E = &S->ev[(size_t) 3 * group];
+    return PB_OK;
 }
 
 static int stream_network(pb_variant_encoder_t *e, pb_variant_net_t *net, VariantStream *S, int64_t run) {
@@ -284,12 +298,13 @@ extern "C" int pb_variant_stream_run(pb_variant_encoder_t *e, pb_variant_net_t *
     const int b = S->next_run;
     if (!S->staged[b]) { set_error("no staged group"); return PB_ERR_STATE; }
     cudaStream_t st = S->st;
-    if (S->timing_pending) { PB_CUDA(cudaStreamSynchronize(st)); stream_collect_timing(e, S); }
+    cudaEvent_t *E;
+    PB_TRY(stream_events(S, S->groups, &E));
     PB_CUDA(cudaStreamWaitEvent(st, e->copied[b], 0));
     GroupView &V = S->V[b];
     int64_t n_g = 0;
     const int64_t done = S->done, room = std::max<int64_t>(S->capacity - done, 0);
-    PB_CUDA(cudaEventRecord(e->pevt[0], st));
+    PB_CUDA(cudaEventRecord(E[0], st));
     int rc = pb_variant_encode_device(e, &V.d, V.d_regions, (int64_t) V.h_regions.size(), V.h_regions.data(), V.d_ref, 0, &S->params, room,
                                       e->p_images.as<int8_t>() + done * 33 * 26, e->p_positions.as<int64_t>() + done,
                                       e->p_depths.as<uint8_t>() + done, e->p_freqs.as<uint8_t>() + done,
@@ -298,15 +313,15 @@ extern "C" int pb_variant_stream_run(pb_variant_encoder_t *e, pb_variant_net_t *
     if (n_total) *n_total = done + n_g;
     if (rc != PB_OK) { if (rc == PB_ERR_CAPACITY) cudaStreamSynchronize(e->copy_stream); return rc; }
     for (int i = 0; i < 5; i++) S->enc_phase_ms[i] += e->ms[i];
-    S->enc_launches += e->launches; S->groups++;
+    S->enc_launches += e->launches;
     if (n_g > 0 && S->region_id0[b] != 0)
         k_add_offset_i32<<<(unsigned) ceil_div(n_g, 256), 256, 0, st>>>(e->p_region_of.as<int32_t>() + done, n_g, S->region_id0[b]);
-    PB_CUDA(cudaEventRecord(e->pevt[1], st));
+    PB_CUDA(cudaEventRecord(E[1], st));
     S->done = done + n_g;
     const int64_t avail = S->done - S->net_done;
     PB_TRY(stream_network(e, net, S, flush ? avail : avail / PIPE_NET_CHUNK * PIPE_NET_CHUNK));
-    PB_CUDA(cudaEventRecord(e->pevt[2], st));
-    S->timing_pending = true;
+    PB_CUDA(cudaEventRecord(E[2], st));
+    S->groups++;
     return PB_OK;
 }
 
@@ -314,7 +329,7 @@ extern "C" int pb_variant_stream_sync(pb_variant_encoder_t *e) {
     VariantStream *S;
     PB_TRY(session(e, &S, true));
     PB_CUDA(cudaStreamSynchronize(S->st));
-    stream_collect_timing(e, S);
+    stream_collect_timing(S);
     return PB_OK;
 }
 
@@ -325,15 +340,15 @@ extern "C" int pb_variant_stream_end(pb_variant_encoder_t *e, pb_variant_net_t *
     if (!net || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
     cudaStream_t st = S->st;
     PB_CUDA(cudaStreamSynchronize(st));
-    stream_collect_timing(e, S);
+    stream_collect_timing(S);
     if (S->done > S->net_done) {
-        PB_CUDA(cudaEventRecord(e->pevt[0], st));
         PB_CUDA(cudaEventRecord(e->pevt[1], st));
         PB_TRY(stream_network(e, net, S, S->done - S->net_done));
         PB_CUDA(cudaEventRecord(e->pevt[2], st));
-        S->timing_pending = true;
         PB_CUDA(cudaStreamSynchronize(st));
-        stream_collect_timing(e, S);
+        float b = 0.f;
+        cudaEventElapsedTime(&b, e->pevt[1], e->pevt[2]);
+        S->net_ms += b;
     }
     PB_CUDA(cudaStreamSynchronize(e->copy_stream));
     e->pms[0] = S->enc_ms; e->pms[1] = S->net_ms;
@@ -425,8 +440,9 @@ extern "C" int pb_variant_call_host(pb_variant_encoder_t *e, pb_variant_net_t *n
         if (rc != PB_OK) { e->vstream->active = false; return rc; }
         // the network of this group is queued: issue the next group's copies now, so that neither the host work of staging nor
         // the copies themselves leave the compute stream idle
+        // no sync here: the next run() builds its host-side tables while this group's network runs, and its encoder synchronises the
+        // stream before any staging buffer is reused
         if (g + 1 < n_groups) PB_TRY(pb_variant_stream_stage_host(e, h_reads, h_regions, gb[g + 1], gb[g + 2], h_ref, (int32_t) gb[g + 1]));
-        PB_TRY(pb_variant_stream_sync(e));
     }
     PB_TRY(pb_variant_stream_end(e, net, n_out));
     return pb_variant_stream_fetch(e, *n_out, h_images, h_positions, h_depths, h_freqs, h_keys, h_region_of, h_probs, stream_);

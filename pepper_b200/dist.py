@@ -48,6 +48,18 @@ def plan_groups(n_regions: int, group: int = 32) -> list[tuple[int, int]]:
     return [(g, min(n_regions, g + group)) for g in range(0, n_regions, group)]
 
 
+def plan_groups_tapered(n_regions: int, group: int, world: int, min_group: int = 4) -> list[tuple[int, int]]:
+    """Guided self-scheduling for the dynamic schedule: full `group`-sized groups, then shrinking ones (remaining / (2 world), at
+    least `min_group`) so that the tail imbalance between ranks is a few regions, not one full group."""
+    out, g = [], 0
+    while g < n_regions:
+        rem = n_regions - g
+        size = max(min_group, min(group, -(-rem // (2 * max(1, world)))))
+        out.append((g, min(n_regions, g + size)))
+        g += size
+    return out
+
+
 def group_work(seq_off: np.ndarray, table: np.ndarray, groups: list[tuple[int, int]]) -> np.ndarray:
     """Aligned bases per group (the balance criterion of SURVEY 8e) from the reads' sequence offsets."""
     return np.array([int(seq_off[int(table[g1 - 1, 7])] - seq_off[int(table[g0, 6])]) for g0, g1 in groups], dtype=np.int64)
@@ -288,12 +300,17 @@ class DistributedVariantCaller:
         import torch
         from .abi import HostReads, regions_array
         from .pipeline import DeviceReads
-        groups = plan_groups(regions.n_regions, self.group_regions)
-        G, n_reg = len(groups), regions.n_regions
-        work = group_work(seq_off, regions.table, groups) if seq_off is not None else None
-        if work is not None and replicas > 1:
-            work = np.tile(work, replicas)
-        n_job = G * replicas
+        n_reg = regions.n_regions
+        plain = plan_groups(n_reg, self.group_regions)
+        dynamic = self.schedule == "dynamic" and self.world > 1
+        last = plan_groups_tapered(n_reg, self.group_regions, self.world) if dynamic else plain
+        # the job: `replicas` copies of the region list; only the last copy is cut into shrinking groups
+        job = [(rep, g0, g1) for rep in range(replicas - 1) for (g0, g1) in plain] + [(replicas - 1, g0, g1) for (g0, g1) in last]
+        work = None
+        if seq_off is not None:
+            w_plain, w_last = group_work(seq_off, regions.table, plain), group_work(seq_off, regions.table, last)
+            work = np.concatenate([np.tile(w_plain, replicas - 1), w_last])
+        n_job = len(job)
         if self.buffer is None or self.buffer.max_groups < n_job:
             self.buffer = GatherBuffer(self._capacity, self.world, self.rank, self.device, max_groups=n_job)
         self._calls += 1
@@ -301,16 +318,16 @@ class DistributedVariantCaller:
         s = self.caller.stream(params, self.buffer.capacity, d_records=self.buffer.my_ptr())
         if isinstance(source, DeviceReads):
             def stage(j):
-                g0, g1 = groups[j % G]
-                s.stage_device(source, g0, g1, (j // G) * n_reg + g0)
+                rep, g0, g1 = job[j]
+                s.stage_device(source, g0, g1, rep * n_reg + g0)
         else:
             assert isinstance(source, HostReads)
             regs, keep = regions_array(regions)
             ref = np.ascontiguousarray(regions.ref, dtype=np.uint8)
 
             def stage(j):
-                g0, g1 = groups[j % G]
-                s.stage_host(source, regs, g0, g1, ref, (j // G) * n_reg + g0)
+                rep, g0, g1 = job[j]
+                s.stage_host(source, regs, g0, g1, ref, rep * n_reg + g0)
         cur = claimer.next()
         if cur is not None:
             stage(cur)
@@ -328,8 +345,7 @@ class DistributedVariantCaller:
             seen = tot
             if nxt is not None:
                 stage(nxt)
-            s.sync()
-            cur = nxt
+            cur = nxt                         # no sync: the next run() prepares its tables while this group's network runs
         n = s.end()
         self.groups_done = len(segments)
         t = self.caller.timings()

@@ -206,8 +206,9 @@ class VariantFromFiles(_FromFiles):
             t2 = time.perf_counter()
             got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
                                          max_reads=max_reads, downsample_rate=downsample_rate, stream=self._side.cuda_stream)
+            fetched = FetchedReads(got, regions, self.device, stream=self._side)
             prof["ref_table"] += t2 - t1; prof["get_reads"] += time.perf_counter() - t2
-            return got, regions
+            return fetched
         while True:
             s = self.caller.stream(params, cap)
             try:
@@ -221,9 +222,8 @@ class VariantFromFiles(_FromFiles):
                     nxt = trim(view, groups[0])
                     done = 0
                     for k, g in enumerate(groups):
-                        got, regions = nxt
+                        fetched = nxt
                         t3 = time.perf_counter()
-                        fetched = FetchedReads(got, regions, self.device)
                         s.stage_device(fetched, 0, len(g), done)
                         t4 = time.perf_counter()
                         s.run(flush=False)                 # encoder done (host-synchronous), network of this batch queued
@@ -235,9 +235,9 @@ class VariantFromFiles(_FromFiles):
                             if k + 2 < len(groups):
                                 fut = pool.submit(timed_prefetch, k + 2)
                             nxt = trim(view, groups[k + 1])
-                        t7 = time.perf_counter()
-                        s.sync()
-                        prof["stage"] += t4 - t3; prof["run"] += t5 - t4; prof["sync"] += time.perf_counter() - t7
+                        # no sync: run(k+1) builds its tables while network(k) runs; its encoder synchronises the stream before the
+                        # trimmer's buffers (consumed by encoder(k+1)) are overwritten by the trim of batch k+2
+                        prof["stage"] += t4 - t3; prof["run"] += t5 - t4
                         done += len(g)
                 t0 = time.perf_counter()
                 n = s.end()

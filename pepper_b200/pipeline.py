@@ -336,7 +336,10 @@ class FetchedReads:
     VariantCaller.call_device / PolishCaller.call_device take in place of DeviceReads.  read_begin / read_end of the
     table come from the trimmer."""
 
-    def __init__(self, trimmed, regions: RegionTable, device: int = 0):
+    def __init__(self, trimmed, regions: RegionTable, device: int = 0, stream=None):
+        """`stream`: optional torch.cuda.Stream for the two small uploads (region table, reference strings), so that they do not
+        queue behind kernels running on the default stream."""
+        import contextlib
         import torch
         dev = torch.device("cuda", device)
         assert trimmed.read_begin.shape[0] == regions.n_regions
@@ -347,7 +350,10 @@ class FetchedReads:
         self._trimmed = trimmed
         self.struct = trimmed.struct
         self.h_regions = (PbRegion * tab.shape[0]).from_buffer(tab)
-        self._keep = [torch.from_numpy(tab).to(dev), torch.from_numpy(np.ascontiguousarray(regions.ref, dtype=np.uint8)).to(dev)]
+        with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+            self._keep = [torch.from_numpy(tab).to(dev), torch.from_numpy(np.ascontiguousarray(regions.ref, dtype=np.uint8)).to(dev)]
+            if stream is not None:
+                stream.synchronize()
         self.d_regions = self._keep[0].data_ptr()
         self.d_ref = self._keep[1].data_ptr()
         self.ref_bytes = int(self._keep[1].numel())

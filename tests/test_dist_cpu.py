@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from pepper_b200.abi import PRED_RECORD
-from pepper_b200.dist import shard_regions, plan_groups, group_work, GroupClaimer, GatherBuffer, order_records, records_from_calls
+from pepper_b200.dist import shard_regions, plan_groups, plan_groups_tapered, group_work, GroupClaimer, GatherBuffer, order_records, records_from_calls
 
 
 def test_shard_regions_contiguous_and_balanced():
@@ -28,6 +28,11 @@ def test_plan_groups_and_work():
     g = plan_groups(70, 32)
     assert g == [(0, 32), (32, 64), (64, 70)]
     assert plan_groups(0, 32) == []
+    t = plan_groups_tapered(645, 32, 8)
+    assert t[0] == (0, 32) and t[-1][1] == 645 and all(a[1] == b[0] for a, b in zip(t, t[1:]))
+    sizes = [b - a for a, b in t]
+    assert sizes == sorted(sizes, reverse=True) and sizes[-1] <= 8 and max(sizes) == 32        # shrinking tail
+    assert plan_groups_tapered(10, 32, 2) == [(0, 4), (4, 8), (8, 10)]
     # 70 regions with 3 reads each, read i has i+1 bases
     table = np.zeros((70, 8), np.int64)
     table[:, 6] = np.arange(70) * 3

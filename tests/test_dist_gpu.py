@@ -125,4 +125,6 @@ def test_two_rank_gather_equals_one_rank():
             n_tot += n
             g_tot += phases["groups"]
             assert (phases["network_ms"] > 0) == (n > 0)           # under the dynamic schedule a rank may end up with no group at all
-        assert n_tot == want.shape[0] and g_tot == 15                # 72 regions in groups of 5, each group run exactly once
+        from pepper_b200.dist import plan_groups, plan_groups_tapered
+        n_groups = len(plan_groups_tapered(72, 5, world)) if key[0] == "dynamic" else len(plan_groups(72, 5))
+        assert n_tot == want.shape[0] and g_tot == n_groups           # every group of the plan run exactly once
