@@ -937,12 +937,21 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
         for (int64_t i = h_regions[r].read_begin; i < h_regions[r].read_end; i++) read_region[i] = (int32_t) r;
 
     // total ops: last cigar_off (device) -> fetch
-    int64_t n_ops = 0;
-    if (n_reads > 0) PB_CUDA(cudaMemcpyAsync(&n_ops, dr->cigar_off + n_reads, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    // ops of THIS batch: cigar_off may carry absolute offsets into a larger array (region groups of a streaming session view a
+    // resident workload through shifted base pointers), so the per-op prefix arrays are sized by last - first and addressed through
+    // a base pointer shifted back by `first` — not by the absolute end, which grew (and re-allocated) with every group
+    int64_t op_first = 0, op_last = 0;
+    if (n_reads > 0) {
+        PB_CUDA(cudaMemcpyAsync(&op_first, dr->cigar_off, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(&op_last, dr->cigar_off + n_reads, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
     PB_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_ops = op_last - op_first;
+    if (n_ops < 0) { set_error("cigar offsets are not ascending"); return PB_ERR_ARG; }
 
     PB_TRY(e->op_ref.reserve(sizeof(int32_t) * (n_ops + 1)));
     PB_TRY(e->op_rd.reserve(sizeof(int32_t) * (n_ops + 1)));
+    int32_t *const op_ref_base = e->op_ref.as<int32_t>() - op_first, *const op_rd_base = e->op_rd.as<int32_t>() - op_first;
     PB_TRY(e->read_reflen.reserve(sizeof(int32_t) * (n_reads + 1)));
     PB_TRY(e->read_region.reserve(sizeof(int32_t) * (n_reads + 1)));
     PB_TRY(e->tile_region.reserve(sizeof(int32_t) * n_tiles));
@@ -973,7 +982,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
     PB_CUDA(cudaEventRecord(e->evt[0], st));
     if (n_reads > 0) {
         const int wpb = 8;
-        k_cigar_prefix<<<(unsigned) ceil_div(n_reads, wpb), wpb * 32, 0, st>>>(R, e->op_ref.as<int32_t>(), e->op_rd.as<int32_t>(),
+        k_cigar_prefix<<<(unsigned) ceil_div(n_reads, wpb), wpb * 32, 0, st>>>(R, op_ref_base, op_rd_base,
                                                                               e->read_reflen.as<int32_t>());
         e->launches++;
     }
@@ -981,7 +990,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
 
     TileArgs TA;
     TA.R = R; TA.regions = d_regions; TA.ref = d_ref;
-    TA.op_ref = e->op_ref.as<int32_t>(); TA.op_rd = e->op_rd.as<int32_t>(); TA.read_reflen = e->read_reflen.as<int32_t>();
+    TA.op_ref = op_ref_base; TA.op_rd = op_rd_base; TA.read_reflen = e->read_reflen.as<int32_t>();
     TA.tile_region = e->tile_region.as<int32_t>(); TA.tile_x0 = e->tile_x0.as<int32_t>();
     TA.region_goff = e->region_goff.as<int64_t>();
     TA.M16 = e->M16.as<int16_t>(); TA.cov = e->cov.as<int32_t>(); TA.meta = e->meta.as<uint32_t>();
