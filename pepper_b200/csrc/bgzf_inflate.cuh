@@ -13,7 +13,6 @@
 //   k_rec_scatter    warp per kept record: 4-bit sequence (re-packed when the output nibble offset is odd), qualities, CIGAR.
 #pragma once
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace pb {
 namespace bgzf {
@@ -75,30 +74,18 @@ struct BitReader {
     }
 };
 
-// A BGZF block is decoded by a GROUP of G consecutive lanes (G = 8: four blocks per warp).  The group's first lane ("leader")
-// owns the bit reader; the group builds tables and performs LZ77 copies together; all synchronisation is group-scoped
-// (__shfl_sync / __syncwarp with the group's lane mask).  The groups of a warp run the SAME one-symbol-per-iteration loop, so
-// the instructions of the (leader-only) symbol decode are issued once for all four leaders — the kernel is instruction-issue
-// bound with a single active lane per warp (ncu: 52 warp instructions per output byte at G = 32).
-struct Grp {
-    unsigned mask;      // lanes of this group
-    int lead;           // lane index of the leader inside the warp
-    int sub;            // this lane's index inside the group
-    int G;
-};
-
 // Builds the primary table + the canonical (count, sorted symbols) arrays for `n` symbols with code lengths lens[0..n).
-// Whole group; returns false when the lengths over-subscribe the code space.
-__device__ bool build_table(const uint8_t *lens, int n, uint16_t *tab, int tab_bits, uint16_t *cnt, uint16_t *sorted, uint16_t *code, const Grp &g) {
-    for (int i = g.sub; i < 16; i += g.G) cnt[i] = 0;
-    for (int i = g.sub; i < (1 << tab_bits); i += g.G) tab[i] = 0;
-    __syncwarp(g.mask);
-    int ok = 1;
-    if (g.sub == 0) {
+// Whole warp; returns false when the lengths over-subscribe the code space.
+__device__ bool build_table(const uint8_t *lens, int n, uint16_t *tab, int tab_bits, uint16_t *cnt, uint16_t *sorted, uint16_t *code, int lane) {
+    if (lane < 16) cnt[lane] = 0;
+    for (int i = lane; i < (1 << tab_bits); i += 32) tab[i] = 0;
+    __syncwarp();
+    bool ok = true;
+    if (lane == 0) {
         for (int s = 0; s < n; s++) cnt[lens[s]]++;
         cnt[0] = 0;
         int left = 1;
-        for (int l = 1; l <= 15; l++) { left = (left << 1) - cnt[l]; if (left < 0) ok = 0; }
+        for (int l = 1; l <= 15; l++) { left = (left << 1) - cnt[l]; if (left < 0) ok = false; }
         // canonical codes + symbols sorted by (length, symbol)
         uint16_t next[16], offs[16];
         uint32_t c = 0;
@@ -109,10 +96,10 @@ __device__ bool build_table(const uint8_t *lens, int n, uint16_t *tab, int tab_b
             if (l) { code[s] = next[l]++; sorted[offs[l]++] = (uint16_t) s; }
         }
     }
-    ok = __shfl_sync(g.mask, ok, g.lead);
-    __syncwarp(g.mask);
+    ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+    __syncwarp();
     if (!ok) return false;
-    for (int s = g.sub; s < n; s += g.G) {
+    for (int s = lane; s < n; s += 32) {
         const int l = lens[s];
         if (l && l <= tab_bits) {
             const uint32_t rev = __brev((uint32_t) code[s]) >> (32 - l);       // DEFLATE packs Huffman codes MSB first
@@ -120,11 +107,11 @@ __device__ bool build_table(const uint8_t *lens, int n, uint16_t *tab, int tab_b
             for (uint32_t i = rev; i < (1u << tab_bits); i += 1u << l) tab[i] = e;
         }
     }
-    __syncwarp(g.mask);
+    __syncwarp();
     return true;
 }
 
-// leader only: one symbol
+// lane 0 only: one symbol
 __device__ __forceinline__ int decode_sym(BitReader &br, const uint16_t *tab, int tab_bits, const uint16_t *cnt, const uint16_t *sorted) {
     br.refill();
     const uint16_t e = tab[br.peek(tab_bits)];
@@ -143,69 +130,61 @@ __device__ __forceinline__ int decode_sym(BitReader &br, const uint16_t *tab, in
 
 // status: 0 ok, 1 bad block type / stored header, 2 bad code lengths, 3 bad symbol, 4 output overrun, 5 distance too far,
 //         6 size mismatch, 7 input overrun
-template <int G>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8_t *__restrict__ comp, const BlockDesc *__restrict__ blocks, int n_blocks,
                                                                      uint8_t *out, int *__restrict__ status) {
-    constexpr int NG = 32 / G;                                   // blocks per warp
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    WarpTables *T_all = reinterpret_cast<WarpTables *>(smem_raw);   // [WARPS_PER_CTA][NG]
+    __shared__ WarpTables T_all[WARPS_PER_CTA];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Grp g;
-    g.G = G; g.sub = lane % G; g.lead = lane - g.sub;
-    g.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << g.lead);
-    const int64_t b = ((int64_t) blockIdx.x * WARPS_PER_CTA + wid) * NG + lane / G;
+    const int64_t b = (int64_t) blockIdx.x * WARPS_PER_CTA + wid;
     if (b >= n_blocks) return;
-    WarpTables &T = T_all[wid * NG + lane / G];
+    WarpTables &T = T_all[wid];
     const BlockDesc D = blocks[b];
     uint8_t *dst = out + D.out_off;
     BitReader br;
     br.init(comp + D.in_off, D.in_len);
-    const bool leader = g.sub == 0;
     int pos = 0, err = 0;
     int last = 0;
     while (!last && !err) {
         int type = 0;
-        if (leader) { last = (int) br.get(1); type = (int) br.get(2); }
-        last = __shfl_sync(g.mask, last, g.lead); type = __shfl_sync(g.mask, type, g.lead);
+        if (lane == 0) { last = (int) br.get(1); type = (int) br.get(2); }
+        last = __shfl_sync(0xffffffffu, last, 0); type = __shfl_sync(0xffffffffu, type, 0);
         if (type == 0) {
             // stored: skip to the byte boundary, LEN / NLEN, raw bytes
             int len = 0;
             int64_t src = 0;
-            if (leader) {
+            if (lane == 0) {
                 br.skip(br.cnt & 7);
                 const uint32_t l = br.get(16), nl = br.get(16);
                 if ((l ^ 0xffffu) != nl) err = 1;
                 len = (int) l;
                 src = br.consumed();                                  // byte position of the next unread input byte
             }
-            err = __shfl_sync(g.mask, err, g.lead); len = __shfl_sync(g.mask, len, g.lead); src = __shfl_sync(g.mask, src, g.lead);
-            pos = __shfl_sync(g.mask, pos, g.lead);
+            err = __shfl_sync(0xffffffffu, err, 0); len = __shfl_sync(0xffffffffu, len, 0); src = __shfl_sync(0xffffffffu, src, 0);
             if (!err && (pos + len > D.out_len || src + len > D.in_len)) err = 4;
             if (err) break;
-            for (int i = g.sub; i < len; i += G) dst[pos + i] = br.p[src + i];
+            for (int i = lane; i < len; i += 32) dst[pos + i] = br.p[src + i];
             pos += len;
-            if (leader) br.seek(src + len);
-            __syncwarp(g.mask);
+            if (lane == 0) br.seek(src + len);
+            __syncwarp();
             continue;
         }
         if (type == 3) { err = 1; break; }
         int hlit = 288, hdist = 30;
         if (type == 1) {
-            for (int s = g.sub; s < 288; s += G) T.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
-            for (int s = g.sub; s < 30; s += G) T.lens[288 + s] = 5;
-            __syncwarp(g.mask);
+            for (int s = lane; s < 288; s += 32) T.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+            if (lane < 30) T.lens[288 + lane] = 5;
+            __syncwarp();
         } else {
             // dynamic: HLIT, HDIST, HCLEN, the code-length code, then the literal/length + distance code lengths
             int hclen = 0;
-            if (leader) { hlit = (int) br.get(5) + 257; hdist = (int) br.get(5) + 1; hclen = (int) br.get(4) + 4; }
-            hlit = __shfl_sync(g.mask, hlit, g.lead); hdist = __shfl_sync(g.mask, hdist, g.lead);
+            if (lane == 0) { hlit = (int) br.get(5) + 257; hdist = (int) br.get(5) + 1; hclen = (int) br.get(4) + 4; }
+            hlit = __shfl_sync(0xffffffffu, hlit, 0); hdist = __shfl_sync(0xffffffffu, hdist, 0);
             if (hlit > 286 || hdist > 30) { err = 2; break; }
-            for (int s = g.sub; s < 19; s += G) T.lens[s] = 0;
-            __syncwarp(g.mask);
-            if (leader) for (int i = 0; i < hclen; i++) T.lens[c_clen_order[i]] = (uint8_t) br.get(3);
-            __syncwarp(g.mask);
-            if (!build_table(T.lens, 19, T.dist, 7, T.dist_cnt, T.dist_sym, T.code, g)) { err = 2; break; }
-            if (leader) {
+            if (lane < 19) T.lens[lane] = 0;
+            __syncwarp();
+            if (lane == 0) for (int i = 0; i < hclen; i++) T.lens[c_clen_order[i]] = (uint8_t) br.get(3);
+            __syncwarp();
+            if (!build_table(T.lens, 19, T.dist, 7, T.dist_cnt, T.dist_sym, T.code, lane)) { err = 2; break; }
+            if (lane == 0) {
                 uint8_t tmp[320];
                 int i = 0;
                 const int total = hlit + hdist;
@@ -228,43 +207,41 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8
                     if (T.lens[256] == 0) err = 2;                      // no end-of-block code
                 }
             }
-            err = __shfl_sync(g.mask, err, g.lead);
+            err = __shfl_sync(0xffffffffu, err, 0);
             if (err) break;
-            __syncwarp(g.mask);
+            __syncwarp();
         }
-        if (!build_table(T.lens, 288, T.lit, LIT_BITS, T.lit_cnt, T.lit_sym, T.code, g)) { err = 2; break; }
+        if (!build_table(T.lens, 288, T.lit, LIT_BITS, T.lit_cnt, T.lit_sym, T.code, lane)) { err = 2; break; }
         // an incomplete distance code is legal when only one distance code is used (zlib emits it): do not reject under-subscription
-        if (!build_table(T.lens + 288, 30, T.dist, DIST_BITS, T.dist_cnt, T.dist_sym, T.code, g)) { err = 2; break; }
-        // ---- ONE symbol per iteration and group: the leader decodes it; a literal is stored by the leader, a match is copied by the
-        //      group.  Packed broadcast: bits 0-15 distance (1..32768), 16-24 length, 27 literal, 28-30 error, 31 end of block.
+        if (!build_table(T.lens + 288, 30, T.dist, DIST_BITS, T.dist_cnt, T.dist_sym, T.code, lane)) { err = 2; break; }
+        // ---- symbols: lane 0 decodes (writing literals itself) up to the next match / end of block, the warp performs the copy.
+        //      One packed broadcast per match: bits 0-15 distance (1..32768), 16-24 length, 28-30 error, bit 31 end of block.
         for (;;) {
             uint32_t msg = 0;
-            if (leader) {
-                const int s = decode_sym(br, T.lit, LIT_BITS, T.lit_cnt, T.lit_sym);              // refills: > 32 bits before, >= 18 after
-                if (s < 256) {
-                    if (s < 0) err = 3;
-                    else if (pos >= D.out_len) err = 4;
-                    else { dst[pos++] = (uint8_t) s; msg = 1u << 27; }
-                } else if (s == 256) {
-                    msg = 0x80000000u;
-                } else if (s > 285) {
-                    err = 3;
-                } else {
+            if (lane == 0) {
+                for (;;) {
+                    const int s = decode_sym(br, T.lit, LIT_BITS, T.lit_cnt, T.lit_sym);          // refills: > 32 bits before, >= 18 after
+                    if (s < 256) {
+                        if (s < 0) { err = 3; break; }
+                        if (pos >= D.out_len) { err = 4; break; }
+                        dst[pos++] = (uint8_t) s;
+                        continue;
+                    }
+                    if (s == 256) { msg = 0x80000000u; break; }
+                    if (s > 285) { err = 3; break; }
                     const int li = s - 257;
                     const int mlen = c_len_base[li] + (int) br.get_nofill(c_len_extra[li]);       // <= 5 extra bits: still in the buffer
                     const int ds = decode_sym(br, T.dist, DIST_BITS, T.dist_cnt, T.dist_sym);      // refills again: > 32 bits before
-                    if (ds < 0 || ds > 29) err = 3;
-                    else {
-                        const int mdist = c_dist_base[ds] + (int) br.get_nofill(c_dist_extra[ds]);    // 15 + 13 bits <= 32
-                        msg = (uint32_t) (mdist & 0xffff) | ((uint32_t) mlen << 16);
-                    }
+                    if (ds < 0 || ds > 29) { err = 3; break; }
+                    const int mdist = c_dist_base[ds] + (int) br.get_nofill(c_dist_extra[ds]);    // 15 + 13 bits <= 32
+                    msg = (uint32_t) (mdist & 0xffff) | ((uint32_t) mlen << 16);
+                    break;
                 }
                 if (br.overrun()) err = 7;
                 msg |= (uint32_t) err << 28;
             }
-            msg = __shfl_sync(g.mask, msg, g.lead);
-            if ((msg >> 27) == 1u) continue;                            // a literal (no error, not end of block): nothing for the group to do
-            pos = __shfl_sync(g.mask, pos, g.lead);
+            msg = __shfl_sync(0xffffffffu, msg, 0);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
             err = (int) ((msg >> 28) & 7u);
             if (err) break;
             if (msg >> 31) break;                                       // end of this deflate block
@@ -272,43 +249,18 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8
             const int mdist = (msg & 0xffffu) ? (int) (msg & 0xffffu) : 65536;     // 32768 fits; 0 cannot occur (bases start at 1)
             if (mdist > pos) { err = 5; break; }
             if (pos + mlen > D.out_len) { err = 4; break; }
-            __syncwarp(g.mask);                                         // earlier stores of this group (literals, previous copy) are visible
+            __syncwarp();                                               // earlier stores of this warp (literals, previous copy) are visible
             const uint8_t *src = dst + pos - mdist;
             if (mdist >= mlen) {
-                for (int i = g.sub; i < mlen; i += G) dst[pos + i] = src[i];
+                for (int i = lane; i < mlen; i += 32) dst[pos + i] = src[i];
             } else {
-                for (int i = g.sub; i < mlen; i += G) dst[pos + i] = src[i % mdist];
+                for (int i = lane; i < mlen; i += 32) dst[pos + i] = src[i % mdist];
             }
             pos += mlen;
         }
     }
-    pos = __shfl_sync(g.mask, pos, g.lead);
     if (!err && pos != D.out_len) err = 6;
-    if (leader) status[b] = err;
-}
-
-constexpr int INFLATE_GROUP = 8;                                  // lanes per BGZF block (4 blocks per warp)
-static inline size_t inflate_smem_bytes(int G) { return sizeof(WarpTables) * WARPS_PER_CTA * (32 / G); }
-
-// launch helper: blocks are spread over warps NG at a time
-static inline int launch_inflate(const uint8_t *comp, const BlockDesc *blocks, int64_t n_blocks, uint8_t *out, int *status, cudaStream_t st) {
-    static const int G = []() { const char *e = getenv("PB_INFLATE_GROUP"); const int v = e ? atoi(e) : INFLATE_GROUP; return (v == 32 || v == 16 || v == 8 || v == 4) ? v : INFLATE_GROUP; }();
-    const int per_cta = WARPS_PER_CTA * (32 / G);
-    const unsigned grid = (unsigned) ceil_div(n_blocks, per_cta);
-    const size_t smem = inflate_smem_bytes(G);
-#define PB_INFLATE_LAUNCH(GG)                                                                                                    \
-    do {                                                                                                                         \
-        static bool attr = false;                                                                                                \
-        if (!attr) { PB_CUDA(cudaFuncSetAttribute(k_bgzf_inflate<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr = true; } \
-        k_bgzf_inflate<GG><<<grid, 32 * WARPS_PER_CTA, smem, st>>>(comp, blocks, (int) n_blocks, out, status);                   \
-    } while (0)
-    if (G == 32) PB_INFLATE_LAUNCH(32);
-    else if (G == 16) PB_INFLATE_LAUNCH(16);
-    else if (G == 4) PB_INFLATE_LAUNCH(4);
-    else PB_INFLATE_LAUNCH(8);
-#undef PB_INFLATE_LAUNCH
-    PB_CUDA(cudaGetLastError());
-    return PB_OK;
+    if (lane == 0) status[b] = err;
 }
 
 // ------------------------------------------------------------------------------------------------------ record chains
