@@ -749,9 +749,7 @@ extern "C" int pb_bam_fetch_device(pb_bam_t *b, int tid, int64_t beg, int64_t en
     PB_CUDA(cudaMemsetAsync(b->d_scal.p, 0, sizeof(int64_t) * 8, st));
     int64_t *sc = b->d_scal.as<int64_t>();                      // [0] n_rec [1] n_keep [2] n_bases [3] n_cigar [4] err (int)
     int *d_err = reinterpret_cast<int *>(sc + 4);
-    k_bgzf_inflate<<<(unsigned) ceil_div(n_blocks, WARPS_PER_CTA), 32 * WARPS_PER_CTA, 0, st>>>(b->d_comp.as<uint8_t>(), b->d_blocks.as<BlockDesc>(), (int) n_blocks,
-                                                                                                 b->d_ubuf.as<uint8_t>(), b->d_status.as<int>());
-    PB_CUDA(cudaGetLastError());
+    PB_TRY(launch_inflate(b->d_comp.as<uint8_t>(), b->d_blocks.as<BlockDesc>(), n_blocks, b->d_ubuf.as<uint8_t>(), b->d_status.as<int>(), st));
     PB_CUDA(cudaEventRecord(b->dev_evt[1], st));
     // ---- record chains
     int64_t n_rec = 0;
@@ -849,9 +847,7 @@ extern "C" int pb_inflate_blocks_host(const uint8_t *h_comp, int64_t comp_bytes,
         if ((rc = upload(db, desc.data(), sizeof(BlockDesc) * n_blocks, st)) != PB_OK) break;
         if ((rc = ds.reserve(sizeof(int) * (n_blocks + 1))) != PB_OK) break;
         if ((rc = du.reserve((size_t) utotal + 64)) != PB_OK) break;
-        if (n_blocks) k_bgzf_inflate<<<(unsigned) ceil_div(n_blocks, WARPS_PER_CTA), 32 * WARPS_PER_CTA, 0, st>>>(dc.as<uint8_t>(), db.as<BlockDesc>(), (int) n_blocks,
-                                                                                                                  du.as<uint8_t>(), ds.as<int>());
-        if (cudaGetLastError() != cudaSuccess) { set_error("k_bgzf_inflate launch failed"); rc = PB_ERR_CUDA; break; }
+        if (n_blocks && (rc = launch_inflate(dc.as<uint8_t>(), db.as<BlockDesc>(), n_blocks, du.as<uint8_t>(), ds.as<int>(), st)) != PB_OK) break;
         cudaMemcpyAsync(h_status, ds.p, sizeof(int) * n_blocks, cudaMemcpyDeviceToHost, st);
         if (utotal) cudaMemcpyAsync(h_out, du.p, (size_t) utotal, cudaMemcpyDeviceToHost, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("inflate kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = PB_ERR_CUDA; }

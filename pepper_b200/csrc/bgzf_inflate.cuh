@@ -13,6 +13,7 @@
 //   k_rec_scatter    warp per kept record: 4-bit sequence (re-packed when the output nibble offset is odd), qualities, CIGAR.
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace pb {
 namespace bgzf {
@@ -64,6 +65,8 @@ struct BitReader {
     __device__ __forceinline__ uint32_t get_nofill(int n) { const uint32_t v = peek(n); skip(n); return v; }     // caller guarantees n <= cnt
     __device__ __forceinline__ int64_t consumed() const { return loaded - (cnt >> 3); }                           // whole bytes consumed
     __device__ __forceinline__ bool overrun() const { return consumed() > end; }
+    __device__ __forceinline__ int64_t bitpos() const { return loaded * 8 - cnt; }                                // bits consumed so far
+    __device__ __forceinline__ void seek_bits(int64_t bit_pos) { seek(bit_pos >> 3); skip((int) (bit_pos & 7)); }
     __device__ __forceinline__ void seek(int64_t byte_pos) {                                                     // restart at a byte position
         const uint8_t *q = p + byte_pos;
         const int mis = (int) ((uintptr_t) q & 3);
@@ -128,11 +131,137 @@ __device__ __forceinline__ int decode_sym(BitReader &br, const uint16_t *tab, in
     return -1;
 }
 
+// ---------------------------------------------------------------------------------------------- warp-parallel symbol decode
+// The symbol stream of a deflate block is serial (every code length decides where the next code starts), which leaves 31 lanes
+// idle in the classic one-decoder-per-warp scheme and makes the kernel instruction-issue bound.  Here all 32 lanes decode
+// SPECULATIVELY: lane i decodes the complete symbol (literal, or length + extra + distance + extra) that would start at bit
+// bp + i; the true symbol starts are then found by a short walk over the per-lane bit counts (p = 0; p += nbits[p]) done with
+// warp shuffles; lanes on the chain own a symbol of this round, store their literal / copy their short match themselves, and
+// the rare matches that read bytes produced in the same round (or are long) are copied cooperatively in stream order.
+// Roughly 4-5 symbols per round of ~150 warp instructions instead of ~100 instructions per symbol.
+enum { K_LIT = 0, K_MATCH = 1, K_EOB = 2, K_BAD = 3, K_SLOW = 4 };
+
+struct SpecTabs { uint16_t len_base[32]; uint16_t dist_base[32]; uint8_t len_extra[32]; uint8_t dist_extra[32]; };
+
+// 64 bits of the payload starting at absolute bit `bit` (aligned 32-bit loads; may read a few bytes past the payload)
+__device__ __forceinline__ uint64_t load_window(const uint8_t *p, int64_t bit) {
+    const uint64_t a = (uint64_t) (uintptr_t) p * 8ull + (uint64_t) bit;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>((uintptr_t) ((a >> 5) << 2));
+    const uint32_t sh = (uint32_t) (a & 31);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    return (uint64_t) lo | ((uint64_t) hi << 32);
+}
+
+// canonical (first-code) decode of one code from the low bits of `b`; returns the symbol, length in `len` (-1: invalid)
+__device__ __forceinline__ int canon_decode(uint64_t b, const uint16_t *cnt, const uint16_t *sorted, int &len) {
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l <= 15; l++) {
+        code |= (int) (b & 1); b >>= 1;
+        const int c = cnt[l];
+        if (code - c < first) { len = l; return sorted[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    len = 1;
+    return -1;
+}
+
+// one complete symbol from the window; `exact`: codes longer than the lookup tables are resolved (canonical walk), else K_SLOW
+__device__ __forceinline__ void decode_full(uint64_t wnd, const WarpTables &T, const SpecTabs &X, bool exact, int &kind, int &nbits, int &olen, int &val, int &dist) {
+    kind = K_BAD; nbits = 1; olen = 0; val = 0; dist = 0;
+    int l1, sym;
+    const uint16_t e = T.lit[(uint32_t) wnd & ((1u << LIT_BITS) - 1u)];
+    if (e) { l1 = e & 15; sym = e >> 4; }
+    else if (!exact) { kind = K_SLOW; return; }
+    else { sym = canon_decode(wnd, T.lit_cnt, T.lit_sym, l1); if (sym < 0) return; }
+    if (sym < 256) { kind = K_LIT; nbits = l1; olen = 1; val = sym; return; }
+    if (sym == 256) { kind = K_EOB; nbits = l1; return; }
+    if (sym > 285) return;
+    const int li = sym - 257;
+    const int xb = X.len_extra[li];
+    const int mlen = X.len_base[li] + (int) ((uint32_t) (wnd >> l1) & ((1u << xb) - 1u));
+    const int t = l1 + xb;                                                    // <= 20
+    int l2, ds;
+    const uint16_t e2 = T.dist[(uint32_t) (wnd >> t) & ((1u << DIST_BITS) - 1u)];
+    if (e2) { l2 = e2 & 15; ds = e2 >> 4; }
+    else if (!exact) { kind = K_SLOW; return; }
+    else { ds = canon_decode(wnd >> t, T.dist_cnt, T.dist_sym, l2); if (ds < 0) return; }
+    if (ds > 29) return;
+    const int xd = X.dist_extra[ds];
+    dist = X.dist_base[ds] + (int) ((uint32_t) (wnd >> (t + l2)) & ((1u << xd) - 1u));
+    kind = K_MATCH; nbits = t + l2 + xd; olen = mlen; val = mlen;               // <= 48 bits
+}
+
+// decodes symbols from bit position `bp` until the end-of-block code; all 32 lanes.  Returns the error code (0 ok).
+__device__ int spec_symbols(const uint8_t *payload, int64_t in_bits, int64_t &bp, uint8_t *dst, int out_len, int &pos, const WarpTables &T, const SpecTabs &X,
+                            int lane) {
+    for (;;) {
+        const uint64_t wnd = load_window(payload, bp + lane);
+        int kind, nbits, olen, val, dist;
+        decode_full(wnd, T, X, false, kind, nbits, olen, val, dist);
+        // ---- the chain of true symbol starts inside [0, 32): uniform walk
+        int p = 0, off = 0, myoff = -1, err = 0;
+        bool eob = false;
+        while (p < 32) {
+            int k = __shfl_sync(0xffffffffu, kind, p);
+            if (k == K_SLOW) {                                                  // a code longer than the lookup table at a TRUE start: rare
+                const uint32_t wl = __shfl_sync(0xffffffffu, (uint32_t) wnd, p), wh = __shfl_sync(0xffffffffu, (uint32_t) (wnd >> 32), p);
+                int k2, n2, o2, v2, d2;
+                decode_full((uint64_t) wl | ((uint64_t) wh << 32), T, X, true, k2, n2, o2, v2, d2);
+                if (lane == p) { kind = k2; nbits = n2; olen = o2; val = v2; dist = d2; }
+                k = k2;
+            }
+            const int n = __shfl_sync(0xffffffffu, nbits, p), o = __shfl_sync(0xffffffffu, olen, p);
+            if (k == K_BAD) { err = 3; break; }
+            if (lane == p) myoff = off;
+            off += o; p += n;
+            if (k == K_EOB) { eob = true; break; }
+        }
+        if (err) return err;
+        if (pos + off > out_len) return 4;
+        if (bp + p > in_bits + 64) return 7;                                     // ran past the payload (tolerates the padded tail of the last code)
+        // ---- output: literals and short matches that read only bytes of earlier rounds are written by their own lanes
+        const bool mine = myoff >= 0;
+        bool coop = false;
+        if (mine && kind == K_LIT) dst[pos + myoff] = (uint8_t) val;
+        if (mine && kind == K_MATCH) {
+            if (dist > pos + myoff) err = 5;
+            else if (val <= 8 && dist >= myoff + val) {
+                const uint8_t *src = dst + pos + myoff - dist;
+#pragma unroll 1
+                for (int i = 0; i < val; i++) dst[pos + myoff + i] = src[i];
+            } else coop = true;
+        }
+        if (__any_sync(0xffffffffu, err != 0)) return 5;
+        unsigned cm = __ballot_sync(0xffffffffu, coop);
+        while (cm) {                                                            // in stream order (= lane order)
+            const int j = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int o = __shfl_sync(0xffffffffu, myoff, j), l = __shfl_sync(0xffffffffu, val, j), d = __shfl_sync(0xffffffffu, dist, j);
+            __syncwarp();                                                       // everything written so far in this round is visible
+            const uint8_t *src = dst + pos + o - d;
+            if (d >= l) { for (int i = lane; i < l; i += 32) dst[pos + o + i] = src[i]; }
+            else { for (int i = lane; i < l; i += 32) dst[pos + o + i] = src[i % d]; }
+        }
+        pos += off;
+        bp += p;
+        __syncwarp();                                                           // the next round may read what this one wrote
+        if (eob) return 0;
+    }
+}
+
 // status: 0 ok, 1 bad block type / stored header, 2 bad code lengths, 3 bad symbol, 4 output overrun, 5 distance too far,
 //         6 size mismatch, 7 input overrun
+template <bool SPEC>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8_t *__restrict__ comp, const BlockDesc *__restrict__ blocks, int n_blocks,
                                                                      uint8_t *out, int *__restrict__ status) {
     __shared__ WarpTables T_all[WARPS_PER_CTA];
+    __shared__ SpecTabs X;
+    if (threadIdx.x < 32) {
+        X.len_base[threadIdx.x] = threadIdx.x < 29 ? c_len_base[threadIdx.x] : 0; X.len_extra[threadIdx.x] = threadIdx.x < 29 ? c_len_extra[threadIdx.x] : 0;
+        X.dist_base[threadIdx.x] = threadIdx.x < 30 ? c_dist_base[threadIdx.x] : 0; X.dist_extra[threadIdx.x] = threadIdx.x < 30 ? c_dist_extra[threadIdx.x] : 0;
+    }
+    __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t b = (int64_t) blockIdx.x * WARPS_PER_CTA + wid;
     if (b >= n_blocks) return;
@@ -214,6 +343,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8
         if (!build_table(T.lens, 288, T.lit, LIT_BITS, T.lit_cnt, T.lit_sym, T.code, lane)) { err = 2; break; }
         // an incomplete distance code is legal when only one distance code is used (zlib emits it): do not reject under-subscription
         if (!build_table(T.lens + 288, 30, T.dist, DIST_BITS, T.dist_cnt, T.dist_sym, T.code, lane)) { err = 2; break; }
+        if (SPEC) {
+            // ---- warp-parallel speculative decode (above); lane 0's bit reader is re-synchronised at the end-of-block position
+            int64_t bp = 0;
+            if (lane == 0) bp = br.bitpos();
+            bp = __shfl_sync(0xffffffffu, bp, 0);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            err = spec_symbols(br.p, (int64_t) D.in_len * 8, bp, dst, D.out_len, pos, T, X, lane);
+            if (err) break;
+            if (lane == 0) br.seek_bits(bp);
+            continue;
+        }
         // ---- symbols: lane 0 decodes (writing literals itself) up to the next match / end of block, the warp performs the copy.
         //      One packed broadcast per match: bits 0-15 distance (1..32768), 16-24 length, 28-30 error, bit 31 end of block.
         for (;;) {
@@ -261,6 +401,16 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_bgzf_inflate(const uint8
     }
     if (!err && pos != D.out_len) err = 6;
     if (lane == 0) status[b] = err;
+}
+
+// PB_INFLATE_SPEC=0 selects the one-decoder-per-warp symbol loop (cross-check); default: the warp-parallel speculative decode
+static inline int launch_inflate(const uint8_t *comp, const BlockDesc *blocks, int64_t n_blocks, uint8_t *out, int *status, cudaStream_t st) {
+    static const bool spec = !(getenv("PB_INFLATE_SPEC") && atoi(getenv("PB_INFLATE_SPEC")) == 0);
+    const unsigned grid = (unsigned) ceil_div(n_blocks, WARPS_PER_CTA);
+    if (spec) k_bgzf_inflate<true><<<grid, 32 * WARPS_PER_CTA, 0, st>>>(comp, blocks, (int) n_blocks, out, status);
+    else k_bgzf_inflate<false><<<grid, 32 * WARPS_PER_CTA, 0, st>>>(comp, blocks, (int) n_blocks, out, status);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------ record chains
