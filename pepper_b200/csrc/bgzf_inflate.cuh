@@ -3,9 +3,10 @@
 // BAM_handler::get_reads (pepper/modules/src/dataio/bam_handler.cpp:115-135), with only the COMPRESSED bytes crossing PCIe.
 //
 //   k_bgzf_inflate   one warp per BGZF block (RFC 1951 DEFLATE: stored / fixed / dynamic Huffman blocks).  Lane 0 owns the bit
-//                    reader and decodes symbols through a 10-bit (literal/length) and an 8-bit (distance) lookup table in shared
-//                    memory, longer codes through the canonical first-code walk; tables are built by the whole warp; LZ77 copies
-//                    are done by the whole warp (overlapping copies replicate the period: src = pos - dist + i mod dist).
+//                    reader for headers; tables (10-bit literal/length, 8-bit distance, canonical first-code walk for longer
+//                    codes) are built by the whole warp.  Symbols: all 32 lanes decode a candidate symbol start speculatively and
+//                    the true chain is found with shuffles (spec_symbols); LZ77 copies that depend on the current round are done
+//                    by the whole warp (overlapping copies replicate the period: src = pos - dist + i mod dist).
 //   k_chain_*        record boundaries: BAM records are chained by their block_size field, a sequential dependency.  The BAI
 //                    linear index provides the virtual offset of a record start for every 16 kb window, so one thread per
 //                    window start hops its own short chain (count pass, scan, write pass).
