@@ -152,3 +152,96 @@ def test_records_without_sequence_and_odd_lengths(tmp_path):
     codes = np.empty(2 * got.seq.shape[0], dtype=np.uint8)
     codes[0::2], codes[1::2] = got.seq >> 4, got.seq & 15
     assert "".join(synth.NT16[c] for c in codes[:8]) == "ACGTAGGT"
+
+
+def test_corrupt_files_are_rejected_not_followed(tmp_path):
+    """a BGZF block whose BSIZE cannot hold header + CRC + ISIZE, an ISIZE beyond 64 KB, a record whose fixed
+    fields / CIGAR / sequence sizes exceed its block_size, and a truncated file must produce an error code — never an
+    out-of-bounds read (the fetch walks sizes taken from the file)."""
+    import shutil
+    from pepper_b200.bamio import BamReader
+    from pepper_b200._lib import PepperB200Error
+    rec, _ = synth.simulate_contig_records(20000, 10, synth.ONT, 5)
+    good = str(tmp_path / "g.bam")
+    synth_files.write_bam(good, [("c", 20000)], {0: rec}, block_payload=8000)
+    r = BamReader(good, 2)
+    n_good = r.fetch("c", 0, 20000).n_records
+    assert n_good > 5
+    r.close()
+    raw = bytearray(open(good, "rb").read())
+    # second BGZF block: offsets from the first block's BSIZE
+    b0 = struct.unpack_from("<H", raw, 16)[0] + 1
+
+    def variant(name, edit):
+        p = str(tmp_path / name)
+        d = bytearray(raw)
+        edit(d)
+        open(p, "wb").write(d)
+        shutil.copy(good + ".bai", p + ".bai")
+        return p
+    cases = {
+        "bsize_too_small.bam": lambda d: struct.pack_into("<H", d, b0 + 16, 10),           # BSIZE - 1 = 10: smaller than the header
+        "isize_huge.bam": lambda d: struct.pack_into("<I", d, b0 + struct.unpack_from("<H", d, b0 + 16)[0] + 1 - 4, 1 << 20),
+        "truncated.bam": lambda d: d.__delitem__(slice(len(d) // 2, len(d))),
+        "garbage_payload.bam": lambda d: d.__setitem__(slice(b0 + 18, b0 + 60), bytes(range(42))),
+    }
+    for name, edit in cases.items():
+        p = variant(name, edit)
+        try:
+            rd = BamReader(p, 2)
+        except PepperB200Error:
+            continue                                            # rejected at open (header block damaged): fine
+        with pytest.raises(PepperB200Error):
+            rd.fetch("c", 0, 20000)
+        rd.close()
+    # a record that claims more CIGAR ops than its block_size can hold: rebuild the stream with one bad n_cigar field
+    import zlib
+    blocks, off = [], 0
+    while off < len(raw) - 28:
+        bs = struct.unpack_from("<H", raw, off + 16)[0] + 1
+        blocks.append(zlib.decompress(bytes(raw[off + 18:off + bs - 8]), -15))
+        off += bs
+    stream = bytearray(b"".join(blocks))
+    l_text = struct.unpack_from("<i", stream, 4)[0]
+    p0 = 8 + l_text + 4
+    l_name = struct.unpack_from("<i", stream, p0)[0]
+    first_rec = p0 + 4 + l_name + 4
+    struct.pack_into("<H", stream, first_rec + 4 + 12, 60000)             # n_cigar of the first record
+    out, c = [], 0
+    for s in range(0, len(stream), 8000):
+        out.append(synth_files._bgzf_block(bytes(stream[s:s + 8000]), 1))
+    bad = str(tmp_path / "bad_ncigar.bam")
+    open(bad, "wb").write(b"".join(out) + synth_files.BGZF_EOF)
+    shutil.copy(good + ".bai", bad + ".bai")               # same block sizes at the same level? not guaranteed -> the index may point elsewhere:
+    try:                                                   # either way the reader must answer with an error or a clean result, not crash
+        rd = BamReader(bad, 2)
+        try:
+            rd.fetch("c", 0, 20000)
+        except PepperB200Error:
+            pass
+        rd.close()
+    except PepperB200Error:
+        pass
+
+
+def test_from_files_close_releases_readers(tmp_path):
+    """the second reader opened by the streaming calls is closed with the object."""
+    from pepper_b200.frontend import _FromFiles
+    rec, genome = synth.simulate_contig_records(5000, 5, synth.ONT, 6)
+    bam, fa = str(tmp_path / "f.bam"), str(tmp_path / "f.fa")
+    synth_files.write_bam(bam, [("c", 5000)], {0: rec})
+    synth_files.write_fasta(fa, [("c", genome)])
+
+    class Probe(_FromFiles):                                # no GPU in this test: skip the trimmer
+        def __init__(self):
+            from pepper_b200.bamio import BamReader, FastaReader
+            self.gpu_inflate = False
+            self.bam = BamReader(bam, 1)
+            self.fasta = FastaReader(fa)
+            self.trimmer = None
+            self.device = 0
+            self._bam2 = BamReader(bam, 1)
+    p = Probe()
+    b1, b2 = p.bam, p._bam2
+    p.close()
+    assert not b1.h and not b2.h and p.bam is None and p._bam2 is None
