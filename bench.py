@@ -290,6 +290,14 @@ def run_variant(args, cfg):
 
     registered = bool(dvc.buffer.registered)
     meta_bytes = int(dvc.buffer.meta.numel() * 8)
+    files_dist = None
+    if (world > 1 or args.files_dist) and not args.no_files:   # north_star's input at N GPUs: every rank opens the same BAM + FASTA
+        try:
+            files_dist = files_leg_dist(args, cfg, local, dvc, world, rank, barrier, replicas)
+        except Exception as ex:
+            if world > 1:
+                raise                                           # (files_leg_dist keeps the ranks in step for failures inside a pass)
+            files_dist = {"error": repr(ex)[:300]}
     if records is not None:
         records = records.copy()
     dvc.close()                                             # releases the NCCL-registered buffer before the process group
@@ -351,7 +359,9 @@ def run_variant(args, cfg):
         line["verified"], base = verify_variant(args, cfg, reads, regions, records, replicas)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = base
-    if world == 1 and not args.no_files:
+    if files_dist is not None:
+        line["e2e_files"] = files_dist
+    elif world == 1 and not args.no_files:
         try:
             line["e2e_files"] = files_leg(args, cfg, local)
         except Exception as ex:                                 # the headline numbers above stand on their own
@@ -412,6 +422,107 @@ def files_leg(args, cfg, local):
                 "api": "pepper_b200.frontend.VariantFromFiles.call_stream -> pb_bam_fetch_device + pb_get_reads_* + pb_variant_stream_*"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def files_leg_dist(args, cfg, local, dvc, world, rank, barrier, replicas):
+    """files_leg over all ranks: rank 0 writes ONE .bam + .bai + .fa (the per-GPU block), every rank opens it
+    (frontend.VariantFileSource) and claims interval groups through the same DistributedVariantCaller as the headline legs; the
+    weak-scaling job is `replicas` passes over the file's intervals.  Timed (host clock around device-synchronised steps, max
+    over ranks): pread + H2D of the compressed blocks of the groups each rank claimed, GPU inflate / parse / trim, encoder,
+    network, the all-gather, D2H of the whole job's records on the writer rank."""
+    import shutil
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from pepper_b200 import synth, synth_files
+    from pepper_b200.dist import RECORD_BYTES
+    from pepper_b200.frontend import VariantFileSource, variant_intervals
+    plat, params = platform_of(cfg)
+    n_regions = args.files_regions or args.regions
+    span = args.block * args.region_size
+    times = -(-(n_regions * args.region_size + 200) // span)
+    box = [None, 0.0]
+    if rank == 0:
+        d = None
+        try:
+            t0 = time.time()
+            rec, genome = synth.simulate_contig_records(span, args.coverage, plat, args.seed + 7)
+            d = tempfile.mkdtemp(prefix="pb_bench_files_")
+            synth_files.write_bam_tiled(os.path.join(d, "s.bam"), "chr20s", rec, span, times)
+            synth_files.write_fasta(os.path.join(d, "s.fa"), [("chr20s", np.tile(genome[:span], times))])
+            with open(os.path.join(d, "s.bam"), "rb") as f:          # page cache
+                while f.read(1 << 26):
+                    pass
+            box = [d, time.time() - t0]
+        except Exception as ex:                                      # e.g. no room in the temp dir: every rank skips the leg together
+            if d is not None:
+                shutil.rmtree(d, ignore_errors=True)
+            box = [None, repr(ex)[:300]]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    if box[0] is None:
+        return {"error": "could not write the synthetic files: %s" % box[1]}
+    d, gen_s = box
+    try:
+        bam, fa = os.path.join(d, "s.bam"), os.path.join(d, "s.fa")
+        L = times * span
+        iv = variant_intervals(100, min(L - 100, 100 + n_regions * args.region_size), args.region_size)
+        genomic = sum(e - s for s, e in iv) * replicas
+        src = VariantFileSource(bam, fa, "chr20s", iv, int(params["min_snp_baseq"]), device=local, gpu_inflate=not args.host_inflate)
+        dev = torch.device("cuda", local)
+
+        def step():
+            """One pass; a rank whose pass fails still joins the step's two collectives (with an empty slice), so that the
+            ranks stay in step and the leg is reported as failed instead of hanging the headline line."""
+            err = 0
+            try:
+                dvc.run(src, None, params, replicas=replicas)
+            except Exception as ex:
+                err = 1
+                print("files leg, rank %d: %r" % (rank, ex), file=sys.stderr, flush=True)
+                if world > 1 and "groups were run" not in str(ex):       # (that one is raised after the collectives, on every rank)
+                    dvc.buffer.gather(0, [])
+            if world > 1:
+                tt = torch.tensor([err], dtype=torch.int32, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                err = int(tt.item())
+            return err
+        if step():                                               # warm-up: reader buffers, staging, the file's pages
+            return {"error": "a rank failed in the warm-up pass (stderr has the exception)"}
+        if rank == 0:
+            dvc.buffer.to_host()
+        torch.cuda.synchronize()
+        steps = max(1, args.files_steps)
+        barrier()
+        t0 = time.perf_counter()
+        n_cand = 0
+        for _ in range(steps):
+            if step():
+                return {"error": "a rank failed in a timed pass (stderr has the exception)"}
+            if rank == 0:
+                n_cand = len(dvc.buffer.to_host())
+        torch.cuda.synchronize()
+        barrier()
+        dt = (time.perf_counter() - t0) / steps
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        phase = dict(dvc.phase_ms)
+        ft = src.bam.fetch_device_timings() if not args.host_inflate else {}
+        size = os.path.getsize(bam)
+        src.close()
+        barrier()
+        return {"value": genomic / dt, "unit": "bases/s", "ms_per_step": dt * 1e3, "steps": steps, "regions": len(iv) * replicas,
+                "genomic_bases": genomic, "candidates": n_cand, "bam_bytes": size, "batch_regions": args.group_regions,
+                "inflate": "host zlib thread pool" if args.host_inflate else "GPU (k_bgzf_inflate, warp per BGZF block)",
+                "last_group_fetch_ms": ft, "rank0_phase_ms": phase, "h2d_bytes_per_step": int(size * replicas),
+                "d2h_bytes_per_step": int(n_cand * RECORD_BYTES), "gen_seconds": round(gen_s, 1),
+                "api": "pepper_b200.dist.DistributedVariantCaller.run(frontend.VariantFileSource) -> pb_bam_fetch_device + pb_get_reads_* + "
+                       "pb_variant_stream_* per claimed group; GatherBuffer.to_host() on the writer rank"}
+    finally:
+        if rank == 0:
+            shutil.rmtree(d, ignore_errors=True)
 
 
 # figures carried over from the ncu --set full captures under profiles/ (per candidate / per algorithmic byte)
@@ -760,6 +871,8 @@ def main():
     ap.add_argument("--files-regions", type=int, default=0, help="regions of the from-files leg (default: --regions)")
     ap.add_argument("--files-steps", type=int, default=2)
     ap.add_argument("--files-batch", type=int, default=32, help="regions per batch of the from-files streaming session")
+    ap.add_argument("--files-dist", action="store_true", help="N=1: run the from-files leg through DistributedVariantCaller + VariantFileSource "
+                                                             "(the N>1 path) instead of VariantFromFiles.call_stream")
     ap.add_argument("--host-inflate", action="store_true", help="from-files leg with the host zlib pool instead of the GPU inflate")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

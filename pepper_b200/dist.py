@@ -265,7 +265,8 @@ class DistributedVariantCaller:
     """make_images + run_inference of ONE job (a region list every rank can read) over all ranks of the default process group.
 
         dvc = DistributedVariantCaller(state, local_device, capacity)
-        dvc.run(source, regions, params)        # source: abi.HostReads (pinned host buffers) or pipeline.DeviceReads
+        dvc.run(source, regions, params)        # source: abi.HostReads (pinned host buffers), pipeline.DeviceReads, or
+                                                # frontend.VariantFileSource (BAM + FASTA every rank opens; regions=None)
         records = dvc.buffer.to_host()          # every rank holds the whole job's records after the gather
     """
 
@@ -298,9 +299,12 @@ class DistributedVariantCaller:
         group J mod G with region ids shifted by (J div G) * n_regions — so that a weak-scaling run can hand out N x the
         per-GPU block without holding N copies of it."""
         import torch
+        from collections import deque
         from .abi import HostReads, regions_array
+        from .frontend import VariantFileSource
         from .pipeline import DeviceReads
-        n_reg = regions.n_regions
+        from_files = isinstance(source, VariantFileSource)
+        n_reg = source.n_regions if from_files else regions.n_regions
         plain = plan_groups(n_reg, self.group_regions)
         dynamic = self.schedule == "dynamic" and self.world > 1
         last = plan_groups_tapered(n_reg, self.group_regions, self.world) if dynamic else plain
@@ -316,7 +320,14 @@ class DistributedVariantCaller:
         self._calls += 1
         claimer = GroupClaimer(n_job, self.rank, self.world, self.schedule, work, key="pb_claim_%d" % self._calls)
         s = self.caller.stream(params, self.buffer.capacity, d_records=self.buffer.my_ptr())
-        if isinstance(source, DeviceReads):
+        depth = 1                                 # groups claimed ahead of the one being run
+        if from_files:
+            depth = 2                             # the fetch (read + H2D + inflate) of a group gets a whole group period on the helper thread
+
+            def stage(j):
+                rep, g0, g1 = job[j]
+                s.stage_device(source.take(j, g0, g1), 0, g1 - g0, rep * n_reg + g0)
+        elif isinstance(source, DeviceReads):
             def stage(j):
                 rep, g0, g1 = job[j]
                 s.stage_device(source, g0, g1, rep * n_reg + g0)
@@ -328,24 +339,34 @@ class DistributedVariantCaller:
             def stage(j):
                 rep, g0, g1 = job[j]
                 s.stage_host(source, regs, g0, g1, ref, rep * n_reg + g0)
-        cur = claimer.next()
-        if cur is not None:
-            stage(cur)
         segments, seen = [], 0
-        # a rank stops claiming when its slice of the gather buffer could not hold two more groups (the one in flight and the
-        # one it would claim): under the dynamic schedule a rank that started early may otherwise take more than its capacity;
-        # what it leaves is claimed by the others
+        # a rank stops claiming when its slice of the gather buffer could not hold the groups in flight plus the one it would
+        # claim: under the dynamic schedule a rank that started early may otherwise take more than its capacity; what it leaves is
+        # claimed by the others
         worst = max(1, self.buffer.capacity // max(4, 2 * n_job // max(1, self.world)))
+        ahead = deque()
+
+        def claim():
+            while len(ahead) < depth and self.buffer.capacity - seen >= (len(ahead) + 2.2) * worst:
+                j = claimer.next()
+                if j is None:
+                    return
+                if from_files:
+                    source.request(j, job[j][1], job[j][2])
+                ahead.append(j)
+        claim()
+        cur = ahead.popleft() if ahead else None
+        if cur is not None:
+            stage(cur)                        # (file source: takes this group's records before its reader is asked for another span)
         while cur is not None:
-            room = self.buffer.capacity - seen
-            nxt = claimer.next() if room >= 2.2 * worst else None     # claimed one ahead: its copies overlap this group's kernels
+            claim()                           # claimed ahead: the next group's copies (or file fetch) overlap this group's kernels
             tot = s.run(flush=False)
             segments.append((cur, tot - seen))
             worst = max(worst, tot - seen)
             seen = tot
-            if nxt is not None:
-                stage(nxt)
-            cur = nxt                         # no sync: the next run() prepares its tables while this group's network runs
+            cur = ahead.popleft() if ahead else None
+            if cur is not None:
+                stage(cur)                    # no sync: the next run() prepares its tables while this group's network runs
         n = s.end()
         self.groups_done = len(segments)
         t = self.caller.timings()

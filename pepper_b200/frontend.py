@@ -66,6 +66,37 @@ class _FromFiles:
     def _fetch(self, reader, contig: str, beg: int, end: int):
         return reader.fetch_device(contig, beg, end, self.device) if self.gpu_inflate else reader.fetch(contig, beg, end)
 
+    @staticmethod
+    def _group_span(g: list[tuple[int, int]]) -> tuple[int, int]:
+        """The BAM span one batch of intervals needs (each interval widened by REGION_SAFE_BASES, AlignmentSummarizer.py:181-182)."""
+        return max(0, min(s for s, _ in g) - REGION_SAFE_BASES), max(e for _, e in g) + REGION_SAFE_BASES
+
+    def _side_stream(self):
+        import torch
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)        # get_reads of batch k+1 runs here, beside the network of batch k
+        return self._side
+
+    def _trim_variant(self, view, contig: str, g: list[tuple[int, int]], min_snp_baseq: int, include_supplementary: bool = False,
+                      min_mapq: int = 0, max_reads: int = VARIANT_MAX_READS, downsample_rate: float = 1.0, prof: dict | None = None):
+        """Reference strings + batched get_reads of one batch of variant intervals on the side stream (synchronous for the host):
+        fetched records -> the FetchedReads the encoder consumes."""
+        import time
+        t1 = time.perf_counter()
+        rows, queries, spans = [], [], []
+        for (a, b) in g:
+            rs, re_ = max(0, a - REGION_SAFE_BASES), b + REGION_SAFE_BASES
+            queries.append((rs, re_)); rows.append([rs, re_, a, b, 0, 0, 0, 0]); spans.append((rs, re_ + 1))
+        regions = self._ref_table(contig, rows, spans)
+        t2 = time.perf_counter()
+        side = self._side_stream()
+        got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, min_snp_baseq,
+                                     max_reads=max_reads, downsample_rate=downsample_rate, stream=side.cuda_stream)
+        fetched = FetchedReads(got, regions, self.device, stream=side)
+        if prof is not None:
+            prof["ref_table"] += t2 - t1; prof["get_reads"] += time.perf_counter() - t2
+        return fetched
+
     def _ref_table(self, contig: str, rows: list[list[int]], spans: list[tuple[int, int]]) -> RegionTable:
         """Region table + reference strings: ONE faidx fetch of the covering span, the (overlapping) per-region strings are
         offsets into it (get_reference_sequence clamps at the contig end; so do the lengths here)."""
@@ -177,11 +208,8 @@ class VariantFromFiles(_FromFiles):
         readers = [self.bam, self._bam2]
         groups = [intervals[i:i + batch] for i in range(0, len(intervals), batch)]
 
-        def span(g):
-            return max(0, min(s for s, _ in g) - REGION_SAFE_BASES), max(e for _, e in g) + REGION_SAFE_BASES
-
         def prefetch(k):
-            return self._fetch(readers[k & 1], contig, *span(groups[k]))
+            return self._fetch(readers[k & 1], contig, *self._group_span(groups[k]))
         import time
         cap = capacity or max(4096, int(sum(e - s + 1 for s, e in intervals)) // 30)
         prof = dict(wait_fetch=0.0, ref_table=0.0, get_reads=0.0, stage=0.0, run=0.0, sync=0.0, end_fetch=0.0, fetch_thread=0.0)
@@ -191,24 +219,9 @@ class VariantFromFiles(_FromFiles):
             v = prefetch(k)
             prof["fetch_thread"] += time.perf_counter() - t0
             return v
-        import torch
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)        # get_reads of batch k+1 runs here, beside the network of batch k
-
         def trim(view, g):
-            """reference strings + batched get_reads of one batch (side stream; synchronous for the host)."""
-            t1 = time.perf_counter()
-            rows, queries, spans = [], [], []
-            for (a, b) in g:
-                rs, re_ = max(0, a - REGION_SAFE_BASES), b + REGION_SAFE_BASES
-                queries.append((rs, re_)); rows.append([rs, re_, a, b, 0, 0, 0, 0]); spans.append((rs, re_ + 1))
-            regions = self._ref_table(contig, rows, spans)
-            t2 = time.perf_counter()
-            got = self.trimmer.get_reads(view, queries, include_supplementary, min_mapq, int(params["min_snp_baseq"]),
-                                         max_reads=max_reads, downsample_rate=downsample_rate, stream=self._side.cuda_stream)
-            fetched = FetchedReads(got, regions, self.device, stream=self._side)
-            prof["ref_table"] += t2 - t1; prof["get_reads"] += time.perf_counter() - t2
-            return fetched
+            return self._trim_variant(view, contig, g, int(params["min_snp_baseq"]), include_supplementary, min_mapq, max_reads,
+                                      downsample_rate, prof)
         while True:
             s = self.caller.stream(params, cap)
             try:
@@ -249,6 +262,49 @@ class VariantFromFiles(_FromFiles):
                 if ex.rc != PB_ERR_CAPACITY:
                     raise
                 cap *= 2
+
+
+class VariantFileSource(_FromFiles):
+    """The read source of dist.DistributedVariantCaller for a job given as FILES: every rank opens the same coordinate-sorted BAM
+    (+ .bai) and FASTA and turns the interval groups it claims into trimmed device reads (GPU inflate -> record parse -> batched
+    get_reads), so that make_images + run_inference of one contig shard over the ranks from the alignment file itself — no rank
+    reads, inflates or copies a block outside the groups it runs.  `request(key, g0, g1)` starts the fetch of intervals[g0:g1] on the
+    helper thread (two readers alternate, so the records of the group being trimmed stay valid while the next span is inflated);
+    `take(key, g0, g1)` waits for it and returns the FetchedReads of that group."""
+
+    def __init__(self, bam_path: str, fasta_path: str, contig: str, intervals: list[tuple[int, int]], min_snp_baseq: int,
+                 device: int = 0, threads: int = 0, gpu_inflate: bool = True, include_supplementary: bool = False, min_mapq: int = 0,
+                 downsample_rate: float = 1.0, max_reads: int = VARIANT_MAX_READS):
+        from concurrent.futures import ThreadPoolExecutor
+        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate)
+        self._bam2 = BamReader(bam_path, 0)
+        self.contig, self.intervals = contig, list(intervals)
+        self._filters = (int(min_snp_baseq), include_supplementary, min_mapq, max_reads, downsample_rate)
+        self._pool = ThreadPoolExecutor(max_workers=1)
+        self._futs, self._issued = {}, 0
+
+    @property
+    def n_regions(self) -> int:
+        return len(self.intervals)
+
+    def interval_work(self) -> np.ndarray:
+        """Interval lengths: the work estimate the static schedule balances when the read counts are not known before the fetch."""
+        return np.array([e - s + 1 for s, e in self.intervals], dtype=np.int64)
+
+    def request(self, key, g0: int, g1: int) -> None:
+        reader = (self.bam, self._bam2)[self._issued & 1]
+        self._issued += 1
+        self._futs[key] = self._pool.submit(self._fetch, reader, self.contig, *self._group_span(self.intervals[g0:g1]))
+
+    def take(self, key, g0: int, g1: int) -> FetchedReads:
+        view = self._futs.pop(key).result()            # a Future re-raises the worker's exception (bad contig, corrupt block) here
+        return self._trim_variant(view, self.contig, self.intervals[g0:g1], *self._filters)
+
+    def close(self):
+        if getattr(self, "_pool", None) is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        super().close()
 
 
 class PolishFromFiles(_FromFiles):

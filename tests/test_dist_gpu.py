@@ -70,7 +70,7 @@ def test_stream_session_matches_one_shot_call():
     caller.close()
 
 
-def _rank_main(rank, world, port, q):
+def _rank_main(rank, world, port, q, paths=None):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -90,28 +90,46 @@ def _rank_main(rank, world, port, q):
             src = HostReads(reads, pin=True) if src_name == "host" else DeviceReads(reads, regions, device=rank)
             n = dvc.run(src, regions, params, seq_off=reads.seq_off)
             out[(schedule, src_name)] = (dvc.buffer.to_host().copy(), n, dict(dvc.phase_ms), dvc.buffer.registered)
+        if paths is not None:                  # the same job given as files every rank opens (frontend.VariantFileSource)
+            from pepper_b200.frontend import VariantFileSource
+            bam, fa, iv = paths
+            src = VariantFileSource(bam, fa, "ctg", iv, int(params["min_snp_baseq"]), device=rank)
+            n = dvc.run(src, None, params)
+            out[(schedule, "files")] = (dvc.buffer.to_host().copy(), n, dict(dvc.phase_ms), dvc.buffer.registered)
+            src.close()
         dvc.close()
     q.put((rank, out))
     dist.destroy_process_group()
 
 
-def test_two_rank_gather_equals_one_rank():
+def test_two_rank_gather_equals_one_rank(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     from oracle import nets
+    from pepper_b200 import synth_files
     from pepper_b200.dist import records_from_calls
+    from pepper_b200.frontend import VariantFromFiles, variant_intervals
     from pepper_b200.pipeline import VariantCaller
     reads, regions = _workload()
     caller = VariantCaller(nets.make_variant_weights(5))
     want = records_from_calls(caller.call(reads, regions, synth.ont_params()))
     caller.close()
+    # the from-files job: 36 intervals of a small BAM; its 1-rank answer through the single-GPU front end
+    rec, genome = synth.simulate_contig_records(40000, 30, synth.ONT, 29)
+    bam, fa = str(tmp_path / "d.bam"), str(tmp_path / "d.fa")
+    synth_files.write_bam(bam, [("ctg", genome.shape[0])], {0: rec})
+    synth_files.write_fasta(fa, [("ctg", genome)])
+    iv = variant_intervals(1000, 37000, 1000)
+    with VariantFromFiles(bam, fa, nets.make_variant_weights(5)) as vf:
+        want_files = records_from_calls(vf.call_stream("ctg", iv, synth.ont_params(), batch=5))
+    assert want_files.shape[0] > 100
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_rank_main, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, q, (bam, fa, iv))) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in range(world))
@@ -119,12 +137,14 @@ def test_two_rank_gather_equals_one_rank():
         p.join(timeout=120)
     for key in res[0]:
         n_tot, g_tot = 0, 0
+        from_files = key[1] == "files"
         for rank in range(world):
             rec, n, phases, registered = res[rank][key]
-            assert np.array_equal(rec, want), (key, rank)
+            assert np.array_equal(rec, want_files if from_files else want), (key, rank)
             n_tot += n
             g_tot += phases["groups"]
             assert (phases["network_ms"] > 0) == (n > 0)           # under the dynamic schedule a rank may end up with no group at all
         from pepper_b200.dist import plan_groups, plan_groups_tapered
-        n_groups = len(plan_groups_tapered(72, 5, world)) if key[0] == "dynamic" else len(plan_groups(72, 5))
-        assert n_tot == want.shape[0] and g_tot == n_groups           # every group of the plan run exactly once
+        n_units = len(iv) if from_files else 72
+        n_groups = len(plan_groups_tapered(n_units, 5, world)) if key[0] == "dynamic" else len(plan_groups(n_units, 5))
+        assert n_tot == (want_files if from_files else want).shape[0] and g_tot == n_groups           # every group of the plan run exactly once

@@ -124,6 +124,34 @@ def test_variant_stream_equals_single_call(files):
         vf.close()
 
 
+def test_file_source_through_distributed_caller_equals_call_stream(files):
+    """The N-GPU from-files path at world size 1: DistributedVariantCaller over a VariantFileSource (groups of 3 intervals, fetched two
+    ahead by the helper thread) writes the records of VariantFromFiles.call_stream, bit for bit; a second pass over the file
+    (`replicas`, the weak-scaling job of bench.py) repeats them with shifted region ids."""
+    from pepper_b200 import weights
+    from pepper_b200.dist import DistributedVariantCaller, records_from_calls
+    from pepper_b200.frontend import VariantFileSource, VariantFromFiles, variant_intervals
+    params = synth.ont_params()
+    iv = variant_intervals(1000, 25000, 3000)
+    state = weights.random_variant_state(0)
+    with VariantFromFiles(files["bam"], files["fa"], state) as vf:
+        want = records_from_calls(vf.call_stream("ctg", iv, params, batch=3))
+    assert want.shape[0] > 50
+    for gpu_inflate in (True, False):
+        dvc = DistributedVariantCaller(state, 0, capacity=4 * want.shape[0], group_regions=3)
+        src = VariantFileSource(files["bam"], files["fa"], "ctg", iv, int(params["min_snp_baseq"]), gpu_inflate=gpu_inflate)
+        assert dvc.run(src, None, params) == want.shape[0]
+        assert np.array_equal(dvc.buffer.to_host(), want)
+        assert dvc.run(src, None, params, replicas=2) == 2 * want.shape[0]
+        twice = dvc.buffer.to_host()
+        assert np.array_equal(twice[:want.shape[0]], want)
+        tail = twice[want.shape[0]:].copy()
+        tail["region"] -= len(iv)
+        assert np.array_equal(tail, want)
+        src.close()
+        dvc.close()
+
+
 def test_polish_contig_from_files_to_consensus(files):
     """files -> tiling -> get_reads -> realign -> encoder -> GRU -> stitch, in batches, equals the oracle stitch of the same calls
     and does not depend on the batch size."""
