@@ -104,6 +104,9 @@ __device__ __forceinline__ void op_consumes(uint32_t w, int &dref, int &drd) {
     }
 }
 
+// One warp per read; every lane takes 4 consecutive ops of a 128-op chunk (lane-local prefix, one warp scan of the lane sums),
+// and the next chunk's words are in flight while this one is scanned: the longest read of a batch bounds the launch, so the
+// serial chunk count per read is what matters.
 __global__ void k_cigar_prefix(DevReads R, int32_t *__restrict__ op_ref, int32_t *__restrict__ op_rd,
                                int32_t *__restrict__ read_reflen) {
     const int lane = threadIdx.x & 31;
@@ -111,18 +114,28 @@ __global__ void k_cigar_prefix(DevReads R, int32_t *__restrict__ op_ref, int32_t
     if (r >= R.n_reads) return;
     const int64_t c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
     int cref = 0, crd = 0;
-    for (int64_t c = c0; c < c1; c += 32) {
-        int dref = 0, drd = 0;
-        if (c + lane < c1) op_consumes(__ldg(R.cigar + c + lane), dref, drd);
-        int sref = dref, srd = drd;
+    uint32_t nx[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int64_t i = c0 + 4 * lane + k; nx[k] = (i < c1) ? __ldg(R.cigar + i) : 5u; }   // 5 = H: consumes nothing
+    for (int64_t c = c0; c < c1; c += 128) {
+        const int64_t b = c + 4 * lane;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { w[k] = nx[k]; const int64_t i = b + 128 + k; nx[k] = (i < c1) ? __ldg(R.cigar + i) : 5u; }
+        int dr[4], dd[4], lref = 0, lrd = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { op_consumes(w[k], dr[k], dd[k]); lref += dr[k]; lrd += dd[k]; }
+        int sref = lref, srd = lrd;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            int a = __shfl_up_sync(0xffffffffu, sref, d), b = __shfl_up_sync(0xffffffffu, srd, d);
-            if (lane >= d) { sref += a; srd += b; }
+            int a = __shfl_up_sync(0xffffffffu, sref, d), bb = __shfl_up_sync(0xffffffffu, srd, d);
+            if (lane >= d) { sref += a; srd += bb; }
         }
-        if (c + lane < c1) {
-            op_ref[c + lane] = cref + sref - dref;
-            op_rd[c + lane] = crd + srd - drd;
+        int pref = cref + sref - lref, prd = crd + srd - lrd;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (b + k < c1) { op_ref[b + k] = pref; op_rd[b + k] = prd; }
+            pref += dr[k]; prd += dd[k];
         }
         cref += __shfl_sync(0xffffffffu, sref, 31);
         crd += __shfl_sync(0xffffffffu, srd, 31);
@@ -515,6 +528,7 @@ struct CollectArgs {
     uint32_t *site_cur;
     Ev *ev;
     const RareEv *rare; unsigned long long n_rare;
+    int64_t op_first, op_last;       // the batch's op range in R.cigar / op_ref / op_rd
     VParams P;
 };
 
@@ -523,50 +537,95 @@ __device__ __forceinline__ Ev *claim_slot(const CollectArgs &A, uint32_t m, uint
     return A.ev + A.site_evoff[s] + ((m & F_SNP) ? 4 : 0) + k;
 }
 
+// Flat over the batch's CIGAR ops: a warp takes COLLECT_CHUNK consecutive ops of the op array, whichever reads they belong to
+// (one warp per read made the longest read of a batch — 20 k ops of a 100 kb ONT read — the duration of the launch).  The read
+// of the chunk's first op comes from one cooperative search in cigar_off; after that every lane walks its own read index forward.
+constexpr int COLLECT_CHUNK = 1024;
+
 __global__ void k_collect_ops(CollectArgs A) {
     const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t wid = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const DevReads &R = A.R;
-    if (r >= R.n_reads) return;
-    if (R.mapq[r] == 0) return;
-    const int64_t so = R.seq_off[r], lseq = R.seq_off[r + 1] - so;
-    if (lseq == 0) return;
-    const int reg = A.read_region[r];
-    if (reg < 0) return;
-    const pb_region_t rg = A.regions[reg];
-    const int64_t rpos = R.pos[r];
-    const int64_t c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
-    const int rev = R.flags[r] & 1;
-    for (int64_t c = c0 + lane; c < c1; c += 32) {
-        const uint32_t w = __ldg(R.cigar + c);
-        const int op = w & 15, len = (int) (w >> 4);
-        if (op != 1 && op != 2) continue;
-        const int64_t a = rpos + __ldg(A.op_ref + c);
-        if (a > rg.ref_end) continue;                       // :355
-        const int64_t p = a - 1;
-        if (p < rg.ref_start || p > rg.ref_end) continue;
-        const int64_t x = p - rg.ref_start;
-        const int64_t g = A.region_goff[reg] + x;
-        const uint32_t m = A.meta[g];
-        if (op == 1) {
-            if (!(m & F_INS)) continue;
-            const int pd = __ldg(A.op_rd + c);
-            if (pd < 1) continue;
-            int klen; bool covx;
-            if (!insert_allele(R, so, lseq, pd, len, A.P, klen, covx)) continue;
-            Ev *e = claim_slot(A, m, A.site_of[g]);
-            Ev v; memset(&v, 0, sizeof(v));
-            v.type = 2; v.strand = (uint8_t) rev; v.klen = (uint16_t) klen; v.read = (uint32_t) r; v.ridx = (uint32_t) (pd - 1);
-            v.key = ins_key(R, so, pd - 1, klen);
-            *e = v;
-        } else {
-            if (!(m & F_DEL)) continue;
-            int klen;
-            if (!delete_allele(x, len, rg.ref_len, klen)) continue;
-            Ev *e = claim_slot(A, m, A.site_of[g]);
-            Ev v; memset(&v, 0, sizeof(v));
-            v.type = 3; v.strand = (uint8_t) rev; v.klen = (uint16_t) klen; v.key = (uint64_t) klen;
-            *e = v;
+    const int64_t c_beg = A.op_first + wid * COLLECT_CHUNK;
+    if (c_beg >= A.op_last) return;
+    const int64_t c_end = min(A.op_last, c_beg + (int64_t) COLLECT_CHUNK);
+    // largest r with cigar_off[r] <= c_beg (32-ary: cigar_off is non-decreasing, so the lanes that pass form a prefix)
+    int64_t r = 0;
+    {
+        int64_t base = 0, n = R.n_reads;
+        while (n > 1) {
+            const int64_t stride = (n + 31) / 32;
+            const int64_t off = (int64_t) lane * stride;
+            const bool le = (off < n) && (R.cigar_off[base + off] <= c_beg);
+            const int k = __popc(__ballot_sync(0xffffffffu, le));
+            if (k == 0) { n = 0; break; }
+            const int64_t nb = base + (int64_t) (k - 1) * stride;
+            n = min(stride, base + n - nb);
+            base = nb;
+        }
+        r = base;
+    }
+    int64_t r_have = -1;
+    bool skip = true;
+    int64_t so = 0, lseq = 0, rpos = 0, goff = 0, ref_start = 0, ref_end = 0, ref_len = 0, next_off = R.cigar_off[r + 1];
+    int rev = 0;
+    for (int64_t c4 = c_beg + lane; c4 < c_end; c4 += 128) {
+        uint32_t w4[4]; int pr4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t c = c4 + 32 * k;
+            const bool in = c < c_end;
+            w4[k] = in ? __ldg(R.cigar + c) : 0u;
+            pr4[k] = in ? __ldg(A.op_ref + c) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t c = c4 + 32 * k;
+            const uint32_t w = w4[k];
+            const int op = w & 15, len = (int) (w >> 4);
+            if (op != 1 && op != 2) continue;
+            while (c >= next_off) { r++; next_off = R.cigar_off[r + 1]; }
+            if (r != r_have) {
+                r_have = r;
+                so = R.seq_off[r]; lseq = R.seq_off[r + 1] - so;
+                const int reg = A.read_region[r];
+                skip = (R.mapq[r] == 0) || (lseq == 0) || (reg < 0);
+                if (!skip) {
+                    const pb_region_t *rg = A.regions + reg;
+                    ref_start = rg->ref_start; ref_end = rg->ref_end; ref_len = rg->ref_len;
+                    goff = A.region_goff[reg];
+                    rpos = R.pos[r];
+                    rev = R.flags[r] & 1;
+                }
+            }
+            if (skip) continue;
+            const int64_t a = rpos + pr4[k];
+            if (a > ref_end) continue;                          // :355
+            const int64_t p = a - 1;
+            if (p < ref_start || p > ref_end) continue;
+            const int64_t x = p - ref_start;
+            const int64_t g = goff + x;
+            const uint32_t m = A.meta[g];
+            if (op == 1) {
+                if (!(m & F_INS)) continue;
+                const int pd = __ldg(A.op_rd + c);
+                if (pd < 1) continue;
+                int klen; bool covx;
+                if (!insert_allele(R, so, lseq, pd, len, A.P, klen, covx)) continue;
+                Ev *e = claim_slot(A, m, A.site_of[g]);
+                Ev v; memset(&v, 0, sizeof(v));
+                v.type = 2; v.strand = (uint8_t) rev; v.klen = (uint16_t) klen; v.read = (uint32_t) r; v.ridx = (uint32_t) (pd - 1);
+                v.key = ins_key(R, so, pd - 1, klen);
+                *e = v;
+            } else {
+                if (!(m & F_DEL)) continue;
+                int klen;
+                if (!delete_allele(x, len, ref_len, klen)) continue;
+                Ev *e = claim_slot(A, m, A.site_of[g]);
+                Ev v; memset(&v, 0, sizeof(v));
+                v.type = 3; v.strand = (uint8_t) rev; v.klen = (uint16_t) klen; v.key = (uint64_t) klen;
+                *e = v;
+            }
         }
     }
 }
@@ -731,19 +790,6 @@ struct WindowArgs {
     int8_t *images; int64_t *positions; uint8_t *depths, *freqs; char *keys; int32_t *region_of;
 };
 
-// value of base-matrix cell (row position xr of region, column j) after the clamp of :648-653
-__device__ __forceinline__ int matrix_cell(const WindowArgs &A, const pb_region_t &rg, int64_t gbase, int64_t xr, int64_t L1, int j) {
-    if (xr < 0 || xr >= L1) return 0;          // rows outside [0, region_size) are zero; row region_size is the spare zero row
-    if (j == 0) {
-        const char c = (xr < rg.ref_len) ? to_upper(A.ref[rg.ref_off + xr]) : '\0';
-        return c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 3 : c == 'T' ? 4 : 5;
-    }
-    int k;
-    if (j == 4) k = 0; else if (j >= 8 && j <= 14) k = j - 7; else if (j == 15) k = 8; else if (j >= 19) k = j - 10; else return 0;
-    int v = A.M16[(gbase + xr) * 16 + k];
-    if (j >= 11 && j <= 24) v = v >= 0 ? min(v, 125) : max(v, -125);
-    return v;
-}
 // region_summary.cpp:201-230 for an upper-case class of the reference base
 __device__ __forceinline__ int feat_col(int rcls, char base, int rev) {
     if (rcls >= 4) return -1;
@@ -754,9 +800,19 @@ __device__ __forceinline__ int feat_col(int rcls, char base, int rev) {
     }
 }
 
-__global__ void k_windows(WindowArgs A) {
-    const int lane = threadIdx.x & 31;
-    const int64_t s = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// One warp per flagged site.  The 33 x 26 window of the (clamped, int8) base matrix around the site is built ONCE per site in
+// shared memory — 33 matrix rows fetched as 16-byte vectors — and every candidate of the site is that window with the few
+// candidate cells of row 16 (rows 17.. for a deletion) patched on the way out, stored two bytes per lane.
+constexpr int WIN_CELLS = 33 * 26;
+// image column j -> column of the 16-wide int16 matrix row (REFF, 7 forward features, REFR, 7 reverse features), -1 = a zero column
+__device__ __forceinline__ int win_col(int j) { return j == 4 ? 0 : (j >= 8 && j <= 15) ? j - 7 : j >= 19 ? j - 10 : -1; }
+
+__global__ void __launch_bounds__(128) k_windows(WindowArgs A) {
+    __shared__ __align__(16) int16_t s_rows[4][33][16];
+    __shared__ __align__(4) int8_t s_base[4][WIN_CELLS + 6];
+    __shared__ int8_t s_refc[4][36];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t s = (int64_t) blockIdx.x * (blockDim.x >> 5) + wib;
     if (s >= A.n_sites) return;
     const int64_t o0 = A.site_candoff[s];
     const int nc = (int) (A.site_candoff[s + 1] - o0);
@@ -770,6 +826,38 @@ __global__ void k_windows(WindowArgs A) {
     const char rch = (x < rg.ref_len) ? A.ref[rg.ref_off + x] : '\0';
     const int rcls = ref_class(rch);
     const int depth = min(A.cov[g], 125);
+    // ---- the site's window: rows outside [0, region_size) are zero; row region_size is the spare zero row
+    for (int it = lane; it < 66; it += 32) {
+        const int i = it >> 1, h = it & 1;
+        const int64_t xr = x - 16 + i;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (xr >= 0 && xr < L1) v = __ldg(reinterpret_cast<const int4 *>(A.M16 + (gbase + xr) * 16 + h * 8));
+        *reinterpret_cast<int4 *>(&s_rows[wib][i][h * 8]) = v;
+    }
+    for (int i = lane; i < 33; i += 32) {                            // column 0: the reference base code of every row
+        const int64_t xr = x - 16 + i;
+        int v = 0;
+        if (xr >= 0 && xr < L1) {
+            const char c = (xr < rg.ref_len) ? to_upper(A.ref[rg.ref_off + xr]) : '\0';
+            v = c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 3 : c == 'T' ? 4 : 5;
+        }
+        s_refc[wib][i] = (int8_t) v;
+    }
+    __syncwarp();
+#pragma unroll 9
+    for (int e = lane; e < WIN_CELLS; e += 32) {
+        const int i = e / 26, j = e - i * 26;
+        const int k = win_col(j);
+        int v = 0;
+        if (j == 0) v = s_refc[wib][i];
+        else if (k >= 0) {                                           // rows outside the region were staged as zeros
+            v = s_rows[wib][i][k];
+            if (j >= 11 && j <= 24) v = v >= 0 ? min(v, 125) : max(v, -125);      // the clamp of :648-653
+        }
+        s_base[wib][e] = (int8_t) v;                                 // int8 wrap == DataStore.py:68 astype
+    }
+    __syncwarp();
+    const int8_t *base = s_base[wib];
     for (int c = 0; c < nc; c++) {
         const int64_t o = o0 + c;
         if (o >= A.capacity) return;
@@ -788,25 +876,36 @@ __global__ void k_windows(WindowArgs A) {
             sf = feat_col(rcls, '*', 0); sr = feat_col(rcls, '*', 1);
             end_index = min(16 + klen - 1, 31);
         }
-        int8_t *img = A.images + o * (33 * 26);
-        for (int e = lane; e < 33 * 26; e += 32) {
-            const int i = e / 26, j = e - i * 26;
-            int v = matrix_cell(A, rg, gbase, x - 16 + i, L1, j);
-            if (i == 16) {
-                if (cd.type == 1) {
-                    if (j == 1) v = (snp_char == 'A') ? 1 : (snp_char == 'C') ? 2 : (snp_char == 'G') ? 3 : (snp_char == 'T') ? 4 : 5;
-                    else if (j == 5) v = fwd; else if (j == 16) v = rev;
-                } else if (cd.type == 2) {
-                    if (j == 2) v = min(klen, 125); else if (j == 6) v = fwd; else if (j == 17) v = rev;
-                } else {
-                    if (j == 3) v = min(klen, 125); else if (j == 7) v = fwd; else if (j == 18) v = rev;
+        const int patch_end = (end_index + 1) * 26;                  // cells [16 * 26, patch_end) may differ from the window
+        uint16_t *img = reinterpret_cast<uint16_t *>(A.images + o * WIN_CELLS);        // o * 858 is even
+        for (int t = lane; t < WIN_CELLS / 2; t += 32) {
+            const int e0 = 2 * t;
+            const uint32_t pair = reinterpret_cast<const uint16_t *>(base)[t];
+            int v2[2] = {(int) (int8_t) (pair & 0xffu), (int) (int8_t) (pair >> 8)};
+            if (e0 + 1 >= 16 * 26 && e0 < patch_end) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int e = e0 + q;
+                    const int i = e / 26, j = e - i * 26;
+                    int v = v2[q];
+                    if (i == 16) {
+                        if (cd.type == 1) {
+                            if (j == 1) v = (snp_char == 'A') ? 1 : (snp_char == 'C') ? 2 : (snp_char == 'G') ? 3 : (snp_char == 'T') ? 4 : 5;
+                            else if (j == 5) v = fwd; else if (j == 16) v = rev;
+                        } else if (cd.type == 2) {
+                            if (j == 2) v = min(klen, 125); else if (j == 6) v = fwd; else if (j == 17) v = rev;
+                        } else {
+                            if (j == 3) v = min(klen, 125); else if (j == 7) v = fwd; else if (j == 18) v = rev;
+                        }
+                        if (j == ff || j == fr) v = -v;
+                    } else if (cd.type == 3 && i > 16 && i <= end_index) {
+                        if (j == 3) v = min(klen, 125); else if (j == 7) v = fwd; else if (j == 18) v = rev;
+                        if (j == sf || j == sr) v = -v;
+                    }
+                    v2[q] = v;
                 }
-                if (j == ff || j == fr) v = -v;
-            } else if (cd.type == 3 && i > 16 && i <= end_index) {
-                if (j == 3) v = min(klen, 125); else if (j == 7) v = fwd; else if (j == 18) v = rev;
-                if (j == sf || j == sr) v = -v;
             }
-            img[e] = (int8_t) v;                     // int8 wrap == DataStore.py:68 astype
+            img[t] = (uint16_t) ((uint32_t) (uint8_t) (int8_t) v2[0] | ((uint32_t) (uint8_t) (int8_t) v2[1] << 8));
         }
         // key string, 64 B
         for (int k = lane; k < PB_ALLELE_STRIDE; k += 32) {
@@ -907,6 +1006,7 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
                                         char *d_keys, int32_t *d_region_of, int64_t *d_n_per_region, int64_t *n_out,
                                         void *stream_) {
     if (!e || !dr || !h_regions || !params || !n_out) { set_error("null argument"); return PB_ERR_ARG; }
+    if (reinterpret_cast<uintptr_t>(d_images) & 1) { set_error("d_images must be 2-byte aligned"); return PB_ERR_ARG; }   // k_windows stores pairs
     (void) ref_bytes;
     cudaStream_t st = (cudaStream_t) stream_;
     PB_CUDA(cudaSetDevice(e->device));
@@ -1052,8 +1152,8 @@ extern "C" int pb_variant_encode_device(pb_variant_encoder_t *e, const pb_reads_
         CA.R = R; CA.regions = d_regions; CA.read_region = e->read_region.as<int32_t>(); CA.region_goff = TA.region_goff;
         CA.op_ref = TA.op_ref; CA.op_rd = TA.op_rd; CA.meta = TA.meta; CA.site_of = SA.site_of; CA.site_evoff = SA.site_evoff;
         CA.site_cur = e->site_cur.as<uint32_t>(); CA.ev = e->ev.as<Ev>(); CA.rare = e->rare.as<RareEv>(); CA.n_rare = n_rare;
-        CA.P = P;
-        if (n_reads > 0) { k_collect_ops<<<(unsigned) ceil_div(n_reads, 8), 256, 0, st>>>(CA); e->launches++; }
+        CA.P = P; CA.op_first = op_first; CA.op_last = op_last;
+        if (n_ops > 0) { k_collect_ops<<<(unsigned) ceil_div(n_ops, (int64_t) 8 * COLLECT_CHUNK), 256, 0, st>>>(CA); e->launches++; }
         if (n_rare > 0) { k_collect_rare<<<(unsigned) ceil_div((int64_t) n_rare, 256), 256, 0, st>>>(CA); e->launches++; }
 
         AlleleArgs AA;
