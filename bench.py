@@ -528,9 +528,10 @@ def files_leg_dist(args, cfg, local, dvc, world, rank, barrier, replicas):
 # figures carried over from the ncu --set full captures under profiles/ (per candidate / per algorithmic byte)
 PRODUCTS = 3
 OPERAND = "fp16"
-TRAFFIC_RATIO_COUNT = 1.30
-TRAFFIC_NOTE_COUNT = ("dram__bytes_read+write of k_tile_count = 1.30 x algorithmic bytes in the ncu --set full capture "
-                      "(77.2 MB vs 59.4 MB at 8 regions, profiles/README.md); scaled to this step")
+TRAFFIC_RATIO_COUNT = 1.60
+TRAFFIC_NOTE_COUNT = ("dram__bytes_read+write of k_tile_count = 1.60 x algorithmic bytes in the ncu --set full capture of one "
+                      "32-region group (277.0 MB read + 102.7 MB written vs 237.6 MB, profiles/r2c_prof_k_tile_count_summary.txt: "
+                      "the excess is the 8 B/op prefix arrays read beside the 4 B CIGAR words); scaled to this step")
 TRAFFIC_PER_CAND = 237.36e6 / 3840 + 767.39e6 / 3840 + 678.66e6 / 9472
 TRAFFIC_NOTE_NET = ("dram__bytes_read+write of the ncu --set full captures, per candidate: encoder LSTM layer (k_lstm_layer) 237.4 MB and "
                     "decoder LSTM layer 767.4 MB per launch over 3,840 candidates, linear_1 678.7 MB per launch over 9,472 "

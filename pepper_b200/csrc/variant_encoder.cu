@@ -150,9 +150,17 @@ __device__ __forceinline__ bool insert_allele(const DevReads &R, int64_t so, int
                                               const VParams &P, int &klen, bool &cov_extra) {
     const int64_t s = (int64_t) rd_idx - 1;
     const int64_t n = (int64_t) len + 1;
-    double qsum = 0;
-    for (int64_t i = s; i < s + n; i++) qsum += (double) __ldg(R.qual + so + i);
-    const bool qok = qsum >= P.min_indel_baseq * (double) n;
+    // (sum of small integers: exact in the reference's double accumulator, so an integer sum compares identically; four
+    //  independent loads per step instead of one dependent add per load)
+    const uint8_t *qp = R.qual + so + s;
+    long long qs = 0;
+    int64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const int q0 = __ldg(qp + i), q1 = __ldg(qp + i + 1), q2 = __ldg(qp + i + 2), q3 = __ldg(qp + i + 3);
+        qs += (q0 + q1) + (q2 + q3);
+    }
+    for (; i < n; i++) qs += __ldg(qp + i);
+    const bool qok = (double) qs >= P.min_indel_baseq * (double) n;
     cov_extra = qok && ((double) __ldg(R.qual + so + s) < P.min_snp_baseq);
     int64_t k = n;
     if (s + k > lseq) k = lseq - s;          // std::string::substr clamps
@@ -233,6 +241,8 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
 
     const DevReads &R = A.R;
     const VParams &P = A.P;
+    const bool minq_all = P.minq_snp > 255;                          // no 8-bit quality can pass
+    const uint32_t minq4 = (uint32_t) max(0, min(P.minq_snp, 255)) * 0x01010101u;
 
     // ---- overlapping reads are first compacted into a shared list (reads are position sorted, so the ones touching a
     //      tile are neighbours: handing out groups of 32 consecutive reads per warp would leave most warps idle),
@@ -329,19 +339,28 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
                         }
                     }
                 }
-                // --- per-position work, balanced over the warp
-                int incl = scnt;
+                // --- range counters as difference arrays (prefix-summed in the epilogue): every M op adds its clipped segment to
+                //     the strand's base total, every D op to the strand's '*' column — two atomics per op instead of one per base
+                if (scnt > 0) {
+                    int32_t *d = cnt + ((is_m ? C_TOT_F : C_S_F) + rev) * TILE;
+                    atomicAdd(d + s0, 1);
+                    if (s0 + scnt <= hi_rel) atomicAdd(d + s0 + scnt, -1);
+                }
+                // --- per-base work of the M ops, balanced over the warp in QUADS of 4 consecutive bases of one op: a quad whose
+                //     bases all pass the quality threshold and equal the reference character needs nothing beyond the range add
+                const int nq = is_m ? (scnt + 3) >> 2 : 0;
+                int incl = nq;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const int v = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= d) incl += v;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
-                // per-op record for the per-position loop: x = base + idx, read index = rdb + idx
-                const int excl = incl - scnt;
-                const int base_x = s0 - excl;                               // x of position idx
-                const int base_rd = pd + (s0 - a) - excl;                   // read index of position idx (M ops)
-                const int tag = (op == 2) ? -1 : op_last;                   // -1: deleted positions; else anchor x (or none)
+                const int excl = incl - nq;
+                const int base_x = s0 - 4 * excl;                           // x of the first base of quad idx: base_x + 4 idx
+                const int base_rd = pd + (s0 - a) - 4 * excl;               // read index of that base
+                // exclusive end of the segment, bit 0: the segment's last base anchors an I/D (and lies in this tile)
+                const int pk = ((s0 + scnt) << 1) | ((nq > 0 && op_last == s0 + scnt - 1) ? 1 : 0);
                 for (int k0 = 0; k0 < total; k0 += 32) {
                     const int idx = k0 + lane;
                     // smallest l with incl[l] > idx
@@ -354,41 +373,70 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
                     l = min(l, 31);
                     const int o_bx = __shfl_sync(0xffffffffu, base_x, l);
                     const int o_brd = __shfl_sync(0xffffffffu, base_rd, l);
-                    const int o_tag = __shfl_sync(0xffffffffu, tag, l);
+                    const int o_pk = __shfl_sync(0xffffffffu, pk, l);
                     if (idx < total) {
-                        const int x = o_bx + idx;
-                        const uint32_t rinfo = s_rinfo[x];
-                        const int rcls = (int) (rinfo >> 5);
-                        if (o_tag == -1) {
-                            if (rcls < 4) atomicAdd(&cnt[(C_S_F + rev) * TILE + x], 1);
-                        } else {
-                            const int64_t ri = so + (int64_t) (o_brd + idx);
-                            const int q = __ldg(R.qual + ri);
-                            const int code = seq_code_at(R.seq, ri);
-                            if (q >= P.minq_snp) {
-                                atomicAdd(&cnt[(C_TOT_F + rev) * TILE + x], 1);
-                                const int cls = base_class(code);
-                                // rare paths: anchor of an indel, column differing from the reference column, raw mismatch
-                                if (x == o_tag) atomicAdd(&cnt[(C_ANC_F + rev) * TILE + x], 1);
-                                if (rcls < 4 && cls != rcls) {
-                                    if (cls < 4) {
-                                        atomicAdd(&cnt[(C_A_F + 4 * rev + cls) * TILE + x], 1);
-                                    } else {
-                                        atomicAdd(&cnt[(C_NON_F + rev) * TILE + x], 1);
-                                        atomicAdd(&cnt[((cls == 4 ? C_D_F : C_S_F) + rev) * TILE + x], 1);
+                        const int xq = o_bx + 4 * idx;
+                        const int nb = min(4, (o_pk >> 1) - xq);            // bases of this quad (1..4)
+                        const int64_t ri = so + (int64_t) (o_brd + 4 * idx);
+                        const uint8_t *qp = R.qual + ri;
+                        const uint8_t *sp = R.seq + (ri >> 1);
+                        const int odd = (int) (ri & 1);
+                        // qualities / reference info of the quad, one byte per base; the 4-bit codes as a 24-bit nibble stream
+                        uint32_t qw = __ldg(qp), rw = s_rinfo[xq], sw = (uint32_t) __ldg(sp) << 16;
+                        if (nb > 1) { qw |= (uint32_t) __ldg(qp + 1) << 8; rw |= (uint32_t) s_rinfo[xq + 1] << 8; }
+                        if (nb > 2) { qw |= (uint32_t) __ldg(qp + 2) << 16; rw |= (uint32_t) s_rinfo[xq + 2] << 16; }
+                        if (nb > 3) { qw |= (uint32_t) __ldg(qp + 3) << 24; rw |= (uint32_t) s_rinfo[xq + 3] << 24; }
+                        if (odd + nb > 2) sw |= (uint32_t) __ldg(sp + 1) << 8;
+                        if (odd + nb > 4) sw |= (uint32_t) __ldg(sp + 2);
+                        sw >>= 4 * (1 - odd);                               // base k of the quad: bits [19 - 4k, 16 - 4k]
+                        // codes spread to one byte per base (byte k = base k), then byte-wise SIMD tests of the whole quad
+                        uint32_t cw = (sw >> 4) & 0xffffu;
+                        cw = (cw | (cw << 8)) & 0x00ff00ffu;
+                        cw = (cw | (cw << 4)) & 0x0f0f0f0fu;
+                        cw = __byte_perm(cw, 0, 0x0123);
+                        unsigned ex = (__vcmpne4(cw, rw & 0x1f1f1f1fu) | (minq_all ? 0xffffffffu : __vcmpltu4(qw, minq4))) &
+                                      (0xffffffffu >> (8 * (4 - nb)));
+                        if (o_pk & 1) {                                     // anchor of an I/D: the last base of the segment (:381-391)
+                            const int ka = (o_pk >> 1) - 1 - xq;
+                            if (ka < nb && (int) ((qw >> (8 * ka)) & 255u) >= P.minq_snp)
+                                atomicAdd(&cnt[(C_ANC_F + rev) * TILE + xq + ka], 1);
+                        }
+                        while (ex) {
+                            const int k = (__ffs((int) ex) - 1) >> 3;
+                            ex &= ~(0xffu << (8 * k));
+                            const int x = xq + k;
+                            const int q = (int) ((qw >> (8 * k)) & 255u);
+                            if (q < P.minq_snp) {                           // not a counted base: take it out of the range total
+                                atomicAdd(&cnt[(C_TOT_F + rev) * TILE + x], -1);
+                                if (x < hi_rel) atomicAdd(&cnt[(C_TOT_F + rev) * TILE + x + 1], 1);
+                                continue;
+                            }
+                            const int code = (int) ((cw >> (8 * k)) & 15u);
+                            const uint32_t rinfo = (rw >> (8 * k)) & 255u;
+                            const int rcls = (int) (rinfo >> 5);
+                            const int cls = base_class(code);
+                            // column differing from the reference column
+                            if (rcls < 4 && cls != rcls) {
+                                if (cls < 4) {
+                                    atomicAdd(&cnt[(C_A_F + 4 * rev + cls) * TILE + x], 1);
+                                } else {
+                                    atomicAdd(&cnt[(C_NON_F + rev) * TILE + x], 1);
+                                    if (cls == 4) atomicAdd(&cnt[(C_D_F + rev) * TILE + x], 1);
+                                    else {                                  // point add to the '*' difference array
+                                        atomicAdd(&cnt[(C_S_F + rev) * TILE + x], 1);
+                                        if (x < hi_rel) atomicAdd(&cnt[(C_S_F + rev) * TILE + x + 1], -1);
                                     }
                                 }
-                                if ((rinfo & 31u) != (uint32_t) code) {          // nt16_char(code) != reference character
-                                    atomicAdd(&cnt[C_SNP * TILE + x], 1);
-                                    if (rcls >= 4 || cls >= 4) {
-                                        atomicAdd(&cnt[C_RARE * TILE + x], 1);
-                                        const unsigned long long slot = atomicAdd(A.rare_n, 1ULL);
-                                        if (slot < A.rare_cap) {
-                                            RareEv e; e.g = (uint32_t) (A.region_goff[reg] + x0 + x); e.code = (uint8_t) code;
-                                            e.strand = (uint8_t) rev; e.pad = 0;
-                                            A.rare[slot] = e;
-                                        }
-                                    }
+                            }
+                            // nt16_char(code) != reference character (always true here: the quad test let equal bases through)
+                            atomicAdd(&cnt[C_SNP * TILE + x], 1);
+                            if (rcls >= 4 || cls >= 4) {
+                                atomicAdd(&cnt[C_RARE * TILE + x], 1);
+                                const unsigned long long slot = atomicAdd(A.rare_n, 1ULL);
+                                if (slot < A.rare_cap) {
+                                    RareEv e; e.g = (uint32_t) (A.region_goff[reg] + x0 + x); e.code = (uint8_t) code;
+                                    e.strand = (uint8_t) rev; e.pad = 0;
+                                    A.rare[slot] = e;
                                 }
                             }
                         }
@@ -400,6 +448,37 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
         }
         __syncthreads();
         if (tid == 0) { s_nlist = 0; s_next = 0; }
+        __syncthreads();
+    }
+
+    // ---- the four difference arrays (base totals and '*' columns per strand) -> counts: block-wide inclusive prefix sums,
+    //      two positions per thread
+    {
+        __shared__ int s_wsum[4][TC_THREADS / 32];
+        static_assert(TILE == 2 * TC_THREADS, "the scan below takes two positions per thread");
+        const int cols[4] = {C_TOT_F, C_TOT_R, C_S_F, C_S_R};
+        int v0[4], v1[4], inc[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            v0[c] = cnt[cols[c] * TILE + 2 * tid];
+            v1[c] = cnt[cols[c] * TILE + 2 * tid + 1];
+            inc[c] = v0[c] + v1[c];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc[c], d);
+                if (lane >= d) inc[c] += v;
+            }
+            if (lane == 31) s_wsum[c][tid >> 5] = inc[c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int off = 0;
+            for (int w = 0; w < (tid >> 5); w++) off += s_wsum[c][w];
+            const int before = off + inc[c] - v0[c] - v1[c];
+            cnt[cols[c] * TILE + 2 * tid] = before + v0[c];
+            cnt[cols[c] * TILE + 2 * tid + 1] = before + v0[c] + v1[c];
+        }
         __syncthreads();
     }
 
@@ -428,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tile_count(TileArgs A) {
             for (int b = 0; b < 4; b++) row[o + b] = (int16_t) -((rcls < 4) ? n[b] : 0);
             row[o + 4] = (int16_t) -CN(C_I_F + s);
             row[o + 5] = (int16_t) -CN(C_D_F + s);
-            row[o + 6] = (int16_t) -CN(C_S_F + s);
+            row[o + 6] = (int16_t) -((rcls < 4) ? CN(C_S_F + s) : 0);     // deleted positions count only over a valid reference base
         }
         const int64_t g = g0 + x;
         int4 *dst = reinterpret_cast<int4 *>(A.M16 + g * 16);
