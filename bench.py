@@ -395,7 +395,8 @@ def files_leg(args, cfg, local):
         gen_s = time.time() - t0
         iv = variant_intervals(100, min(L - 100, 100 + n_regions * args.region_size), args.region_size)
         genomic = sum(e - s for s, e in iv)
-        vf = VariantFromFiles(bam, fa, weights.random_variant_state(0), device=local, gpu_inflate=not args.host_inflate)
+        vf = VariantFromFiles(bam, fa, weights.random_variant_state(0), device=local, gpu_inflate=not args.host_inflate,
+                              host_share=args.inflate_host_share)
         cap = int(genomic // (40 if cfg["platform"] == "ONT" else 250)) + 65536
         vf.call_stream("chr20s", iv[:2 * args.files_batch], params, batch=args.files_batch, capacity=cap)   # warm-up (allocations, page cache of the head)
         with open(bam, "rb") as f:                               # page cache: the file was just written, read it once anyway
@@ -412,12 +413,13 @@ def files_leg(args, cfg, local):
         dt = (time.perf_counter() - t0) / steps
         comp, infl = vf.bam.io_stats()
         ft = vf.bam.fetch_device_timings() if not args.host_inflate else {}
+        split = list(vf.inflate_split())
         stage_prof = getattr(vf, "last_profile", None)
         vf.close()
         return {"value": genomic / dt, "unit": "bases/s", "ms_per_step": dt * 1e3, "steps": steps, "regions": len(iv), "genomic_bases": genomic,
                 "candidates": n_cand, "bam_bytes": os.path.getsize(bam), "records_per_block": rec.n_records, "batch_regions": args.files_batch,
-                "inflate": "host zlib thread pool" if args.host_inflate else "GPU (k_bgzf_inflate, warp per BGZF block)",
-                "last_batch_fetch_ms": ft, "host_stage_ms": stage_prof, "h2d_bytes_per_step": int(os.path.getsize(bam)), "d2h_bytes_per_step": int(n_cand * 90),
+                "inflate": "host zlib thread pool" if args.host_inflate else "GPU (k_bgzf_inflate, warp per BGZF block)" + (" + host pool on %.2f of the blocks" % args.inflate_host_share if args.inflate_host_share else ""),
+                "inflate_blocks_host_device": split, "last_batch_fetch_ms": ft, "host_stage_ms": stage_prof, "h2d_bytes_per_step": int(os.path.getsize(bam)), "d2h_bytes_per_step": int(n_cand * 90),
                 "gen_seconds": round(gen_s, 1),
                 "api": "pepper_b200.frontend.VariantFromFiles.call_stream -> pb_bam_fetch_device + pb_get_reads_* + pb_variant_stream_*"}
     finally:
@@ -468,7 +470,8 @@ def files_leg_dist(args, cfg, local, dvc, world, rank, barrier, replicas):
         L = times * span
         iv = variant_intervals(100, min(L - 100, 100 + n_regions * args.region_size), args.region_size)
         genomic = sum(e - s for s, e in iv) * replicas
-        src = VariantFileSource(bam, fa, "chr20s", iv, int(params["min_snp_baseq"]), device=local, gpu_inflate=not args.host_inflate)
+        src = VariantFileSource(bam, fa, "chr20s", iv, int(params["min_snp_baseq"]), device=local, gpu_inflate=not args.host_inflate,
+                                host_share=args.inflate_host_share)
         dev = torch.device("cuda", local)
 
         def step():
@@ -510,13 +513,14 @@ def files_leg_dist(args, cfg, local, dvc, world, rank, barrier, replicas):
             dt = float(tt.item())
         phase = dict(dvc.phase_ms)
         ft = src.bam.fetch_device_timings() if not args.host_inflate else {}
+        split = list(src.inflate_split())
         size = os.path.getsize(bam)
         src.close()
         barrier()
         return {"value": genomic / dt, "unit": "bases/s", "ms_per_step": dt * 1e3, "steps": steps, "regions": len(iv) * replicas,
                 "genomic_bases": genomic, "candidates": n_cand, "bam_bytes": size, "batch_regions": args.group_regions,
-                "inflate": "host zlib thread pool" if args.host_inflate else "GPU (k_bgzf_inflate, warp per BGZF block)",
-                "last_group_fetch_ms": ft, "rank0_phase_ms": phase, "h2d_bytes_per_step": int(size * replicas),
+                "inflate": "host zlib thread pool" if args.host_inflate else "GPU (k_bgzf_inflate, warp per BGZF block)" + (" + host pool on %.2f of the blocks" % args.inflate_host_share if args.inflate_host_share else ""),
+                "inflate_blocks_host_device_rank0": split, "last_group_fetch_ms": ft, "rank0_phase_ms": phase, "h2d_bytes_per_step": int(size * replicas),
                 "d2h_bytes_per_step": int(n_cand * RECORD_BYTES), "gen_seconds": round(gen_s, 1),
                 "api": "pepper_b200.dist.DistributedVariantCaller.run(frontend.VariantFileSource) -> pb_bam_fetch_device + pb_get_reads_* + "
                        "pb_variant_stream_* per claimed group; GatherBuffer.to_host() on the writer rank"}
@@ -874,6 +878,8 @@ def main():
     ap.add_argument("--files-batch", type=int, default=32, help="regions per batch of the from-files streaming session")
     ap.add_argument("--files-dist", action="store_true", help="N=1: run the from-files leg through DistributedVariantCaller + VariantFileSource "
                                                              "(the N>1 path) instead of VariantFromFiles.call_stream")
+    ap.add_argument("--inflate-host-share", type=float, default=None,
+                    help="from-files leg: share of the BGZF blocks inflated by the host pool beside the kernel (default 0: all on the GPU)")
     ap.add_argument("--host-inflate", action="store_true", help="from-files leg with the host zlib pool instead of the GPU inflate")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -210,6 +210,13 @@ int pb_bam_io_stats(pb_bam_t *b, int64_t *compressed_bytes, int64_t *inflated_by
 int pb_bam_fetch_device(pb_bam_t *bam, int tid, int64_t beg, int64_t end, int device, pb_records_t *view, void *stream);
 /* device time (ms) of the last pb_bam_fetch_device: [H2D + inflate, record chains + parse, scatter] */
 int pb_bam_fetch_device_timings(pb_bam_t *bam, float *ms3);
+/* Hybrid inflate of pb_bam_fetch_device: `share` (0..1) of the BGZF blocks — runs of 16 consecutive blocks — is inflated by the
+ * reader's host thread pool (zlib) WHILE the kernel inflates the rest; the host runs reach the same device buffer through a copy
+ * stream, and the record kernels wait for both.  Default 0 (everything on the GPU); the environment variable
+ * PB_INFLATE_HOST_SHARE overrides the default.  The records are identical for every share. */
+int pb_bam_set_host_share(pb_bam_t *bam, double share);
+/* blocks inflated by the host pool / by the kernel over all pb_bam_fetch_device calls of this reader */
+int pb_bam_inflate_split(pb_bam_t *bam, int64_t *host_blocks, int64_t *device_blocks);
 /* diagnostics: raw DEFLATE streams inflated by the GPU kernel (outputs concatenated; h_status[i] != 0 = rejected stream) */
 int pb_inflate_blocks_host(const uint8_t *h_comp, int64_t comp_bytes, const int64_t *h_in_off, const int32_t *h_in_len,
                            const int32_t *h_out_len, int64_t n_blocks, uint8_t *h_out, int32_t *h_status, void *stream);

@@ -28,6 +28,8 @@ def _bind(L):
     L.pb_bam_io_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pb_bam_fetch_device.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.POINTER(PbRecords), C.c_void_p]
     L.pb_bam_fetch_device_timings.argtypes = [C.c_void_p, C.c_void_p]
+    L.pb_bam_set_host_share.argtypes = [C.c_void_p, C.c_double]
+    L.pb_bam_inflate_split.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pb_inflate_blocks_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pb_fasta_open.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
     L.pb_fasta_close.argtypes = [C.c_void_p]
@@ -184,6 +186,16 @@ class BamReader:
         ms = (C.c_float * 3)()
         self.L.pb_bam_fetch_device_timings(self.h, ms)
         return dict(inflate_ms=float(ms[0]), chain_parse_ms=float(ms[1]), scatter_ms=float(ms[2]))
+
+    def set_host_share(self, share: float) -> None:
+        """Share (0..1) of the BGZF blocks fetch_device leaves to the host zlib pool while the kernel inflates the rest."""
+        _lib.check(self.L.pb_bam_set_host_share(self.h, float(share)), "pb_bam_set_host_share")
+
+    def inflate_split(self) -> tuple[int, int]:
+        """(blocks inflated by the host pool, blocks inflated by the kernel) over all fetch_device calls."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.L.pb_bam_inflate_split(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
     def io_stats(self) -> tuple[int, int]:
         a, b = C.c_int64(0), C.c_int64(0)

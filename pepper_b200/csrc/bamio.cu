@@ -14,6 +14,7 @@
 #include "bgzf_inflate.cuh"
 #include <zlib.h>
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -213,7 +214,33 @@ struct pb_bam {
     cudaStream_t own_stream = nullptr;
     float dev_ms[3] = {0, 0, 0};        // inflate, chain + parse, scatter
     cudaEvent_t dev_evt[4] = {nullptr, nullptr, nullptr, nullptr};
+    // hybrid inflate: a share of the BGZF blocks (runs of HOST_RUN consecutive blocks) is inflated by the host pool while the
+    // kernel works on the rest, and lands in the same device buffer through a copy stream
+    double host_share = 0.0;
+    HostBuf u_host;                     // page-locked staging of the host-inflated runs
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_evt = nullptr;
+    int64_t n_host_blocks = 0, n_dev_blocks = 0;
 };
+
+// cores this process may really use: scheduler affinity capped by the cgroup CPU quota (a container that shows 128 hardware
+// threads may be allowed 16)
+static int usable_cores() {
+    int n = (int) std::max(1u, std::thread::hardware_concurrency());
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int c = CPU_COUNT(&set); if (c > 0) n = std::min(n, c); }
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64] = {0}; long long period = 0;
+        if (fscanf(f, "%63s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+            const long long quota = atoll(q);
+            if (quota > 0) n = (int) std::max(1ll, std::min<long long>(n, quota / period));
+        }
+        fclose(f);
+    }
+    return n;
+}
+constexpr size_t HOST_RUN = 16;
 
 struct pb_fasta {
     MappedFile f;
@@ -346,8 +373,13 @@ extern "C" int pb_bam_open(pb_bam_t **out, const char *path, int n_threads) {
     if (!out || !path) { set_error("null argument"); return PB_ERR_ARG; }
     auto *b = new pb_bam();
     if (!b->f.open(path)) { delete b; set_error("cannot open BAM file %s", path); return PB_ERR_ARG; }
-    b->n_threads = n_threads > 0 ? n_threads : (int) std::max(1u, std::thread::hardware_concurrency());
+    b->n_threads = n_threads > 0 ? n_threads : usable_cores();
     b->pool = new Pool(b->n_threads - 1);
+    // share of the blocks left to the host pool in pb_bam_fetch_device: off by default (measured on the chr20-scale files leg: a
+    // third of the blocks on 16 cores = 846 ms per step against 862 ms — the fetch thread's pread -> zlib chain takes what the kernel
+    // saves); PB_INFLATE_HOST_SHARE or pb_bam_set_host_share turn it on
+    b->host_share = 0.0;
+    if (const char *e = getenv("PB_INFLATE_HOST_SHARE")) b->host_share = std::min(1.0, std::max(0.0, atof(e)));
     int ndev = 0;
     b->pinned = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
     if (!b->pinned) cudaGetLastError();
@@ -372,6 +404,9 @@ extern "C" int pb_bam_close(pb_bam_t *b) {
     HostBuf *bufs[] = {&b->o_pos, &b->o_seq_off, &b->o_cigar_off, &b->o_flag, &b->o_mapq, &b->o_seq, &b->o_qual, &b->o_cigar};
     for (auto *x : bufs) x->release();
     b->c_host.release();
+    b->u_host.release();
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    if (b->copy_evt) cudaEventDestroy(b->copy_evt);
     pb::DevBuf *dbufs[] = {&b->d_comp, &b->d_blocks, &b->d_status, &b->d_ubuf, &b->d_starts, &b->d_stops, &b->d_counts, &b->d_base, &b->d_rec_off, &b->d_info,
                            &b->d_keep32, &b->d_lseq32, &b->d_ncig32, &b->d_keep_off, &b->d_so, &b->d_co, &b->d_scal, &b->d_pos, &b->d_seq_off, &b->d_cigar_off,
                            &b->d_flag, &b->d_mapq, &b->d_seq, &b->d_qual, &b->d_cigar};
@@ -733,23 +768,60 @@ extern "C" int pb_bam_fetch_device(pb_bam_t *b, int tid, int64_t beg, int64_t en
         for (size_t i = 0; i < s.size(); i++) { starts.push_back(s[i]); stops.push_back(i + 1 < s.size() ? s[i + 1] : limit); }
     }
     const int n_starts = (int) starts.size();
-    // ---- device: copy, inflate
-    std::vector<BlockDesc> desc((size_t) n_blocks);
+    // ---- device: copy, inflate.  Runs of HOST_RUN consecutive blocks alternate between the kernel and the host pool in the
+    //      ratio host_share; a host run lands at its place in the inflated device buffer through the copy stream
+    const int host_of_16 = (int) (b->host_share * 16.0 + 0.5);
+    auto on_host = [&](int64_t i) { return (int) ((i / (int64_t) HOST_RUN) % 16) < host_of_16 && blocks[i].isize > 0; };
+    std::vector<BlockDesc> desc;
+    std::vector<int64_t> dev_block;                             // index of the block each descriptor stands for
+    std::vector<int64_t> host_block;
+    std::vector<size_t> host_off;                               // offset of the host block in the staging buffer
+    size_t htotal = 0;
+    desc.reserve((size_t) n_blocks); dev_block.reserve((size_t) n_blocks);
     for (int64_t i = 0; i < n_blocks; i++) {
         const Block &k = blocks[i];
-        desc[i] = {(int64_t) (block_in_off[i] + k.data_off), (int32_t) (k.bsize - k.data_off - 8), (int32_t) k.isize, (int64_t) k.uoff};
         b->n_compressed += (int64_t) k.bsize; b->n_inflated += k.isize;
+        if (on_host(i)) { host_block.push_back(i); host_off.push_back(htotal); htotal += k.isize; continue; }
+        desc.push_back({(int64_t) (block_in_off[i] + k.data_off), (int32_t) (k.bsize - k.data_off - 8), (int32_t) k.isize, (int64_t) k.uoff});
+        dev_block.push_back(i);
     }
+    const int64_t n_dev = (int64_t) desc.size(), n_host = (int64_t) host_block.size();
+    b->n_dev_blocks += n_dev; b->n_host_blocks += n_host;
     PB_CUDA(cudaEventRecord(b->dev_evt[0], st));
     PB_TRY(upload(b->d_comp, b->c_host.p, ctotal + 16, st));
-    PB_TRY(upload(b->d_blocks, desc.data(), sizeof(BlockDesc) * n_blocks, st));
     PB_TRY(b->d_status.reserve(sizeof(int) * (n_blocks + 4)));
     PB_TRY(b->d_ubuf.reserve(utotal + 64));
     PB_TRY(b->d_scal.reserve(sizeof(int64_t) * 8));
     PB_CUDA(cudaMemsetAsync(b->d_scal.p, 0, sizeof(int64_t) * 8, st));
     int64_t *sc = b->d_scal.as<int64_t>();                      // [0] n_rec [1] n_keep [2] n_bases [3] n_cigar [4] err (int)
     int *d_err = reinterpret_cast<int *>(sc + 4);
-    PB_TRY(launch_inflate(b->d_comp.as<uint8_t>(), b->d_blocks.as<BlockDesc>(), n_blocks, b->d_ubuf.as<uint8_t>(), b->d_status.as<int>(), st));
+    if (n_dev > 0) {
+        PB_TRY(upload(b->d_blocks, desc.data(), sizeof(BlockDesc) * n_dev, st));
+        PB_TRY(launch_inflate(b->d_comp.as<uint8_t>(), b->d_blocks.as<BlockDesc>(), n_dev, b->d_ubuf.as<uint8_t>(), b->d_status.as<int>(), st));
+    }
+    if (n_host > 0) {                                           // while the kernel runs: zlib on the pool, straight from the staged bytes
+        if (!b->u_host.reserve(htotal + 64, true)) { set_error("out of host memory"); return PB_ERR_ARG; }
+        if (!b->copy_stream) PB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+        if (!b->copy_evt) PB_CUDA(cudaEventCreateWithFlags(&b->copy_evt, cudaEventDisableTiming));
+        const uint8_t *cb = b->c_host.as<uint8_t>();
+        uint8_t *ub = b->u_host.as<uint8_t>();
+        std::atomic<int> bad(0);
+        b->pool->run((size_t) n_host, [&](size_t j) {
+            const Block &k = blocks[host_block[j]];
+            if (!inflate_block(cb + block_in_off[host_block[j]] + k.data_off, k.bsize - k.data_off - 8, ub + host_off[j], k.isize)) bad = 1;
+        });
+        if (bad) { cudaStreamSynchronize(st); set_error("BGZF inflate failed"); return PB_ERR_ARG; }
+        for (int64_t j = 0; j < n_host;) {                      // one copy per run of blocks adjacent in the inflated buffer
+            int64_t e = j + 1;
+            size_t len = blocks[host_block[j]].isize;
+            while (e < n_host && host_block[e] == host_block[e - 1] + 1 &&
+                   blocks[host_block[e]].uoff == blocks[host_block[e - 1]].uoff + blocks[host_block[e - 1]].isize) { len += blocks[host_block[e]].isize; e++; }
+            PB_CUDA(cudaMemcpyAsync(b->d_ubuf.as<uint8_t>() + blocks[host_block[j]].uoff, ub + host_off[j], len, cudaMemcpyHostToDevice, b->copy_stream));
+            j = e;
+        }
+        PB_CUDA(cudaEventRecord(b->copy_evt, b->copy_stream));
+        PB_CUDA(cudaStreamWaitEvent(st, b->copy_evt, 0));
+    }
     PB_CUDA(cudaEventRecord(b->dev_evt[1], st));
     // ---- record chains
     int64_t n_rec = 0;
@@ -762,13 +834,13 @@ extern "C" int pb_bam_fetch_device(pb_bam_t *b, int tid, int64_t beg, int64_t en
                                                                        b->d_counts.as<int32_t>(), nullptr, nullptr, d_err);
         k_scan_excl<<<1, 1024, 0, st>>>(b->d_counts.as<int32_t>(), b->d_base.as<int64_t>(), n_starts, sc + 0);
     }
-    std::vector<int> h_status((size_t) n_blocks);
+    std::vector<int> h_status((size_t) n_dev + 1);
     int64_t h_sc[5] = {0, 0, 0, 0, 0};
-    PB_CUDA(cudaMemcpyAsync(h_status.data(), b->d_status.p, sizeof(int) * n_blocks, cudaMemcpyDeviceToHost, st));
+    if (n_dev > 0) PB_CUDA(cudaMemcpyAsync(h_status.data(), b->d_status.p, sizeof(int) * n_dev, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
-    for (int64_t i = 0; i < n_blocks; i++)
-        if (h_status[i]) { set_error("BGZF inflate failed on the GPU: block at file offset %zu, status %d", blocks[i].coff, h_status[i]); return PB_ERR_ARG; }
+    for (int64_t i = 0; i < n_dev; i++)
+        if (h_status[i]) { set_error("BGZF inflate failed on the GPU: block at file offset %zu, status %d", blocks[dev_block[i]].coff, h_status[i]); return PB_ERR_ARG; }
     if ((int) h_sc[4]) { set_error("BAM record chain is inconsistent with the index (code %d)", (int) h_sc[4]); return PB_ERR_ARG; }
     n_rec = h_sc[0];
     int64_t n_keep = 0, nb = 0, nc = 0;
@@ -821,6 +893,21 @@ extern "C" int pb_bam_fetch_device(pb_bam_t *b, int tid, int64_t beg, int64_t en
 extern "C" int pb_bam_fetch_device_timings(pb_bam_t *b, float *ms3) {
     if (!b || !ms3) return PB_ERR_ARG;
     for (int i = 0; i < 3; i++) ms3[i] = b->dev_ms[i];
+    return PB_OK;
+}
+
+// share of the BGZF blocks pb_bam_fetch_device leaves to the host pool (0 = all on the GPU — the default —, 1 = all on the host;
+// env PB_INFLATE_HOST_SHARE overrides the default)
+extern "C" int pb_bam_set_host_share(pb_bam_t *b, double share) {
+    if (!b || !(share >= 0.0 && share <= 1.0)) { set_error("host share must be in [0, 1]"); return PB_ERR_ARG; }
+    b->host_share = share;
+    return PB_OK;
+}
+// blocks inflated by the host pool / by the kernel in all pb_bam_fetch_device calls so far
+extern "C" int pb_bam_inflate_split(pb_bam_t *b, int64_t *host_blocks, int64_t *device_blocks) {
+    if (!b) return PB_ERR_ARG;
+    if (host_blocks) *host_blocks = b->n_host_blocks;
+    if (device_blocks) *device_blocks = b->n_dev_blocks;
     return PB_OK;
 }
 

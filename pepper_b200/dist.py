@@ -322,7 +322,9 @@ class DistributedVariantCaller:
         s = self.caller.stream(params, self.buffer.capacity, d_records=self.buffer.my_ptr())
         depth = 1                                 # groups claimed ahead of the one being run
         if from_files:
-            depth = 2                             # the fetch (read + H2D + inflate) of a group gets a whole group period on the helper thread
+            from .frontend import FETCH_READERS
+            depth = FETCH_READERS                 # fetches (pread + H2D + inflate) outstanding beside the group being run: one per reader of
+                                                  # the source's rotation (the reader of the group just taken is free again)
 
             def stage(j):
                 rep, g0, g1 = job[j]

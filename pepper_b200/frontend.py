@@ -20,6 +20,11 @@ from .synth import RegionTable
 REGION_SAFE_BASES = 100              # ConsensCandidateFinder.REGION_SAFE_BASES (pepper_variant Options.py:2)
 MIN_IMAGE_OVERLAP = 100              # ImageSizeOptions.MIN_IMAGE_OVERLAP (pepper Options.py:10)
 VARIANT_MAX_READS = 5000             # AlingerOptions.MAX_READS_IN_REGION (pepper_variant Options.py:98)
+# BAM fetches in flight in the streaming calls, and readers in rotation (FETCH_WORKERS being filled + the one whose records are
+# being trimmed).  Measured on the chr20-scale files leg: 2 workers / 3 readers = 988 ms per step against 862 ms with 1 / 2 — the GPU
+# is the bottleneck of that path, and two inflate kernels beside the network only slow the network down.
+FETCH_WORKERS = 1
+FETCH_READERS = 2
 POLISH_MAX_READS = 1500              # AlingerOptions.MAX_READS_IN_REGION (pepper Options.py:28)
 
 
@@ -38,21 +43,44 @@ class _FromFiles:
     """`gpu_inflate` (default): BGZF inflate, record walk and parse run on the GPU (pb_bam_fetch_device; only compressed blocks
     cross PCIe); False = the host thread-pool zlib path (pb_bam_fetch)."""
 
-    def __init__(self, bam_path: str, fasta_path: str, device: int = 0, threads: int = 0, gpu_inflate: bool = True):
+    def __init__(self, bam_path: str, fasta_path: str, device: int = 0, threads: int = 0, gpu_inflate: bool = True,
+                 host_share: float | None = None):
         self.gpu_inflate = gpu_inflate
-        self.bam = BamReader(bam_path, threads)
+        self.host_share = host_share          # None = the reader's default (pb_bam_set_host_share)
+        self.threads = threads
+        self.bam = self._open_bam(bam_path)
         self.fasta = FastaReader(fasta_path)
         self.trimmer = ReadTrimmer(device)
         self.device = device
-        self._bam2 = None
+        self._extra = []                      # further readers of the same file (one per fetch in flight)
+
+    def _open_bam(self, path: str) -> BamReader:
+        r = BamReader(path, self.threads)
+        if self.host_share is not None:
+            r.set_host_share(self.host_share)
+        return r
+
+    def _readers(self, n: int) -> list:
+        """`n` readers of the BAM (each owns the host / device buffers of one fetch in flight)."""
+        while 1 + len(self._extra) < n:
+            self._extra.append(self._open_bam(self.bam.path))
+        return [self.bam] + self._extra[:n - 1]
+
+    @property
+    def _bam2(self):
+        return self._extra[0] if self._extra else None
+
+    def inflate_split(self) -> tuple[int, int]:
+        """(BGZF blocks inflated by the host pools, by the kernel) over all readers."""
+        parts = [r.inflate_split() for r in [self.bam] + self._extra if r is not None]
+        return sum(a for a, _ in parts), sum(b for _, b in parts)
 
     def close(self):
-        """Releases the file readers (the second reader of call_batches included) and the trimmer."""
-        for name in ("bam", "_bam2"):
-            r = getattr(self, name, None)
+        """Releases the file readers (the extra readers of the streaming calls included) and the trimmer."""
+        for r in [getattr(self, "bam", None)] + list(getattr(self, "_extra", [])):
             if r is not None and hasattr(r, "close"):
                 r.close()
-            setattr(self, name, None)
+        self.bam, self._extra = None, []
         if getattr(self, "trimmer", None) is not None:
             self.trimmer.close()
             self.trimmer = None
@@ -111,8 +139,9 @@ class _FromFiles:
 class VariantFromFiles(_FromFiles):
     """call_variant's make_images + run_inference for a list of intervals of one contig."""
 
-    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0, gpu_inflate: bool = True):
-        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate)
+    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0, gpu_inflate: bool = True,
+                 host_share: float | None = None):
+        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate, host_share)
         self.caller = VariantCaller(state, device)
 
     def call(self, contig: str, intervals: list[tuple[int, int]], params: dict, include_supplementary: bool = False,
@@ -173,9 +202,7 @@ class VariantFromFiles(_FromFiles):
         """Streaming form: yields (VariantCalls, RegionTable) per batch of `batch` intervals while a helper thread inflates the next
         batch's BAM span with a second reader (pb_bam_fetch runs outside the GIL), so the host inflate overlaps the GPU work."""
         from concurrent.futures import ThreadPoolExecutor
-        if self._bam2 is None:
-            self._bam2 = BamReader(self.bam.path, 0)
-        readers = [self.bam, self._bam2]
+        readers = self._readers(2)
         groups = [intervals[i:i + batch] for i in range(0, len(intervals), batch)]
 
         def span(g):
@@ -203,13 +230,11 @@ class VariantFromFiles(_FromFiles):
         from concurrent.futures import ThreadPoolExecutor
         if not intervals:
             raise ValueError("no intervals")
-        if self._bam2 is None:
-            self._bam2 = BamReader(self.bam.path, 0)
-        readers = [self.bam, self._bam2]
+        readers = self._readers(FETCH_READERS)
         groups = [intervals[i:i + batch] for i in range(0, len(intervals), batch)]
 
         def prefetch(k):
-            return self._fetch(readers[k & 1], contig, *self._group_span(groups[k]))
+            return self._fetch(readers[k % FETCH_READERS], contig, *self._group_span(groups[k]))
         import time
         cap = capacity or max(4096, int(sum(e - s + 1 for s, e in intervals)) // 30)
         prof = dict(wait_fetch=0.0, ref_table=0.0, get_reads=0.0, stage=0.0, run=0.0, sync=0.0, end_fetch=0.0, fetch_thread=0.0)
@@ -225,14 +250,20 @@ class VariantFromFiles(_FromFiles):
         while True:
             s = self.caller.stream(params, cap)
             try:
-                with ThreadPoolExecutor(max_workers=1) as pool:
-                    fut = pool.submit(timed_prefetch, 0)
-                    t0 = time.perf_counter()
-                    view = fut.result()
-                    prof["wait_fetch"] += time.perf_counter() - t0
-                    if len(groups) > 1:
-                        fut = pool.submit(timed_prefetch, 1)
-                    nxt = trim(view, groups[0])
+                with ThreadPoolExecutor(max_workers=FETCH_WORKERS) as pool:
+                    # FETCH_WORKERS fetches run at once (the pread of one batch beside the inflate of another), each on its own
+                    # reader; batch j + FETCH_READERS is requested on the reader of batch j as soon as j's records are trimmed
+                    futs = {k: pool.submit(timed_prefetch, k) for k in range(min(FETCH_READERS, len(groups)))}
+
+                    def take(k):
+                        t0 = time.perf_counter()
+                        view = futs.pop(k).result()
+                        prof["wait_fetch"] += time.perf_counter() - t0
+                        fetched = trim(view, groups[k])
+                        if k + FETCH_READERS < len(groups):
+                            futs[k + FETCH_READERS] = pool.submit(timed_prefetch, k + FETCH_READERS)
+                        return fetched
+                    nxt = take(0)
                     done = 0
                     for k, g in enumerate(groups):
                         fetched = nxt
@@ -242,12 +273,7 @@ class VariantFromFiles(_FromFiles):
                         s.run(flush=False)                 # encoder done (host-synchronous), network of this batch queued
                         t5 = time.perf_counter()
                         if k + 1 < len(groups):            # while that network runs: the next batch's records -> trimmed reads
-                            view = fut.result()
-                            t6 = time.perf_counter()
-                            prof["wait_fetch"] += t6 - t5
-                            if k + 2 < len(groups):
-                                fut = pool.submit(timed_prefetch, k + 2)
-                            nxt = trim(view, groups[k + 1])
+                            nxt = take(k + 1)
                         # no sync: run(k+1) builds its tables while network(k) runs; its encoder synchronises the stream before the
                         # trimmer's buffers (consumed by encoder(k+1)) are overwritten by the trim of batch k+2
                         prof["stage"] += t4 - t3; prof["run"] += t5 - t4
@@ -268,19 +294,20 @@ class VariantFileSource(_FromFiles):
     """The read source of dist.DistributedVariantCaller for a job given as FILES: every rank opens the same coordinate-sorted BAM
     (+ .bai) and FASTA and turns the interval groups it claims into trimmed device reads (GPU inflate -> record parse -> batched
     get_reads), so that make_images + run_inference of one contig shard over the ranks from the alignment file itself — no rank
-    reads, inflates or copies a block outside the groups it runs.  `request(key, g0, g1)` starts the fetch of intervals[g0:g1] on the
-    helper thread (two readers alternate, so the records of the group being trimmed stay valid while the next span is inflated);
-    `take(key, g0, g1)` waits for it and returns the FetchedReads of that group."""
+    reads, inflates or copies a block outside the groups it runs.  `request(key, g0, g1)` starts the fetch of intervals[g0:g1] on a
+    helper thread (FETCH_WORKERS fetches at once, FETCH_READERS readers in rotation, so the records of the group being trimmed stay
+    valid while later spans are read and inflated — the caller keeps at most FETCH_READERS requests outstanding and takes them in
+    request order); `take(key, g0, g1)` waits for it and returns the FetchedReads of that group."""
 
     def __init__(self, bam_path: str, fasta_path: str, contig: str, intervals: list[tuple[int, int]], min_snp_baseq: int,
                  device: int = 0, threads: int = 0, gpu_inflate: bool = True, include_supplementary: bool = False, min_mapq: int = 0,
-                 downsample_rate: float = 1.0, max_reads: int = VARIANT_MAX_READS):
+                 downsample_rate: float = 1.0, max_reads: int = VARIANT_MAX_READS, host_share: float | None = None):
         from concurrent.futures import ThreadPoolExecutor
-        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate)
-        self._bam2 = BamReader(bam_path, 0)
+        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate, host_share)
+        self._ring = self._readers(FETCH_READERS)
         self.contig, self.intervals = contig, list(intervals)
         self._filters = (int(min_snp_baseq), include_supplementary, min_mapq, max_reads, downsample_rate)
-        self._pool = ThreadPoolExecutor(max_workers=1)
+        self._pool = ThreadPoolExecutor(max_workers=FETCH_WORKERS)
         self._futs, self._issued = {}, 0
 
     @property
@@ -292,7 +319,7 @@ class VariantFileSource(_FromFiles):
         return np.array([e - s + 1 for s, e in self.intervals], dtype=np.int64)
 
     def request(self, key, g0: int, g1: int) -> None:
-        reader = (self.bam, self._bam2)[self._issued & 1]
+        reader = self._ring[self._issued % FETCH_READERS]
         self._issued += 1
         self._futs[key] = self._pool.submit(self._fetch, reader, self.contig, *self._group_span(self.intervals[g0:g1]))
 
@@ -310,8 +337,9 @@ class VariantFileSource(_FromFiles):
 class PolishFromFiles(_FromFiles):
     """polish's make_images (with read realignment) + call_consensus for a list of regions of one contig."""
 
-    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0, gpu_inflate: bool = True):
-        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate)
+    def __init__(self, bam_path: str, fasta_path: str, state: dict, device: int = 0, threads: int = 0, gpu_inflate: bool = True,
+                 host_share: float | None = None):
+        super().__init__(bam_path, fasta_path, device, threads, gpu_inflate, host_share)
         self.caller = PolishCaller(state, device)
         self.realigner = Realigner(device)
 

@@ -225,7 +225,7 @@ def test_corrupt_files_are_rejected_not_followed(tmp_path):
 
 
 def test_from_files_close_releases_readers(tmp_path):
-    """the second reader opened by the streaming calls is closed with the object."""
+    """every extra reader opened by the streaming calls is closed with the object."""
     from pepper_b200.frontend import _FromFiles
     rec, genome = synth.simulate_contig_records(5000, 5, synth.ONT, 6)
     bam, fa = str(tmp_path / "f.bam"), str(tmp_path / "f.fa")
@@ -235,13 +235,15 @@ def test_from_files_close_releases_readers(tmp_path):
     class Probe(_FromFiles):                                # no GPU in this test: skip the trimmer
         def __init__(self):
             from pepper_b200.bamio import BamReader, FastaReader
-            self.gpu_inflate = False
+            self.gpu_inflate, self.host_share, self.threads = False, None, 1
             self.bam = BamReader(bam, 1)
             self.fasta = FastaReader(fa)
             self.trimmer = None
             self.device = 0
-            self._bam2 = BamReader(bam, 1)
+            self._extra = []
     p = Probe()
-    b1, b2 = p.bam, p._bam2
+    ring = p._readers(3)                                    # what the streaming calls open: the first reader + two more
+    assert len(ring) == 3 and ring[0] is p.bam and p._bam2 is ring[1]
+    assert p._readers(2) == ring[:2] and len(p._extra) == 2
     p.close()
-    assert not b1.h and not b2.h and p.bam is None and p._bam2 is None
+    assert all(not r.h for r in ring) and p.bam is None and p._bam2 is None and p._extra == []

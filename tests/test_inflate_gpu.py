@@ -86,10 +86,14 @@ def _same(a, b):
         assert np.array_equal(getattr(a, f), getattr(b, f)), f
 
 
-def test_fetch_device_equals_host_fetch(bam_file):
+@pytest.mark.parametrize("share", [0.0, 0.07, 0.33, 1.0])
+def test_fetch_device_equals_host_fetch(bam_file, share):
+    """`share` of the BGZF blocks (runs of 16) is inflated by the host pool beside the kernel (pb_bam_set_host_share): the records do
+    not depend on it."""
     from pepper_b200.bamio import BamReader
     path, L = bam_file
     r = BamReader(path, 4)
+    r.set_host_share(share)
     windows = [("ctgA", 0, L), ("ctgA", 40_000, 41_000), ("ctgA", 16_384, 32_768), ("ctgA", 99_000, 200_000), ("ctgA", 5, 6),
                ("ctgB", 0, 30_000), ("ctgB", 10_000, 20_000), ("ctgB", 29_990, 40_000)]
     for contig, a, b in windows:
@@ -100,6 +104,12 @@ def test_fetch_device_equals_host_fetch(bam_file):
     assert r.fetch("ctgA", 0, L).n_records > 200
     t = r.fetch_device_timings()
     assert t["inflate_ms"] > 0
+    on_host, on_device = r.inflate_split()
+    assert (on_host == 0) == (share == 0.0) and on_host + on_device > 20
+    if share == 1.0:
+        assert on_host > on_device            # (empty blocks — the EOF marker — stay with the kernel)
+    with pytest.raises(Exception):
+        r.set_host_share(1.5)
     r.close()
 
 
