@@ -323,15 +323,17 @@ def run_variant(args, cfg):
                     achieved=tf, peak=sustained, unit="TFLOP/s", frac=tf / sustained,
                     traffic=int(mine["candidates"] * TRAFFIC_PER_CAND), traffic_note=TRAFFIC_NOTE_NET,
                     peak_source=peaks["source"] + ", sustained bf16", flops=mine["candidates"] * FLOP_PER_CAND, launches_ms=net_s * 1e3,
-                    executed_tflops=PRODUCTS * tf, executed_frac=PRODUCTS * tf / sustained,
-                    note="achieved = fp32-equivalent algorithmic FLOPs (161.4 MFLOP per candidate) / network time of rank 0; every FLOP "
-                         "runs as %d 16-bit tensor-core products (hi/lo operand split, fp32 accumulate), so the tensor pipe runs at "
-                         "executed_frac; the step runs under the board power cap (clocks.reasons)" % PRODUCTS)
+                    executed_tflops=PRODUCTS_VARIANT * tf, executed_frac=PRODUCTS_VARIANT * tf / sustained,
+                    products_per_flop={k: p for k, (_, p) in VARIANT_GEMMS.items()},
+                    note="achieved = fp32-equivalent algorithmic FLOPs (161.4 MFLOP per candidate) / network time of rank 0; a FLOP "
+                         "runs as 2 or 3 16-bit tensor-core products (hi/lo operand split, fp32 accumulate; products_per_flop, %.2f on "
+                         "average), so the tensor pipe runs at executed_frac; the step runs under the board power cap (clocks.reasons)"
+                         % PRODUCTS_VARIANT)
 
     line = {
         "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-        "dtype": "int32 counts / int8 images (encoder); networks f32-equivalent (%s hi/lo split x%d on tcgen05, fp32 accumulate)" % (OPERAND, PRODUCTS),
+        "dtype": "int32 counts / int8 images (encoder); networks f32-equivalent (%s hi/lo split, 2-3 products per GEMM on tcgen05, fp32 accumulate)" % OPERAND,
         "data": "synthetic",
         "config": {"workload": cfg["workload"], "name": args.config, "regions_per_gpu": regions.n_regions if not strong else None,
                    "job_regions": regions.n_regions * replicas, "region_size": args.region_size, "coverage": args.coverage,
@@ -530,8 +532,13 @@ def files_leg_dist(args, cfg, local, dvc, world, rank, barrier, replicas):
 
 
 # figures carried over from the ncu --set full captures under profiles/ (per candidate / per algorithmic byte)
-PRODUCTS = 3
+PRODUCTS = 3                      # polish network: three 16-bit products per fp32-equivalent FLOP everywhere
 OPERAND = "fp16"
+# variant network, FLOP per candidate by GEMM (2 directions x 33 steps; hidden 256, gates 1,024; head 16,896 -> 512 -> 4 x 512 -> 3)
+# and the 16-bit tensor-core products each one executes per FLOP (handles.cuh lo_mask 0x1a): int8 images are exact in one operand,
+# the recurrent GEMMs pass the parity gate with two products, the decoder's x-part and the head need three
+VARIANT_GEMMS = {"encoder_x": (3.51e6, 2), "encoder_h": (34.6e6, 2), "decoder_x": (69.2e6, 3), "decoder_h": (34.6e6, 2), "head": (19.4e6, 3)}
+PRODUCTS_VARIANT = sum(f * p for f, p in VARIANT_GEMMS.values()) / sum(f for f, _ in VARIANT_GEMMS.values())     # 2.55
 TRAFFIC_RATIO_COUNT = 1.60
 TRAFFIC_NOTE_COUNT = ("dram__bytes_read+write of k_tile_count = 1.60 x algorithmic bytes in the ncu --set full capture of one "
                       "32-region group (277.0 MB read + 102.7 MB written vs 237.6 MB, profiles/r2c_prof_k_tile_count_summary.txt: "

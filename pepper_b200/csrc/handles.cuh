@@ -15,8 +15,11 @@ struct TcVariant {
     TcLin lin[5];
     DevBuf img_op, yenc_hi, yenc_lo, ydec_hi, ydec_lo, c, act_hi[2], act_lo[2], final_f32;
     // which GEMMs execute the third (a_lo x w_hi) product: bit 0 encoder h-part, 1 decoder x-part, 2 decoder h-part, 3 linear_1,
-    // 4 linear_2..5.  0x1f = fp32-equivalent everywhere (default); clearing a bit runs that GEMM with two products.
-    int lo_mask = 0x1f;
+    // 4 linear_2..5; clearing a bit runs that GEMM with two products, 0x1f = three everywhere.  Default 0x1a: the recurrent
+    // (h-part) GEMMs of both LSTM layers run with two products — each passes the parity gate on its own (hidden states within
+    // 1e-3, class index exact outside the 1e-4 margin; DESIGN.md section 4 has the per-GEMM errors) — while the decoder's x-part
+    // and the MLP head, which fail it, keep three.
+    int lo_mask = 0x1a;
 };
 struct TcPolish {
     TcRnn enc[2], dec[2];

@@ -17,13 +17,16 @@ from pepper_b200 import weights  # noqa: E402
 from tests.test_nets_gpu import _variant_images, _polish_images  # noqa: E402
 
 out = {"variant": [], "polish": []}
-VN = {0x1f: "all x3 (default)", 0x1e: "encoder h x2", 0x1d: "decoder x x2", 0x1b: "decoder h x2", 0x17: "linear_1 x2", 0x0f: "linear_2-5 x2",
-      0x18: "both LSTM layers x2, head x3", 0x07: "head x2, LSTM x3", 0x00: "all x2"}
+VN = {0x1f: "all x3", 0x1e: "encoder h x2", 0x1d: "decoder x x2", 0x1b: "decoder h x2", 0x17: "linear_1 x2", 0x0f: "linear_2-5 x2",
+      0x1a: "encoder h + decoder h x2 (shipped default)", 0x18: "both LSTM layers x2, head x3", 0x07: "head x2, LSTM x3", 0x00: "all x2"}
+if len(sys.argv) > 1:                       # e.g. `exp_products.py 0x1f,0x1a`: only these variant masks, polish skipped
+    keep = {int(m, 0) for m in sys.argv[1].split(",")}
+    VN = {m: n for m, n in VN.items() if m in keep}
 big = _variant_images(9472 * 4, 11)
 tnet = VariantNet(weights.random_variant_state(0))
 for mask, name in VN.items():
     row = {"mask": mask, "what": name, "max_dh": 0.0, "max_dp": 0.0, "argmax_mismatch_outside_margin": 0, "n": 0}
-    for seed in (1, 2, 3):
+    for seed in (1, 2, 3, 4, 5, 6) if len(sys.argv) > 1 else (1, 2, 3):
         state = nets.make_variant_weights(seed)
         x = _variant_images(700, seed)
         want, whid = nets.variant_predict(state, x, threads=16, return_hidden=True)
@@ -47,6 +50,8 @@ for mask, name in VN.items():
     print(json.dumps(row), file=sys.stderr, flush=True)
 tnet.close()
 PN = {0x7: "all x3 (default)", 0x6: "encoder h x2", 0x5: "decoder x x2", 0x3: "decoder h x2", 0x0: "all x2"}
+if len(sys.argv) > 1:
+    PN = {}
 bigp = _polish_images(1184, 12)
 pnet = PolishNet(weights.random_polish_state(0))
 for mask, name in PN.items():
