@@ -372,8 +372,8 @@ int pb_variant_net_forward_records_device(pb_variant_net_t *net, const int8_t *d
 int pb_variant_net_forward_host(pb_variant_net_t *net, const int8_t *h_images,
                                 int64_t n, float *h_probs, float *h_hidden_dbg,
                                 void *stream);
-/* tensor-pipe precision of the dense GEMMs: 0 = fp32 FFMA (reference-exact
- * ordering), 1 = tcgen05 bf16x3 split (fp32-equivalent)                      */
+/* GEMM path: 0 = fp32 FFMA (reference-exact ordering), 1 = tcgen05 with the fp16 hi/lo operand split (2-3 products per GEMM,
+ * see pb_variant_net_set_lo_mask; default)                                                                                       */
 int pb_variant_net_set_mode(pb_variant_net_t *net, int mode);
 int pb_variant_net_launches(pb_variant_net_t *net, int64_t *n_launches);
 
@@ -400,13 +400,14 @@ int pb_polish_net_forward_host(pb_polish_net_t *net, const uint8_t *h_images,
                                int64_t n, uint8_t *h_bases, uint8_t *h_phred,
                                float *h_hidden_dbg, float *h_acc_dbg, void *stream);
 int pb_polish_net_launches(pb_polish_net_t *net, int64_t *n_launches);
-/* Precision experiments on the tcgen05 path: every GEMM runs as a_hi*w_hi + a_hi*w_lo (+ a_lo*w_hi); the mask says which GEMMs keep
- * the third product (default: all = fp32-equivalent).  variant bits: 0 encoder h, 1 decoder x, 2 decoder h, 3 linear_1,
- * 4 linear_2-5; polish bits: 0 encoder h, 1 decoder x, 2 decoder h.  Two-product GEMMs miss the argmax-outside-1e-4 gate
- * (DESIGN.md), so this is not a supported operating mode.                                                                   */
+/* Products per GEMM on the tcgen05 path: every GEMM runs as a_hi*w_hi + a_hi*w_lo (+ a_lo*w_hi); the mask says which GEMMs keep the
+ * third product.  variant bits: 0 encoder h-part, 1 decoder x-part, 2 decoder h-part, 3 linear_1, 4 linear_2-5 (default 0x1a: the
+ * two recurrent GEMMs, which pass the parity gate with two products, run with two; the decoder's x-part and the head keep three);
+ * polish bits: 0 encoder h, 1 decoder x, 2 decoder h (default 0x7: every polish GEMM needs three).  0x1f / 0x7 = three products
+ * everywhere; DESIGN.md section 4 holds the measured error of every choice.                                                     */
 int pb_variant_net_set_lo_mask(pb_variant_net_t *net, int mask);
 int pb_polish_net_set_lo_mask(pb_polish_net_t *net, int mask);
-/* 0 = fp32 FFMA GEMMs, 1 = tcgen05 bf16x3 GEMMs (fp32-equivalent) */
+/* 0 = fp32 FFMA GEMMs, 1 = tcgen05 GEMMs with the fp16 hi/lo operand split x3 (fp32-equivalent, default) */
 int pb_polish_net_set_mode(pb_polish_net_t *net, int mode);
 
 /* diagnostics: C[M][N] = A[M][K] W[N][K]^T + bias through the tcgen05 kernel (N % 256 == 0, K % 32 == 0) */

@@ -189,12 +189,13 @@ class VariantNet:
         return (probs, hid) if return_hidden else probs
 
     def set_mode(self, mode: int) -> None:
-        """0 = fp32 FFMA GEMMs, 1 = tcgen05 GEMMs with the 16-bit hi/lo operand split x3 (fp32-equivalent, default)."""
+        """0 = fp32 FFMA GEMMs, 1 = tcgen05 GEMMs with the 16-bit hi/lo operand split (2-3 products per GEMM, set_lo_mask; default)."""
         _lib.check(self.L.pb_variant_net_set_mode(self.h, mode), "pb_variant_net_set_mode")
 
     def set_lo_mask(self, mask: int) -> None:
-        """Experiments only (two-product variant): bit set = that GEMM keeps its third tensor-core product.
-        bits: 0 encoder h-part, 1 decoder x-part, 2 decoder h-part, 3 linear_1, 4 linear_2-5; default 0x1f."""
+        """Bit set = that GEMM keeps its third tensor-core product (a_lo x w_hi).  bits: 0 encoder h-part, 1 decoder x-part,
+        2 decoder h-part, 3 linear_1, 4 linear_2-5.  Default 0x1a: the recurrent GEMMs pass the parity gate with two products
+        (DESIGN.md section 4); 0x1f = three everywhere."""
         self.L.pb_variant_net_set_lo_mask.argtypes = [C.c_void_p, C.c_int]
         _lib.check(self.L.pb_variant_net_set_lo_mask(self.h, mask), "pb_variant_net_set_lo_mask")
 
