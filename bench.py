@@ -546,7 +546,9 @@ TRAFFIC_NOTE_COUNT = ("dram__bytes_read+write of k_tile_count = 1.60 x algorithm
 TRAFFIC_PER_CAND = 237.36e6 / 3840 + 767.39e6 / 3840 + 678.66e6 / 9472
 TRAFFIC_NOTE_NET = ("dram__bytes_read+write of the ncu --set full captures, per candidate: encoder LSTM layer (k_lstm_layer) 237.4 MB and "
                     "decoder LSTM layer 767.4 MB per launch over 3,840 candidates, linear_1 678.7 MB per launch over 9,472 "
-                    "(profiles/r1_prof_lstm_*_raw.csv, r1_prof_tcp_lin1_final_raw.csv), scaled to the candidates of this step")
+                    "(profiles/r1_prof_lstm_*_raw.csv, r1_prof_tcp_lin1_final_raw.csv), scaled to the candidates of this step; captured "
+                    "with three products in every GEMM — the shipped mask no longer reads the h_lo operand tiles of the recurrent "
+                    "GEMMs, so this is an upper bound")
 
 
 def verify_variant(args, cfg, reads, regions, records, replicas):
